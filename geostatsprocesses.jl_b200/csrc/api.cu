@@ -1,0 +1,203 @@
+// Context management, argument marshalling and the small standalone entry points of the C ABI.
+#include <cmath>
+#include <cstring>
+
+#include "chol.h"
+#include "cov.cuh"
+
+namespace gsp {
+
+long long g_launches = 0;
+
+int set_err(gsp_ctx* ctx, int code, const std::string& msg) {
+  if (ctx) ctx->err = msg;
+  return code;
+}
+
+int make_cov_dev(gsp_ctx* ctx, const gsp_cov_model* cov, int dim, int argpos, CovDev* out) {
+  if (!cov || !cov->structs) return set_err(ctx, -argpos, "covariance model is NULL");
+  if (cov->nstruct < 1 || cov->nstruct > GSP_MAX_STRUCTS) return set_err(ctx, -argpos, "nstruct must be in 1..GSP_MAX_STRUCTS");
+  std::memset(out, 0, sizeof(*out));
+  out->nstruct = cov->nstruct;
+  out->dim = dim;
+  for (int s = 0; s < cov->nstruct; ++s) {
+    const gsp_structure& st = cov->structs[s];
+    if (st.kind < GSP_NUGGET || st.kind > GSP_PENTASPHERICAL) return set_err(ctx, -argpos, "unknown structure kind");
+    if (!(st.sill >= 0.0)) return set_err(ctx, -argpos, "structure sill must be >= 0");
+    out->kind[s] = st.kind;
+    out->sill[s] = st.sill;
+    for (int i = 0; i < 9; ++i) {
+      if (!std::isfinite(st.A[i])) return set_err(ctx, -argpos, "structure metric is not finite");
+      out->A[s][i] = st.A[i];
+    }
+  }
+  return GSP_OK;
+}
+
+double cov_sill(const CovDev& m) {
+  double s = 0.0;
+  for (int i = 0; i < m.nstruct; ++i) s += m.sill[i];
+  return s;
+}
+
+// NOTE: for kind 0 the caller must replace out->coords by a device copy before launching kernels.
+int make_dom_dev(gsp_ctx* ctx, const gsp_domain* dom, int argpos, DomDev* out) {
+  if (!dom) return set_err(ctx, -argpos, "domain is NULL");
+  if (dom->dim < 1 || dom->dim > 3) return set_err(ctx, -argpos, "domain dim must be 1..3");
+  std::memset(out, 0, sizeof(*out));
+  out->kind = dom->kind;
+  out->dim = dom->dim;
+  if (dom->kind == 1) {
+    long long n = 1;
+    for (int a = 0; a < 3; ++a) {
+      out->dims[a] = a < dom->dim ? dom->dims[a] : 1;
+      out->origin[a] = a < dom->dim ? dom->origin[a] : 0.0;
+      out->spacing[a] = a < dom->dim ? dom->spacing[a] : 1.0;
+      if (out->dims[a] < 1) return set_err(ctx, -argpos, "grid extents must be >= 1");
+      if (a < dom->dim && !(out->spacing[a] > 0.0)) return set_err(ctx, -argpos, "grid spacing must be > 0");
+      n *= out->dims[a];
+    }
+    if (dom->nelems != 0 && dom->nelems != n) return set_err(ctx, -argpos, "nelems does not match prod(dims)");
+    out->nelems = n;
+  } else if (dom->kind == 0) {
+    if (dom->nelems < 1 || !dom->coords) return set_err(ctx, -argpos, "point domain needs coords and nelems >= 1");
+    out->nelems = dom->nelems;
+    out->coords = dom->coords;
+    for (int a = 0; a < 3; ++a) out->dims[a] = 1;
+  } else {
+    return set_err(ctx, -argpos, "domain kind must be 0 (points) or 1 (grid)");
+  }
+  return GSP_OK;
+}
+
+}  // namespace gsp
+
+using namespace gsp;
+
+extern "C" const char* gsp_version(void) {
+#ifdef GSP_EMU
+  return "gsp_b200 0.1.0 (CPU EMULATION BUILD - tests only)";
+#else
+  return "gsp_b200 0.1.0 (sm_100a)";
+#endif
+}
+
+extern "C" int gsp_ctx_create(int32_t ndev, const int32_t* devs, gsp_ctx** out) {
+  if (!out) return -3;
+  *out = nullptr;
+  if (ndev < 1 || ndev > 64) return -1;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count < 1) return GSP_E_CUDA;
+  gsp_ctx* ctx = new gsp_ctx;
+  for (int i = 0; i < ndev; ++i) {
+    DevCtx dc;
+    dc.dev = devs ? devs[i] : i;
+    if (dc.dev < 0 || dc.dev >= count) {
+      delete ctx;
+      return -2;
+    }
+    ctx->devs.push_back(dc);
+  }
+  for (auto& dc : ctx->devs) {
+    cudaError_t e = cudaSetDevice(dc.dev);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&dc.stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&dc.h2d, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&dc.d2h, cudaStreamNonBlocking);
+    cudaDeviceProp prop;
+    if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, dc.dev);
+    if (e != cudaSuccess) {
+      delete ctx;
+      return GSP_E_CUDA;
+    }
+    dc.sms = prop.multiProcessorCount;
+    dc.smem_optin = prop.sharedMemPerBlockOptin;
+  }
+  *out = ctx;
+  return GSP_OK;
+}
+
+extern "C" int gsp_ctx_destroy(gsp_ctx* ctx) {
+  if (!ctx) return GSP_OK;
+  for (auto& dc : ctx->devs) {
+    cudaSetDevice(dc.dev);
+    if (dc.stream) cudaStreamDestroy(dc.stream);
+    if (dc.h2d) cudaStreamDestroy(dc.h2d);
+    if (dc.d2h) cudaStreamDestroy(dc.d2h);
+  }
+  delete ctx;
+  return GSP_OK;
+}
+
+extern "C" const char* gsp_last_error(gsp_ctx* ctx) { return ctx ? ctx->err.c_str() : "context is NULL"; }
+extern "C" int gsp_ctx_ndev(gsp_ctx* ctx) { return ctx ? (int)ctx->devs.size() : 0; }
+extern "C" int64_t gsp_kernel_launches(void) { return g_launches; }
+extern "C" double gsp_last_sample_ms(gsp_ctx* ctx) { return ctx ? ctx->last_sample_ms : 0.0; }
+
+extern "C" int gsp_host_alloc(void** out, int64_t bytes) {
+  if (!out || bytes < 0) return -1;
+  return cudaMallocHost(out, (size_t)bytes) == cudaSuccess ? GSP_OK : GSP_E_NOMEM;
+}
+extern "C" int gsp_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? GSP_OK : GSP_E_CUDA; }
+
+extern "C" int gsp_pairwise(gsp_ctx* ctx, const gsp_cov_model* cov, int32_t dim, int64_t n1, const double* X1, int64_t n2,
+                            const double* X2, double* out) {
+  if (!ctx) return -1;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (dim < 1 || dim > 3) return set_err(ctx, -3, "dim must be 1..3");
+  if (n1 < 1 || !X1) return set_err(ctx, -4, "X1 / n1 invalid");
+  if (!out) return set_err(ctx, -8, "out is NULL");
+  const bool sym = (X2 == nullptr);
+  if (sym) n2 = n1;
+  if (n2 < 1) return set_err(ctx, -6, "n2 invalid");
+  CovDev cd;
+  GSP_TRY(make_cov_dev(ctx, cov, dim, 2, &cd));
+  DevCtx& dc = ctx->devs[0];
+  cudaSetDevice(dc.dev);
+  DevBuf d1, d2, dout;
+  GSP_CUDA_OK(ctx, d1.alloc(dc.dev, (size_t)n1 * dim * sizeof(double)));
+  GSP_CUDA_OK(ctx, cudaMemcpyAsync(d1.p, X1, (size_t)n1 * dim * sizeof(double), cudaMemcpyHostToDevice, dc.stream));
+  if (!sym) {
+    GSP_CUDA_OK(ctx, d2.alloc(dc.dev, (size_t)n2 * dim * sizeof(double)));
+    GSP_CUDA_OK(ctx, cudaMemcpyAsync(d2.p, X2, (size_t)n2 * dim * sizeof(double), cudaMemcpyHostToDevice, dc.stream));
+  }
+  GSP_CUDA_OK(ctx, dout.alloc(dc.dev, (size_t)n1 * n2 * sizeof(double)));
+  DomDev r{}, c{};
+  r.kind = 0; r.dim = dim; r.nelems = n1; r.coords = d1.as<double>();
+  c.kind = 0; c.dim = dim; c.nelems = n2; c.coords = sym ? d1.as<double>() : d2.as<double>();
+  launch_assemble(dc.stream, cd, r, c, nullptr, nullptr, n1, n2, dout.as<double>(), n1, false);
+  GSP_CUDA_OK(ctx, cudaGetLastError());
+  GSP_CUDA_OK(ctx, cudaMemcpyAsync(out, dout.p, (size_t)n1 * n2 * sizeof(double), cudaMemcpyDeviceToHost, dc.stream));
+  GSP_CUDA_OK(ctx, cudaStreamSynchronize(dc.stream));
+  return GSP_OK;
+}
+
+extern "C" int gsp_potrf(gsp_ctx* ctx, int64_t n, double* A) {
+  if (!ctx) return -1;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (n < 1) return set_err(ctx, -2, "n must be >= 1");
+  if (!A) return set_err(ctx, -3, "A is NULL");
+  DevCtx& dc = ctx->devs[0];
+  cudaSetDevice(dc.dev);
+  const long long np = round_up(n, 128);
+  const int nb = (int)(np / 128);
+  DevBuf dA, dinv, dinfo;
+  GSP_CUDA_OK(ctx, dA.alloc(dc.dev, (size_t)np * np * sizeof(double)));
+  GSP_CUDA_OK(ctx, dinv.alloc(dc.dev, (size_t)nb * 128 * 128 * sizeof(double)));
+  GSP_CUDA_OK(ctx, dinfo.alloc(dc.dev, sizeof(int)));
+  // identity padding, then the user matrix in the leading n x n corner
+  std::vector<double> pad((size_t)np * np, 0.0);
+  for (long long j = 0; j < np; ++j) {
+    if (j < n) std::memcpy(&pad[(size_t)j * np], A + (size_t)j * n, (size_t)n * sizeof(double));
+    else pad[(size_t)j * np + j] = 1.0;
+  }
+  GSP_CUDA_OK(ctx, cudaMemcpyAsync(dA.p, pad.data(), pad.size() * sizeof(double), cudaMemcpyHostToDevice, dc.stream));
+  GSP_CUDA_OK(ctx, chol_factor(dc.stream, dA.as<double>(), np, nb, dinv.as<double>(), dinfo.as<int>()));
+  int info = 0;
+  GSP_CUDA_OK(ctx, cudaMemcpyAsync(&info, dinfo.p, sizeof(int), cudaMemcpyDeviceToHost, dc.stream));
+  GSP_CUDA_OK(ctx, cudaMemcpyAsync(pad.data(), dA.p, pad.size() * sizeof(double), cudaMemcpyDeviceToHost, dc.stream));
+  GSP_CUDA_OK(ctx, cudaStreamSynchronize(dc.stream));
+  if (info > 0 && info <= n) return info;
+  for (long long j = 0; j < n; ++j)
+    for (long long i = 0; i < n; ++i) A[(size_t)j * n + i] = (i >= j) ? pad[(size_t)j * np + i] : 0.0;
+  return GSP_OK;
+}

@@ -1,0 +1,80 @@
+// Host-side shared declarations of libgspb200: context, error plumbing, device buffers.
+#pragma once
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/gsp_b200.h"
+#include "gsp_rt.h"
+
+namespace gsp {
+
+extern long long g_launches;  // kernels launched by this library (gsp_kernel_launches)
+
+struct DevCtx {
+  int dev = 0;
+  cudaStream_t stream = nullptr;   // compute
+  cudaStream_t h2d = nullptr;      // copy-in
+  cudaStream_t d2h = nullptr;      // copy-out
+  int sms = 148;
+  size_t smem_optin = 227 * 1024;
+};
+
+}  // namespace gsp
+
+struct gsp_ctx {
+  std::vector<gsp::DevCtx> devs;
+  std::string err;
+  std::mutex mu;
+  double last_sample_ms = 0.0;
+};
+
+namespace gsp {
+
+int set_err(gsp_ctx* ctx, int code, const std::string& msg);
+
+#define GSP_CUDA_OK(ctx, expr)                                                                          \
+  do {                                                                                                  \
+    cudaError_t e_ = (expr);                                                                            \
+    if (e_ != cudaSuccess)                                                                              \
+      return ::gsp::set_err((ctx), GSP_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));     \
+  } while (0)
+
+#define GSP_TRY(expr)            \
+  do {                           \
+    int rc_ = (expr);            \
+    if (rc_ != GSP_OK) return rc_; \
+  } while (0)
+
+// RAII device buffer (freed on the device it was allocated on)
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  int dev = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }
+  cudaError_t alloc(int device, size_t n) {
+    release();
+    dev = device;
+    cudaSetDevice(dev);
+    cudaError_t e = cudaMalloc(&p, n ? n : 16);
+    if (e == cudaSuccess) bytes = n;
+    else p = nullptr;
+    return e;
+  }
+  void release() {
+    if (p) {
+      cudaSetDevice(dev);
+      cudaFree(p);
+      p = nullptr;
+      bytes = 0;
+    }
+  }
+  template <class T> T* as() const { return (T*)p; }
+};
+
+inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+
+}  // namespace gsp

@@ -1,0 +1,701 @@
+// FFTSIM on the device: spectrum build (fftsim.jl:77-91) and the per-realization
+// pipeline (fftsim.jl:124-135) as real-to-complex / complex-to-real passes over a half spectrum.
+//
+// Layout in HBM: real fields [z][y][x] (x fastest = Julia column-major), half spectrum
+// H[z][y][kx] with kx = 0..nx/2 (16-byte complex), F stored as a REAL half spectrum (4N bytes).
+// Per realization:  x-pass R2C  ->  (y-pass fwd)  ->  last-axis pass: fwd, P = s*F*W/|W|, inverse
+//                   ->  (y-pass inverse)  ->  x-pass C2R with the "+mu" epilogue.
+// sigma^2 = var(Z, mean=0) (fftsim.jl:131) does not depend on the noise: |P_k| = F_k, so by Parseval
+// sigma^2 = sum(F^2) / (N (N-1)); it is computed once per plan and folded into the scalar s.
+#include <cmath>
+#include <memory>
+
+#include "cov.cuh"
+#include "chol.h"
+#include "fft_kernels.cuh"
+#include "rng.cuh"
+
+namespace gsp {
+
+// ------------------------------------------------------------------ kernels
+// x-axis forward pass: real rows -> half spectrum rows.  One CTA = B consecutive rows.
+// packed != 0 (even nx): rows are read as nx/2 complex numbers, transformed with a half-length FFT
+// and untangled; packed == 0 (odd nx): plain complex transform of the zero-extended row.
+__global__ void __launch_bounds__(256) xpass_fwd_kernel(LinePlan lp, int nx, int hx, long long nrows, int B, int packed,
+                                                        const double* __restrict__ in, cplx* __restrict__ H) {
+  GSP_DYN_SMEM(smem);
+  const int L = packed ? nx / 2 + 1 : nx;
+  cplx* X = reinterpret_cast<cplx*>(smem);
+  cplx* Y = X + (size_t)L * B;
+  const long long row0 = (long long)blockIdx.x * B;
+  const int nb = (int)((nrows - row0 < B) ? nrows - row0 : B);
+  const int n = lp.n;
+  for (int idx = threadIdx.x; idx < B * n; idx += blockDim.x) {
+    const int b = idx / n, j = idx - b * n;
+    cplx v{0.0, 0.0};
+    if (b < nb) {
+      const double* p = in + (row0 + b) * nx;
+      if (packed) {
+        const double2 t = *reinterpret_cast<const double2*>(p + 2 * j);
+        v = cplx{t.x, t.y};
+      } else {
+        v = cplx{p[j], 0.0};
+      }
+    }
+    X[j * B + b] = v;
+  }
+  __syncthreads();
+  const cplx* Z = fft_bundle<false>(lp, X, Y, B);
+  for (int idx = threadIdx.x; idx < nb * hx; idx += blockDim.x) {
+    const int b = idx / hx, k = idx - b * hx;
+    cplx o;
+    if (packed) {
+      const int h = n;
+      const cplx zk = Z[(k % h) * B + b];
+      const cplx zc = cconj(Z[((h - k) % h) * B + b]);
+      const cplx e = cplx{0.5 * (zk.re + zc.re), 0.5 * (zk.im + zc.im)};
+      const cplx d = csub(zk, zc);
+      const cplx od = cplx{0.5 * d.im, -0.5 * d.re};  // (-i/2) * d
+      o = cadd(e, cmul(lp.tw[k], od));                // tw has stride 1 over the length-nx table here
+    } else {
+      o = Z[k * B + b];
+    }
+    H[(row0 + b) * hx + k] = o;
+  }
+}
+
+// x-axis inverse pass: half spectrum rows -> real rows, out = scale * (unnormalised inverse DFT) + mu
+__global__ void __launch_bounds__(256) xpass_inv_kernel(LinePlan lp, int nx, int hx, long long nrows, int B, int packed,
+                                                        const cplx* __restrict__ H, double* __restrict__ out, double scale,
+                                                        double mu) {
+  GSP_DYN_SMEM(smem);
+  const int L = packed ? nx / 2 + 1 : nx;
+  cplx* X = reinterpret_cast<cplx*>(smem);
+  cplx* Y = X + (size_t)L * B;
+  const long long row0 = (long long)blockIdx.x * B;
+  const int nb = (int)((nrows - row0 < B) ? nrows - row0 : B);
+  const int n = lp.n;
+  for (int idx = threadIdx.x; idx < B * hx; idx += blockDim.x) {
+    const int b = idx / hx, k = idx - b * hx;
+    X[k * B + b] = (b < nb) ? H[(row0 + b) * hx + k] : cplx{0.0, 0.0};
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < B * n; idx += blockDim.x) {
+    const int b = idx / n, k = idx - b * n;
+    cplx v;
+    if (packed) {
+      const int h = n;
+      const cplx xk = X[k * B + b];
+      const cplx xc = cconj(X[(h - k) * B + b]);
+      const cplx s = cadd(xk, xc);
+      const cplx d = csub(xk, xc);
+      const cplx t = cmul(cconj(lp.tw[k]), d);
+      v = cplx{s.re - t.im, s.im + t.re};  // s + i*t
+    } else {
+      v = (k < hx) ? X[k * B + b] : cconj(X[(nx - k) * B + b]);
+    }
+    Y[k * B + b] = v;
+  }
+  __syncthreads();
+  const cplx* z = fft_bundle<true>(lp, Y, X, B);
+  for (int idx = threadIdx.x; idx < nb * n; idx += blockDim.x) {
+    const int b = idx / n, j = idx - b * n;
+    const cplx v = z[j * B + b];
+    double* p = out + (row0 + b) * nx;
+    if (packed)
+      *reinterpret_cast<double2*>(p + 2 * j) = make_double2(v.re * scale + mu, v.im * scale + mu);
+    else
+      p[j] = v.re * scale + mu;
+  }
+}
+
+enum { PASS_FWD = 1, PASS_MUL = 2, PASS_INV = 4 };
+
+// strided-axis pass (y or z) over the half spectrum, in place.  blockIdx.x = bundle of B adjacent kx,
+// blockIdx.y = index along the remaining axis.  With PASS_MUL the spectrum is replaced by
+// P = s * F * W/|W| (angle(0) = 0 => P = s*F) between the forward and inverse transforms (fftsim.jl:125).
+__global__ void __launch_bounds__(256) strided_pass_kernel(LinePlan lp, cplx* __restrict__ H, long long es, int hx, int B,
+                                                           long long other_stride, int flags, const double* __restrict__ Fh,
+                                                           double s) {
+  GSP_DYN_SMEM(smem);
+  const int n = lp.n;
+  cplx* X = reinterpret_cast<cplx*>(smem);
+  cplx* Y = X + (size_t)n * B;
+  const int b0 = blockIdx.x * B;
+  const int nb = (hx - b0 < B) ? hx - b0 : B;
+  const long long base = (long long)blockIdx.y * other_stride + b0;
+  for (int idx = threadIdx.x; idx < n * B; idx += blockDim.x) {
+    const int j = idx / B, b = idx - j * B;
+    X[idx] = (b < nb) ? H[base + (long long)j * es + b] : cplx{0.0, 0.0};
+  }
+  __syncthreads();
+  cplx* cur = X;
+  cplx* oth = Y;
+  if (flags & PASS_FWD) {
+    cur = fft_bundle<false>(lp, X, Y, B);
+    oth = (cur == X) ? Y : X;
+  }
+  if (flags & PASS_MUL) {
+    for (int idx = threadIdx.x; idx < n * B; idx += blockDim.x) {
+      const int j = idx / B, b = idx - j * B;
+      if (b < nb) {
+        const double f = s * Fh[base + (long long)j * es + b];
+        const cplx w = cur[idx];
+        const double m2 = w.re * w.re + w.im * w.im;
+        if (m2 > 0.0) {
+          const double g = f * rsqrt(m2);
+          cur[idx] = cplx{g * w.re, g * w.im};
+        } else {
+          cur[idx] = cplx{f, 0.0};
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (flags & PASS_INV) cur = fft_bundle<true>(lp, cur, oth, B);
+  for (int idx = threadIdx.x; idx < n * B; idx += blockDim.x) {
+    const int j = idx / B, b = idx - j * B;
+    if (b < nb) H[base + (long long)j * es + b] = cur[idx];
+  }
+}
+
+// 1-D grids only: P = s * F * W/|W| elementwise on the half spectrum
+__global__ void __launch_bounds__(256) spectral_mul_kernel(cplx* __restrict__ H, const double* __restrict__ Fh, long long nh,
+                                                           double s) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nh; i += stride) {
+    const double f = s * Fh[i];
+    const cplx w = H[i];
+    const double m2 = w.re * w.re + w.im * w.im;
+    H[i] = (m2 > 0.0) ? cplx{f * rsqrt(m2) * w.re, f * rsqrt(m2) * w.im} : cplx{f, 0.0};
+  }
+}
+
+// F = sqrt(|H|), F[0] = 0 (fftsim.jl:90-91); partial[blockIdx.x] = sum of w_k F_k^2 over the block's
+// elements, w_k = 1 on the self-conjugate planes kx = 0 and (nx even) kx = nx/2, else 2.
+__global__ void __launch_bounds__(256) spectrum_finalize_kernel(const cplx* __restrict__ H, double* __restrict__ Fh, long long nh,
+                                                                int hx, int nx, double* __restrict__ partial) {
+  __shared__ double red[256];
+  double acc = 0.0;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nh; i += stride) {
+    const cplx h = H[i];
+    double f2 = sqrt(h.re * h.re + h.im * h.im);  // F^2 = |fft(C)|
+    if (i == 0) f2 = 0.0;
+    Fh[i] = sqrt(f2);
+    const int kx = (int)(i % hx);
+    const double w = (kx == 0 || ((nx & 1) == 0 && kx == nx / 2)) ? 1.0 : 2.0;
+    acc += w * f2;
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = red[0];
+}
+
+__global__ void __launch_bounds__(256) sum_partials_kernel(const double* __restrict__ partial, int n, double* __restrict__ out) {
+  __shared__ double red[256];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) acc += partial[i];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = red[0];
+}
+
+// out[q + r*n_inds] = src[(inds[q]-1) + r*N]   (Z[parentindices(sdom)], fftsim.jl:135; inds 1-based)
+__global__ void __launch_bounds__(256) gather_kernel(const double* __restrict__ src, long long N, const long long* __restrict__ inds,
+                                                     long long n_inds, long long R, double* __restrict__ out) {
+  const long long total = n_inds * R;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+    const long long r = t / n_inds, q = t - r * n_inds;
+    out[t] = src[(inds[q] - 1) + r * N];
+  }
+}
+
+// ------------------------------------------------------------------ host side
+namespace {
+
+bool choose_radices(int n, LinePlan* lp) {
+  lp->n = n;
+  lp->nst = 0;
+  int m = n;
+  const int cand[] = {16, 8, 4, 2, 3, 5, 7, 11, 13};
+  for (int c : cand) {
+    while (m % c == 0 && m > 1) {
+      if (lp->nst >= FFT_MAX_STAGES) return false;
+      lp->radix[lp->nst++] = c;
+      m /= c;
+    }
+  }
+  return m == 1;
+}
+
+std::vector<cplx> make_twiddles(int n) {
+  std::vector<cplx> t((size_t)n);
+  const long double two_pi = 6.283185307179586476925286766559005768L;
+  for (int i = 0; i < n; ++i) {
+    // reduce to the first octant for accuracy
+    long double a = two_pi * (long double)i / (long double)n;
+    t[i] = cplx{(double)cosl(a), (double)-sinl(a)};
+  }
+  return t;
+}
+
+struct AxisPlan {
+  int len = 1;       // extent
+  LinePlan lp{};     // device-visible plan
+  int B = 1;         // bundle width
+  size_t smem = 0;
+  int packed = 0;    // x axis only
+};
+
+struct FftDev {
+  DevCtx* dc = nullptr;
+  DevBuf tw[3];
+  DevBuf Fh;       // real half spectrum
+  DevBuf H;        // complex half-spectrum work buffer
+  DevBuf win[2], zout[2];  // staging for host-pointer sampling
+  DevBuf inds;
+  long long inds_cap = 0;
+  AxisPlan ax[3];
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+}  // namespace
+}  // namespace gsp
+
+using namespace gsp;
+
+struct gsp_fft_plan {
+  gsp_ctx* ctx = nullptr;
+  int ndim = 1;
+  long long dims[3] = {1, 1, 1};
+  long long N = 1, nh = 1;
+  int hx = 1;
+  double sumF2 = 0.0;  // full-spectrum sum of F^2
+  std::vector<std::unique_ptr<FftDev>> dev;
+  std::mutex mu;
+};
+
+namespace gsp {
+namespace {
+
+const size_t kMaxSmem = 200 * 1024;
+
+int setup_axes(gsp_ctx* ctx, gsp_fft_plan* p, FftDev* d) {
+  const int nx = (int)p->dims[0];
+  // x axis
+  {
+    AxisPlan& a = d->ax[0];
+    a.len = nx;
+    a.packed = (nx % 2 == 0) ? 1 : 0;
+    const int n = a.packed ? nx / 2 : nx;
+    if (!choose_radices(n, &a.lp)) return set_err(ctx, GSP_E_UNSUPPORTED, "grid extent has a prime factor > 13");
+    std::vector<cplx> tw = make_twiddles(nx);
+    GSP_CUDA_OK(ctx, d->tw[0].alloc(d->dc->dev, tw.size() * sizeof(cplx)));
+    GSP_CUDA_OK(ctx, cudaMemcpyAsync(d->tw[0].p, tw.data(), tw.size() * sizeof(cplx), cudaMemcpyHostToDevice, d->dc->stream));
+    GSP_CUDA_OK(ctx, cudaStreamSynchronize(d->dc->stream));
+    a.lp.tw = d->tw[0].as<cplx>();
+    a.lp.tw_stride = a.packed ? 2 : 1;
+    const size_t L = a.packed ? (size_t)nx / 2 + 1 : (size_t)nx;
+    const long long nrows = p->dims[1] * p->dims[2];
+    int B = (int)(32 * 1024 / (L * sizeof(cplx)));
+    if (B < 1) B = 1;
+    if (B > 15) B = 15;
+    if (B > nrows) B = (int)nrows;
+    if (B % 2 == 0) B -= 1;  // odd: conflict-free global<->shared transposition
+    if (B < 1) B = 1;
+    a.B = B;
+    a.smem = 2 * L * B * sizeof(cplx);
+    if (a.smem > kMaxSmem) return set_err(ctx, GSP_E_UNSUPPORTED, "x extent too large for one shared-memory line");
+  }
+  for (int axis = 1; axis < p->ndim; ++axis) {
+    AxisPlan& a = d->ax[axis];
+    const int n = (int)p->dims[axis];
+    a.len = n;
+    if (!choose_radices(n, &a.lp)) return set_err(ctx, GSP_E_UNSUPPORTED, "grid extent has a prime factor > 13");
+    std::vector<cplx> tw = make_twiddles(n);
+    GSP_CUDA_OK(ctx, d->tw[axis].alloc(d->dc->dev, tw.size() * sizeof(cplx)));
+    GSP_CUDA_OK(ctx, cudaMemcpyAsync(d->tw[axis].p, tw.data(), tw.size() * sizeof(cplx), cudaMemcpyHostToDevice, d->dc->stream));
+    GSP_CUDA_OK(ctx, cudaStreamSynchronize(d->dc->stream));
+    a.lp.tw = d->tw[axis].as<cplx>();
+    a.lp.tw_stride = 1;
+    int B = 8;
+    while (B > 1 && 2 * (size_t)n * B * sizeof(cplx) > 96 * 1024) B /= 2;
+    if (B > p->hx) B = p->hx;
+    a.B = B;
+    a.smem = 2 * (size_t)n * B * sizeof(cplx);
+    if (a.smem > kMaxSmem) return set_err(ctx, GSP_E_UNSUPPORTED, "grid extent too large for one shared-memory line");
+  }
+  return GSP_OK;
+}
+
+cudaError_t run_xfwd(FftDev* d, gsp_fft_plan* p, const double* in, cplx* H) {
+  const AxisPlan& a = d->ax[0];
+  const long long nrows = p->dims[1] * p->dims[2];
+  auto kfn = xpass_fwd_kernel;
+  cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.smem);
+  if (e != cudaSuccess) return e;
+  GSP_LAUNCH(kfn, dim3((unsigned)((nrows + a.B - 1) / a.B)), dim3(256), a.smem, d->dc->stream, a.lp, (int)p->dims[0], p->hx, nrows,
+             a.B, a.packed, in, H);
+  g_launches++;
+  return cudaGetLastError();
+}
+
+cudaError_t run_xinv(FftDev* d, gsp_fft_plan* p, const cplx* H, double* out, double scale, double mu) {
+  const AxisPlan& a = d->ax[0];
+  const long long nrows = p->dims[1] * p->dims[2];
+  auto kfn = xpass_inv_kernel;
+  cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.smem);
+  if (e != cudaSuccess) return e;
+  GSP_LAUNCH(kfn, dim3((unsigned)((nrows + a.B - 1) / a.B)), dim3(256), a.smem, d->dc->stream, a.lp, (int)p->dims[0], p->hx, nrows,
+             a.B, a.packed, H, out, scale, mu);
+  g_launches++;
+  return cudaGetLastError();
+}
+
+cudaError_t run_strided(FftDev* d, gsp_fft_plan* p, int axis, cplx* H, int flags, const double* Fh, double s) {
+  const AxisPlan& a = d->ax[axis];
+  const long long hx = p->hx;
+  long long es, other_stride, nother;
+  if (axis == 1) {
+    es = hx;
+    other_stride = hx * p->dims[1];
+    nother = p->dims[2];
+  } else {
+    es = hx * p->dims[1];
+    other_stride = hx;
+    nother = p->dims[1];
+  }
+  auto kfn = strided_pass_kernel;
+  cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.smem);
+  if (e != cudaSuccess) return e;
+  dim3 grid((unsigned)((hx + a.B - 1) / a.B), (unsigned)nother);
+  GSP_LAUNCH(kfn, grid, dim3(256), a.smem, d->dc->stream, a.lp, H, es, (int)hx, a.B, other_stride, flags, Fh, s);
+  g_launches++;
+  return cudaGetLastError();
+}
+
+// forward transform of a real field into d->H (all axes)
+cudaError_t forward_all(FftDev* d, gsp_fft_plan* p, const double* in) {
+  cudaError_t e = run_xfwd(d, p, in, d->H.as<cplx>());
+  for (int axis = 1; axis < p->ndim && e == cudaSuccess; ++axis) e = run_strided(d, p, axis, d->H.as<cplx>(), PASS_FWD, nullptr, 0.0);
+  return e;
+}
+
+// one realization: real noise (device) -> real field (device), full grid
+cudaError_t realization(FftDev* d, gsp_fft_plan* p, const double* w, double* out, double s, double scale_out, double mu) {
+  cplx* H = d->H.as<cplx>();
+  const double* Fh = d->Fh.as<double>();
+  cudaError_t e = run_xfwd(d, p, w, H);
+  if (e != cudaSuccess) return e;
+  const int last = p->ndim - 1;
+  if (last == 0) {
+    long long blocks = (p->nh + 255) / 256;
+    if (blocks > (long long)d->dc->sms * 8) blocks = (long long)d->dc->sms * 8;
+    GSP_LAUNCH(spectral_mul_kernel, dim3((unsigned)blocks), dim3(256), 0, d->dc->stream, H, Fh, p->nh, s);
+    g_launches++;
+    e = cudaGetLastError();
+  } else {
+    for (int axis = 1; axis < last && e == cudaSuccess; ++axis) e = run_strided(d, p, axis, H, PASS_FWD, nullptr, 0.0);
+    if (e == cudaSuccess) e = run_strided(d, p, last, H, PASS_FWD | PASS_MUL | PASS_INV, Fh, s);
+    for (int axis = last - 1; axis >= 1 && e == cudaSuccess; --axis) e = run_strided(d, p, axis, H, PASS_INV, nullptr, 0.0);
+  }
+  if (e != cudaSuccess) return e;
+  return run_xinv(d, p, H, out, scale_out, mu);
+}
+
+int build_device(gsp_ctx* ctx, gsp_fft_plan* p, FftDev* d, const CovDev& cov, const DomDev& dom, long long eref) {
+  cudaSetDevice(d->dc->dev);
+  GSP_TRY(setup_axes(ctx, p, d));
+  GSP_CUDA_OK(ctx, d->Fh.alloc(d->dc->dev, (size_t)p->nh * sizeof(double)));
+  GSP_CUDA_OK(ctx, d->H.alloc(d->dc->dev, (size_t)p->nh * sizeof(cplx)));
+  GSP_CUDA_OK(ctx, cudaEventCreate(&d->ev0));
+  GSP_CUDA_OK(ctx, cudaEventCreate(&d->ev1));
+  DevBuf C, partial, total;
+  GSP_CUDA_OK(ctx, C.alloc(d->dc->dev, (size_t)p->N * sizeof(double)));
+  const int nblocks = d->dc->sms * 4;
+  GSP_CUDA_OK(ctx, partial.alloc(d->dc->dev, (size_t)nblocks * sizeof(double)));
+  GSP_CUDA_OK(ctx, total.alloc(d->dc->dev, sizeof(double)));
+  launch_cov_to_center(d->dc->stream, d->dc->sms, cov, dom, eref, C.as<double>());
+  GSP_CUDA_OK(ctx, cudaGetLastError());
+  GSP_CUDA_OK(ctx, forward_all(d, p, C.as<double>()));
+  GSP_LAUNCH(spectrum_finalize_kernel, dim3((unsigned)nblocks), dim3(256), 0, d->dc->stream, d->H.as<cplx>(), d->Fh.as<double>(),
+             p->nh, p->hx, (int)p->dims[0], partial.as<double>());
+  g_launches++;
+  GSP_LAUNCH(sum_partials_kernel, dim3(1), dim3(256), 0, d->dc->stream, partial.as<double>(), nblocks, total.as<double>());
+  g_launches++;
+  GSP_CUDA_OK(ctx, cudaGetLastError());
+  double s2 = 0.0;
+  GSP_CUDA_OK(ctx, cudaMemcpyAsync(&s2, total.p, sizeof(double), cudaMemcpyDeviceToHost, d->dc->stream));
+  GSP_CUDA_OK(ctx, cudaStreamSynchronize(d->dc->stream));
+  p->sumF2 = s2;
+  return GSP_OK;
+}
+
+// scalar folded into the spectrum multiply: sqrt(sill / sigma^2) / N  (fftsim.jl:128-132)
+double fold_scale(const gsp_fft_plan* p, double sill) {
+  const double N = (double)p->N;
+  const double sigma2 = p->sumF2 / (N * (N - 1.0));
+  return std::sqrt(sill / sigma2) / N;
+}
+
+}  // namespace
+}  // namespace gsp
+
+extern "C" int gsp_fft_plan_create(gsp_ctx* ctx, const gsp_cov_model* cov, const gsp_domain* grid, gsp_fft_plan** out) {
+  if (!ctx) return -1;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (!out) return set_err(ctx, -4, "out is NULL");
+  *out = nullptr;
+  if (!grid || grid->kind != 1) return set_err(ctx, -3, "FFTSIM needs a CartesianGrid domain (kind 1)");
+  DomDev dom;
+  GSP_TRY(make_dom_dev(ctx, grid, 3, &dom));
+  CovDev cd;
+  GSP_TRY(make_cov_dev(ctx, cov, grid->dim, 2, &cd));
+  std::unique_ptr<gsp_fft_plan> p(new gsp_fft_plan);
+  p->ctx = ctx;
+  p->ndim = grid->dim;
+  p->N = 1;
+  for (int a = 0; a < 3; ++a) {
+    p->dims[a] = a < grid->dim ? grid->dims[a] : 1;
+    p->N *= p->dims[a];
+  }
+  if (p->N < 2) return set_err(ctx, -3, "grid must have at least 2 elements");
+  long long eref = 0, stride = 1;
+  for (int a = 0; a < p->ndim; ++a) {
+    const long long c = p->dims[a] / 2;  // CartesianIndex(dims .÷ 2), 1-based (fftsim.jl:80)
+    if (c < 1) return set_err(ctx, -3, "grid extent < 2: dims .÷ 2 is not a valid index in the reference");
+    eref += (c - 1) * stride;
+    stride *= p->dims[a];
+  }
+  p->hx = (int)(p->dims[0] / 2 + 1);
+  p->nh = (long long)p->hx * p->dims[1] * p->dims[2];
+  for (auto& dc : ctx->devs) {
+    std::unique_ptr<FftDev> d(new FftDev);
+    d->dc = &dc;
+    GSP_TRY(build_device(ctx, p.get(), d.get(), cd, dom, eref));
+    p->dev.push_back(std::move(d));
+  }
+  *out = p.release();
+  return GSP_OK;
+}
+
+extern "C" int gsp_fft_plan_destroy(gsp_fft_plan* p) {
+  if (!p) return GSP_OK;
+  for (auto& d : p->dev) {
+    cudaSetDevice(d->dc->dev);
+    cudaStreamSynchronize(d->dc->stream);
+    if (d->ev0) cudaEventDestroy(d->ev0);
+    if (d->ev1) cudaEventDestroy(d->ev1);
+  }
+  delete p;
+  return GSP_OK;
+}
+
+extern "C" int gsp_fft_plan_get(gsp_fft_plan* p, double* F) {
+  if (!p) return -1;
+  gsp_ctx* ctx = p->ctx;
+  std::lock_guard<std::mutex> lk(p->mu);
+  if (!F) return set_err(ctx, -2, "F is NULL");
+  FftDev* d = p->dev[0].get();
+  cudaSetDevice(d->dc->dev);
+  std::vector<double> Fh((size_t)p->nh);
+  GSP_CUDA_OK(ctx, cudaMemcpyAsync(Fh.data(), d->Fh.p, Fh.size() * sizeof(double), cudaMemcpyDeviceToHost, d->dc->stream));
+  GSP_CUDA_OK(ctx, cudaStreamSynchronize(d->dc->stream));
+  const long long nx = p->dims[0], ny = p->dims[1], nz = p->dims[2], hx = p->hx;
+  for (long long z = 0; z < nz; ++z)
+    for (long long y = 0; y < ny; ++y)
+      for (long long x = 0; x < nx; ++x) {
+        double v;
+        if (x < hx)
+          v = Fh[(size_t)(x + hx * (y + ny * z))];
+        else
+          v = Fh[(size_t)((nx - x) + hx * (((ny - y) % ny) + ny * ((nz - z) % nz)))];
+        F[x + nx * (y + ny * z)] = v;
+      }
+  return GSP_OK;
+}
+
+namespace gsp {
+namespace {
+
+// sample R realizations on one device; w/out/inds are DEVICE pointers (w may be NULL => RNG into scratch)
+int sample_on_device(gsp_fft_plan* p, FftDev* d, long long R, const double* w, unsigned long long seed, long long first_real,
+                     double sill, double mu, long long n_inds, const long long* inds_dev, double* out, DevBuf* scratch_w,
+                     DevBuf* scratch_z) {
+  gsp_ctx* ctx = p->ctx;
+  const double s = fold_scale(p, sill);
+  for (long long r = 0; r < R; ++r) {
+    const double* wr;
+    if (w) {
+      wr = w + r * p->N;
+    } else {
+      if (!scratch_w->p) GSP_CUDA_OK(ctx, scratch_w->alloc(d->dc->dev, (size_t)p->N * sizeof(double)));
+      GSP_CUDA_OK(ctx, launch_rng_fill(d->dc->stream, d->dc->sms, scratch_w->as<double>(), p->N, p->N, 1, seed, 0,
+                                       (unsigned long long)(first_real + r), false));
+      wr = scratch_w->as<double>();
+    }
+    if (n_inds > 0) {
+      if (!scratch_z->p) GSP_CUDA_OK(ctx, scratch_z->alloc(d->dc->dev, (size_t)p->N * sizeof(double)));
+      GSP_CUDA_OK(ctx, realization(d, p, wr, scratch_z->as<double>(), s, 1.0, mu));
+      long long blocks = (n_inds + 255) / 256;
+      if (blocks > (long long)d->dc->sms * 8) blocks = (long long)d->dc->sms * 8;
+      GSP_LAUNCH(gather_kernel, dim3((unsigned)blocks), dim3(256), 0, d->dc->stream, scratch_z->as<double>(), p->N, inds_dev, n_inds,
+                 1LL, out + r * n_inds);
+      g_launches++;
+      GSP_CUDA_OK(ctx, cudaGetLastError());
+    } else {
+      GSP_CUDA_OK(ctx, realization(d, p, wr, out + r * p->N, s, 1.0, mu));
+    }
+  }
+  return GSP_OK;
+}
+
+}  // namespace
+}  // namespace gsp
+
+extern "C" int gsp_fft_sample_dev(gsp_fft_plan* p, int64_t R, const double* w, uint64_t seed, int64_t first_real, double sill,
+                                  double mu, int64_t n_inds, const int64_t* inds_dev, double* out) {
+  if (!p) return -1;
+  gsp_ctx* ctx = p->ctx;
+  std::lock_guard<std::mutex> lk(p->mu);
+  if (R < 0) return set_err(ctx, -2, "R < 0");
+  if (!(sill > 0.0)) return set_err(ctx, -6, "sill must be positive");
+  if (!out) return set_err(ctx, -10, "out is NULL");
+  if (n_inds > 0 && !inds_dev) return set_err(ctx, -9, "inds is NULL");
+  FftDev* d = p->dev[0].get();
+  cudaSetDevice(d->dc->dev);
+  DevBuf sw, sz;
+  GSP_CUDA_OK(ctx, cudaEventRecord(d->ev0, d->dc->stream));
+  GSP_TRY(sample_on_device(p, d, R, w, seed, first_real, sill, mu, n_inds, (const long long*)inds_dev, out, &sw, &sz));
+  GSP_CUDA_OK(ctx, cudaEventRecord(d->ev1, d->dc->stream));
+  GSP_CUDA_OK(ctx, cudaStreamSynchronize(d->dc->stream));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, d->ev0, d->ev1);
+  ctx->last_sample_ms = ms;
+  return GSP_OK;
+}
+
+extern "C" int gsp_fft_sample(gsp_fft_plan* p, int64_t R, const double* w, uint64_t seed, int64_t first_real, double sill,
+                              double mu, int64_t n_inds, const int64_t* inds, double* out) {
+  if (!p) return -1;
+  gsp_ctx* ctx = p->ctx;
+  std::lock_guard<std::mutex> lk(p->mu);
+  if (R < 0) return set_err(ctx, -2, "R < 0");
+  if (!(sill > 0.0)) return set_err(ctx, -6, "sill must be positive");
+  if (!out) return set_err(ctx, -10, "out is NULL");
+  if (n_inds > 0 && !inds) return set_err(ctx, -9, "inds is NULL");
+  if (n_inds > 0)
+    for (long long q = 0; q < n_inds; ++q)
+      if (inds[q] < 1 || inds[q] > p->N) return set_err(ctx, -9, "inds out of range (1-based parent indices)");
+  const long long nout = n_inds > 0 ? n_inds : p->N;
+  const int ndev = (int)p->dev.size();
+  // contiguous shards of realizations per device (the reference shards over worker processes, field.jl:103-121)
+  std::vector<long long> r0(ndev + 1, 0);
+  for (int i = 0; i < ndev; ++i) r0[i + 1] = r0[i] + (R / ndev) + (i < R % ndev ? 1 : 0);
+  // upload indices
+  for (int i = 0; i < ndev; ++i) {
+    FftDev* d = p->dev[i].get();
+    cudaSetDevice(d->dc->dev);
+    if (n_inds > 0) {
+      if (d->inds_cap < n_inds) {
+        GSP_CUDA_OK(ctx, d->inds.alloc(d->dc->dev, (size_t)n_inds * sizeof(long long)));
+        d->inds_cap = n_inds;
+      }
+      GSP_CUDA_OK(ctx, cudaMemcpyAsync(d->inds.p, inds, (size_t)n_inds * sizeof(long long), cudaMemcpyHostToDevice, d->dc->stream));
+    }
+    for (int k = 0; k < 2; ++k) {
+      if (w && !d->win[k].p) GSP_CUDA_OK(ctx, d->win[k].alloc(d->dc->dev, (size_t)p->N * sizeof(double)));
+      if (!d->zout[k].p || d->zout[k].bytes < (size_t)nout * sizeof(double))
+        GSP_CUDA_OK(ctx, d->zout[k].alloc(d->dc->dev, (size_t)nout * sizeof(double)));
+    }
+  }
+  // software pipeline per device: H2D(r+1) | compute(r) | D2H(r-1) on three streams, double-buffered
+  std::vector<std::vector<cudaEvent_t>> ev(ndev);
+  int rc = GSP_OK;
+  std::vector<DevBuf> sw(ndev), sz(ndev);
+  long long maxshard = 0;
+  for (int i = 0; i < ndev; ++i) maxshard = std::max(maxshard, r0[i + 1] - r0[i]);
+  // events: per device, per buffer: in_ready, compute_done, out_drained
+  struct Ev { cudaEvent_t in_ready[2], done[2], drained[2], in_free[2]; };
+  std::vector<Ev> evs(ndev);
+  for (int i = 0; i < ndev; ++i) {
+    cudaSetDevice(p->dev[i]->dc->dev);
+    for (int k = 0; k < 2; ++k) {
+      cudaEventCreateWithFlags(&evs[i].in_ready[k], cudaEventDisableTiming);
+      cudaEventCreateWithFlags(&evs[i].done[k], cudaEventDisableTiming);
+      cudaEventCreateWithFlags(&evs[i].drained[k], cudaEventDisableTiming);
+      cudaEventCreateWithFlags(&evs[i].in_free[k], cudaEventDisableTiming);
+    }
+  }
+  {
+    FftDev* d0 = p->dev[0].get();
+    cudaSetDevice(d0->dc->dev);
+    cudaEventRecord(d0->ev0, d0->dc->stream);
+  }
+  for (long long step = 0; step < maxshard && rc == GSP_OK; ++step) {
+    for (int i = 0; i < ndev && rc == GSP_OK; ++i) {
+      const long long nloc = r0[i + 1] - r0[i];
+      if (step >= nloc) continue;
+      FftDev* d = p->dev[i].get();
+      cudaSetDevice(d->dc->dev);
+      const int k = (int)(step & 1);
+      const long long r = r0[i] + step;
+      const double* wdev = nullptr;
+      if (w) {
+        if (step >= 2) cudaStreamWaitEvent(d->dc->h2d, evs[i].in_free[k], 0);
+        cudaError_t e = cudaMemcpyAsync(d->win[k].p, w + r * p->N, (size_t)p->N * sizeof(double), cudaMemcpyHostToDevice, d->dc->h2d);
+        if (e != cudaSuccess) { rc = set_err(ctx, GSP_E_CUDA, cudaGetErrorString(e)); break; }
+        cudaEventRecord(evs[i].in_ready[k], d->dc->h2d);
+        cudaStreamWaitEvent(d->dc->stream, evs[i].in_ready[k], 0);
+        wdev = d->win[k].as<double>();
+      }
+      if (step >= 2) cudaStreamWaitEvent(d->dc->stream, evs[i].drained[k], 0);
+      rc = sample_on_device(p, d, 1, wdev, seed, first_real + r, sill, mu, n_inds, d->inds.as<long long>(), d->zout[k].as<double>(),
+                            &sw[i], &sz[i]);
+      if (rc != GSP_OK) break;
+      cudaEventRecord(evs[i].done[k], d->dc->stream);
+      if (w) cudaEventRecord(evs[i].in_free[k], d->dc->stream);
+      cudaStreamWaitEvent(d->dc->d2h, evs[i].done[k], 0);
+      cudaError_t e = cudaMemcpyAsync(out + r * nout, d->zout[k].p, (size_t)nout * sizeof(double), cudaMemcpyDeviceToHost, d->dc->d2h);
+      if (e != cudaSuccess) { rc = set_err(ctx, GSP_E_CUDA, cudaGetErrorString(e)); break; }
+      cudaEventRecord(evs[i].drained[k], d->dc->d2h);
+    }
+  }
+  {
+    FftDev* d0 = p->dev[0].get();
+    cudaSetDevice(d0->dc->dev);
+    cudaEventRecord(d0->ev1, d0->dc->stream);
+  }
+  for (int i = 0; i < ndev; ++i) {
+    FftDev* d = p->dev[i].get();
+    cudaSetDevice(d->dc->dev);
+    cudaError_t e1 = cudaStreamSynchronize(d->dc->h2d);
+    cudaError_t e2 = cudaStreamSynchronize(d->dc->stream);
+    cudaError_t e3 = cudaStreamSynchronize(d->dc->d2h);
+    if (rc == GSP_OK && (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess))
+      rc = set_err(ctx, GSP_E_CUDA, std::string("fft_sample: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3)));
+    for (int k = 0; k < 2; ++k) {
+      cudaEventDestroy(evs[i].in_ready[k]);
+      cudaEventDestroy(evs[i].done[k]);
+      cudaEventDestroy(evs[i].drained[k]);
+      cudaEventDestroy(evs[i].in_free[k]);
+    }
+  }
+  if (rc == GSP_OK) {
+    FftDev* d0 = p->dev[0].get();
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, d0->ev0, d0->ev1);
+    ctx->last_sample_ms = ms;
+  }
+  return rc;
+}

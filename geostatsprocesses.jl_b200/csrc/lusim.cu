@@ -1,0 +1,417 @@
+// LUSIM on the device: plan = joint covariance assembly over [data; simulation]
+// nodes + blocked Cholesky + conditional mean d2 (lusim.jl:38-110); sample = L22 * W for all
+// realizations with the fused epilogue d2 + ., scatter to sinds, data rows, +mu (lusim.jl:112-175).
+//
+// ONE Cholesky of the joint matrix ordered [dinds; sinds] replaces the reference's block algebra
+// (lusim.jl:95-103): with K = [C11 C12; C21 C22] = L L',  L = [L11 0; A21 L22] where
+// A21 = (L11 \ C12)' and L22 = chol(C22 - A21 B12), and d2 = A21 (L11 \ z1).
+//
+// Layout in HBM: joint matrix (Np x Np doubles, column-major, only lower tiles touched) with
+// the data block padded to a multiple of 128 by identity rows ("dummy data", z = 0) so that L22
+// starts on a tile boundary, and the simulation block padded likewise at the end.
+#include <algorithm>
+#include <cmath>
+#include <memory>
+
+#include "chol.h"
+#include "rng.cuh"
+
+namespace gsp {
+
+// Wp = rho * W1p + sqrt(1 - rho^2) * Wp   (lusim.jl:164)
+__global__ void __launch_bounds__(256) premix_kernel(double* __restrict__ Wp, const double* __restrict__ W1p, long long n, double rho,
+                                                     double c2) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) Wp[i] = rho * W1p[i] + c2 * Wp[i];
+}
+
+// Z[dinds[j] + r*ldz] = z1[j]   (lusim.jl:168; data honoured exactly)
+__global__ void __launch_bounds__(256) scatter_data_kernel(double* __restrict__ Z, long long ldz, const long long* __restrict__ dinds,
+                                                           const double* __restrict__ z1, long long nd, long long R) {
+  const long long total = nd * R;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+    const long long r = t / nd, j = t - r * nd;
+    Z[dinds[j] + r * ldz] = z1[j];
+  }
+}
+
+// dst[i + r*ldd] = (i < rows && r < cols) ? src[i + r*lds] : 0   for i < rows_pad, r < cols_pad
+__global__ void __launch_bounds__(256) pad_copy_kernel(double* __restrict__ dst, long long ldd, long long rows_pad, long long cols_pad,
+                                                       const double* __restrict__ src, long long lds, long long rows, long long cols) {
+  const long long total = rows_pad * cols_pad;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+    const long long r = t / rows_pad, i = t - r * rows_pad;
+    dst[i + r * ldd] = (i < rows && r < cols) ? src[i + r * lds] : 0.0;
+  }
+}
+
+namespace {
+
+struct LuDev {
+  DevCtx* dc = nullptr;
+  DevBuf A;       // Np x Np joint matrix -> L
+  DevBuf invD;    // inverses of the diagonal 128-blocks
+  DevBuf d2;      // Ns_pad
+  DevBuf sinds;   // Ns (0-based)
+  DevBuf dinds;   // Nd (0-based)
+  DevBuf z1;      // Nd
+  DevBuf info;
+  // sampling scratch (per chunk)
+  DevBuf Wp, W1p, Zc, Wraw, W1raw;
+  long long chunk_cols = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+inline unsigned grid_for(long long n, int sms) {
+  long long b = (n + 255) / 256;
+  if (b > (long long)sms * 16) b = (long long)sms * 16;
+  if (b < 1) b = 1;
+  return (unsigned)b;
+}
+
+}  // namespace
+}  // namespace gsp
+
+using namespace gsp;
+
+struct gsp_lu_plan {
+  gsp_ctx* ctx = nullptr;
+  long long N = 0, Nd = 0, Ns = 0, Ndp = 0, Nsp = 0, Np = 0;
+  double mu = 0.0;
+  std::vector<std::unique_ptr<LuDev>> dev;
+  std::mutex mu_lock;
+};
+
+namespace gsp {
+namespace {
+
+int ensure_chunk(gsp_ctx* ctx, gsp_lu_plan* p, LuDev* d, long long cols, bool need_w1) {
+  const long long cpad = round_up(cols, 128);
+  if (d->chunk_cols < cpad) {
+    GSP_CUDA_OK(ctx, d->Wp.alloc(d->dc->dev, (size_t)p->Nsp * cpad * sizeof(double)));
+    GSP_CUDA_OK(ctx, d->Zc.alloc(d->dc->dev, (size_t)p->N * cpad * sizeof(double)));
+    GSP_CUDA_OK(ctx, d->Wraw.alloc(d->dc->dev, (size_t)p->Ns * cpad * sizeof(double)));
+    d->W1p.release();
+    d->W1raw.release();
+    d->chunk_cols = cpad;
+  }
+  if (need_w1 && !d->W1p.p) {
+    GSP_CUDA_OK(ctx, d->W1p.alloc(d->dc->dev, (size_t)p->Nsp * d->chunk_cols * sizeof(double)));
+    GSP_CUDA_OK(ctx, d->W1raw.alloc(d->dc->dev, (size_t)p->Ns * d->chunk_cols * sizeof(double)));
+  }
+  return GSP_OK;
+}
+
+// Build padded noise Wp (Nsp x cpad) for `cols` realizations starting at absolute index `real0`.
+// src: device pointer (ld = lds) or NULL => Philox stream `stream`.
+int stage_noise(gsp_ctx* ctx, gsp_lu_plan* p, LuDev* d, double* Wp, const double* src, long long lds, long long cols, long long cpad,
+                unsigned long long seed, unsigned stream, long long real0) {
+  cudaStream_t st = d->dc->stream;
+  if (src) {
+    GSP_LAUNCH(pad_copy_kernel, dim3(grid_for(p->Nsp * cpad, d->dc->sms)), dim3(256), 0, st, Wp, p->Nsp, p->Nsp, cpad, src, lds, p->Ns, cols);
+    g_launches++;
+  } else {
+    GSP_CUDA_OK(ctx, cudaMemsetAsync(Wp, 0, (size_t)p->Nsp * cpad * sizeof(double), st));
+    GSP_CUDA_OK(ctx, launch_rng_fill(st, d->dc->sms, Wp, p->Ns, p->Nsp, cols, seed, stream, (unsigned long long)real0, true));
+  }
+  GSP_CUDA_OK(ctx, cudaGetLastError());
+  return GSP_OK;
+}
+
+// all-device-pointer core: `cols` realizations into Z (ldz), on device d
+int sample_core(gsp_ctx* ctx, gsp_lu_plan* p, LuDev* d, long long cols, const double* W, long long ldw, unsigned long long seed,
+                int stream, long long real0, double rho, const double* W1, double* Z, long long ldz) {
+  const bool mix = !std::isnan(rho);
+  const long long cpad = round_up(cols, 128);
+  cudaStream_t st = d->dc->stream;
+  double* Wp = d->Wp.as<double>();
+  GSP_TRY(stage_noise(ctx, p, d, Wp, W, ldw, cols, cpad, seed, (unsigned)stream, real0));
+  if (mix) {
+    double* W1p = d->W1p.as<double>();
+    GSP_TRY(stage_noise(ctx, p, d, W1p, W1, ldw, cols, cpad, seed, 0u, real0));
+    const long long n = p->Nsp * cpad;
+    GSP_LAUNCH(premix_kernel, dim3(grid_for(n, d->dc->sms)), dim3(256), 0, st, Wp, (const double*)W1p, n, rho, std::sqrt(1.0 - rho * rho));
+    g_launches++;
+    GSP_CUDA_OK(ctx, cudaGetLastError());
+  }
+  const double* L22 = d->A.as<double>() + p->Ndp * (p->Np + 1);
+  const double addmu = (p->Nd == 0) ? p->mu : 0.0;  // lusim.jl:172
+  GSP_CUDA_OK(ctx, sample_gemm(st, L22, p->Np, (int)(p->Nsp / 128), Wp, p->Nsp, (int)(cpad / 128), Z, ldz, d->d2.as<double>(),
+                               d->sinds.as<long long>(), addmu, p->Ns, cols));
+  if (p->Nd > 0) {
+    GSP_LAUNCH(scatter_data_kernel, dim3(grid_for(p->Nd * cols, d->dc->sms)), dim3(256), 0, st, Z, ldz, (const long long*)d->dinds.as<long long>(),
+               (const double*)d->z1.as<double>(), p->Nd, cols);
+    g_launches++;
+    GSP_CUDA_OK(ctx, cudaGetLastError());
+  }
+  return GSP_OK;
+}
+
+}  // namespace
+}  // namespace gsp
+
+extern "C" int gsp_lu_plan_create(gsp_ctx* ctx, const gsp_cov_model* cov, const gsp_domain* dom, int64_t nd, const int64_t* dinds,
+                                  const double* z1, double mu, gsp_lu_plan** out) {
+  if (!ctx) return -1;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (!out) return set_err(ctx, -8, "out is NULL");
+  *out = nullptr;
+  DomDev dd;
+  GSP_TRY(make_dom_dev(ctx, dom, 3, &dd));
+  CovDev cd;
+  GSP_TRY(make_cov_dev(ctx, cov, dom->dim, 2, &cd));
+  const long long N = dd.nelems;
+  if (nd < 0 || nd >= N) return set_err(ctx, -4, "nd must satisfy 0 <= nd < nelems");
+  if (nd > 0 && (!dinds || !z1)) return set_err(ctx, nd > 0 && !dinds ? -5 : -6, "dinds / z1 is NULL");
+  for (long long j = 0; j < nd; ++j) {
+    if (dinds[j] < 1 || dinds[j] > N) return set_err(ctx, -5, "dinds out of range (1-based)");
+    if (j > 0 && dinds[j] <= dinds[j - 1]) return set_err(ctx, -5, "dinds must be strictly ascending (findall(mask))");
+  }
+  std::unique_ptr<gsp_lu_plan> p(new gsp_lu_plan);
+  p->ctx = ctx;
+  p->N = N;
+  p->Nd = nd;
+  p->Ns = N - nd;
+  p->Ndp = round_up(nd, 128);
+  p->Nsp = round_up(p->Ns, 128);
+  p->Np = p->Ndp + p->Nsp;
+  p->mu = mu;
+
+  // host index maps (0-based): perm = [dinds; pad; sinds; pad]
+  std::vector<long long> perm((size_t)p->Np, -1), sinds((size_t)p->Ns), dind0((size_t)nd);
+  {
+    long long j = 0, s = 0;
+    for (long long e = 0; e < N; ++e) {
+      if (j < nd && dinds[j] - 1 == e) {
+        dind0[(size_t)j] = e;
+        perm[(size_t)j] = e;
+        ++j;
+      } else {
+        sinds[(size_t)s] = e;
+        perm[(size_t)(p->Ndp + s)] = e;
+        ++s;
+      }
+    }
+  }
+
+  // device 0 builds the factor
+  std::unique_ptr<LuDev> d(new LuDev);
+  d->dc = &ctx->devs[0];
+  DevCtx& dc = *d->dc;
+  cudaSetDevice(dc.dev);
+  cudaStream_t st = dc.stream;
+  DevBuf dperm, dcoords, y;
+  GSP_CUDA_OK(ctx, d->A.alloc(dc.dev, (size_t)p->Np * p->Np * sizeof(double)));
+  GSP_CUDA_OK(ctx, d->invD.alloc(dc.dev, (size_t)(p->Np / 128) * 128 * 128 * sizeof(double)));
+  GSP_CUDA_OK(ctx, d->d2.alloc(dc.dev, (size_t)p->Nsp * sizeof(double)));
+  GSP_CUDA_OK(ctx, d->sinds.alloc(dc.dev, (size_t)p->Ns * sizeof(long long)));
+  GSP_CUDA_OK(ctx, d->dinds.alloc(dc.dev, (size_t)std::max<long long>(nd, 1) * sizeof(long long)));
+  GSP_CUDA_OK(ctx, d->z1.alloc(dc.dev, (size_t)std::max<long long>(nd, 1) * sizeof(double)));
+  GSP_CUDA_OK(ctx, d->info.alloc(dc.dev, sizeof(int)));
+  GSP_CUDA_OK(ctx, dperm.alloc(dc.dev, (size_t)p->Np * sizeof(long long)));
+  GSP_CUDA_OK(ctx, cudaEventCreate(&d->ev0));
+  GSP_CUDA_OK(ctx, cudaEventCreate(&d->ev1));
+  GSP_CUDA_OK(ctx, cudaMemcpyAsync(dperm.p, perm.data(), perm.size() * sizeof(long long), cudaMemcpyHostToDevice, st));
+  GSP_CUDA_OK(ctx, cudaMemcpyAsync(d->sinds.p, sinds.data(), sinds.size() * sizeof(long long), cudaMemcpyHostToDevice, st));
+  if (nd > 0) {
+    GSP_CUDA_OK(ctx, cudaMemcpyAsync(d->dinds.p, dind0.data(), dind0.size() * sizeof(long long), cudaMemcpyHostToDevice, st));
+    GSP_CUDA_OK(ctx, cudaMemcpyAsync(d->z1.p, z1, (size_t)nd * sizeof(double), cudaMemcpyHostToDevice, st));
+  }
+  if (dd.kind == 0) {
+    GSP_CUDA_OK(ctx, dcoords.alloc(dc.dev, (size_t)N * dd.dim * sizeof(double)));
+    GSP_CUDA_OK(ctx, cudaMemcpyAsync(dcoords.p, dom->coords, (size_t)N * dd.dim * sizeof(double), cudaMemcpyHostToDevice, st));
+    dd.coords = dcoords.as<double>();
+  }
+  // a1: joint covariance, lower tiles only (lusim.jl:88,95,96)
+  launch_assemble(st, cd, dd, dd, dperm.as<long long>(), dperm.as<long long>(), p->Np, p->Np, d->A.as<double>(), p->Np, true);
+  GSP_CUDA_OK(ctx, cudaGetLastError());
+  // a2/a3: one joint Cholesky (lusim.jl:92 or 98-103)
+  GSP_CUDA_OK(ctx, chol_factor(st, d->A.as<double>(), p->Np, (int)(p->Np / 128), d->invD.as<double>(), d->info.as<int>()));
+  // d2 = A21 * (L11 \ z1)   (lusim.jl:102); zero when unconditional (lusim.jl:91)
+  GSP_CUDA_OK(ctx, cudaMemsetAsync(d->d2.p, 0, (size_t)p->Nsp * sizeof(double), st));
+  if (nd > 0) {
+    GSP_CUDA_OK(ctx, y.alloc(dc.dev, (size_t)p->Ndp * sizeof(double)));
+    GSP_CUDA_OK(ctx, cudaMemsetAsync(y.p, 0, (size_t)p->Ndp * sizeof(double), st));
+    GSP_CUDA_OK(ctx, cudaMemcpyAsync(y.p, z1, (size_t)nd * sizeof(double), cudaMemcpyHostToDevice, st));
+    GSP_CUDA_OK(ctx, chol_forward_solve(st, d->A.as<double>(), p->Np, d->invD.as<double>(), (int)(p->Ndp / 128), y.as<double>()));
+    GSP_CUDA_OK(ctx, chol_gemv_rows(st, d->A.as<double>(), p->Np, p->Ndp, p->Nsp, (int)p->Ndp, y.as<double>(), d->d2.as<double>()));
+  }
+  int info = 0;
+  GSP_CUDA_OK(ctx, cudaMemcpyAsync(&info, d->info.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  GSP_CUDA_OK(ctx, cudaStreamSynchronize(st));
+  if (info > 0) {
+    // map the padded position back to the reference ordering [dinds; sinds] (1-based)
+    long long pos = info - 1;
+    long long ref = pos < p->Ndp ? pos + 1 : (pos - p->Ndp) + nd + 1;
+    set_err(ctx, (int)ref, "matrix is not positive definite (PosDefException)");
+    return (int)ref;
+  }
+  p->dev.push_back(std::move(d));
+
+  // other devices receive L, d2 and the index maps (realizations are sharded, the factor is not)
+  for (size_t i = 1; i < ctx->devs.size(); ++i) {
+    std::unique_ptr<LuDev> e(new LuDev);
+    e->dc = &ctx->devs[i];
+    LuDev* s0 = p->dev[0].get();
+    cudaSetDevice(e->dc->dev);
+    GSP_CUDA_OK(ctx, e->A.alloc(e->dc->dev, s0->A.bytes));
+    GSP_CUDA_OK(ctx, e->d2.alloc(e->dc->dev, s0->d2.bytes));
+    GSP_CUDA_OK(ctx, e->sinds.alloc(e->dc->dev, s0->sinds.bytes));
+    GSP_CUDA_OK(ctx, e->dinds.alloc(e->dc->dev, s0->dinds.bytes));
+    GSP_CUDA_OK(ctx, e->z1.alloc(e->dc->dev, s0->z1.bytes));
+    GSP_CUDA_OK(ctx, cudaEventCreate(&e->ev0));
+    GSP_CUDA_OK(ctx, cudaEventCreate(&e->ev1));
+    GSP_CUDA_OK(ctx, cudaMemcpyPeerAsync(e->A.p, e->dc->dev, s0->A.p, s0->dc->dev, s0->A.bytes, e->dc->stream));
+    GSP_CUDA_OK(ctx, cudaMemcpyPeerAsync(e->d2.p, e->dc->dev, s0->d2.p, s0->dc->dev, s0->d2.bytes, e->dc->stream));
+    GSP_CUDA_OK(ctx, cudaMemcpyPeerAsync(e->sinds.p, e->dc->dev, s0->sinds.p, s0->dc->dev, s0->sinds.bytes, e->dc->stream));
+    GSP_CUDA_OK(ctx, cudaMemcpyPeerAsync(e->dinds.p, e->dc->dev, s0->dinds.p, s0->dc->dev, s0->dinds.bytes, e->dc->stream));
+    GSP_CUDA_OK(ctx, cudaMemcpyPeerAsync(e->z1.p, e->dc->dev, s0->z1.p, s0->dc->dev, s0->z1.bytes, e->dc->stream));
+    GSP_CUDA_OK(ctx, cudaStreamSynchronize(e->dc->stream));
+    p->dev.push_back(std::move(e));
+  }
+  *out = p.release();
+  return GSP_OK;
+}
+
+extern "C" int gsp_lu_plan_destroy(gsp_lu_plan* p) {
+  if (!p) return GSP_OK;
+  for (auto& d : p->dev) {
+    cudaSetDevice(d->dc->dev);
+    cudaStreamSynchronize(d->dc->stream);
+    if (d->ev0) cudaEventDestroy(d->ev0);
+    if (d->ev1) cudaEventDestroy(d->ev1);
+  }
+  delete p;
+  return GSP_OK;
+}
+
+extern "C" int gsp_lu_plan_sizes(gsp_lu_plan* p, int64_t sizes[3]) {
+  if (!p || !sizes) return -1;
+  sizes[0] = p->N;
+  sizes[1] = p->Nd;
+  sizes[2] = p->Ns;
+  return GSP_OK;
+}
+
+extern "C" int gsp_lu_plan_get(gsp_lu_plan* p, double* d2, double* L22) {
+  if (!p) return -1;
+  gsp_ctx* ctx = p->ctx;
+  std::lock_guard<std::mutex> lk(p->mu_lock);
+  LuDev* d = p->dev[0].get();
+  cudaSetDevice(d->dc->dev);
+  cudaStream_t st = d->dc->stream;
+  if (d2) GSP_CUDA_OK(ctx, cudaMemcpyAsync(d2, d->d2.p, (size_t)p->Ns * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (L22) {
+    const double* src = d->A.as<double>() + p->Ndp * (p->Np + 1);
+    GSP_CUDA_OK(ctx, cudaMemcpy2DAsync(L22, (size_t)p->Ns * sizeof(double), src, (size_t)p->Np * sizeof(double), (size_t)p->Ns * sizeof(double),
+                                       (size_t)p->Ns, cudaMemcpyDeviceToHost, st));
+  }
+  GSP_CUDA_OK(ctx, cudaStreamSynchronize(st));
+  if (L22)  // strict upper triangle of off-diagonal tiles was never written: report zeros like `.L`
+    for (long long j = 0; j < p->Ns; ++j)
+      for (long long i = 0; i < j; ++i) L22[(size_t)j * p->Ns + i] = 0.0;
+  return GSP_OK;
+}
+
+extern "C" int gsp_lu_sample_dev(gsp_lu_plan* p, int64_t R, const double* W, int64_t ldw, uint64_t seed, int32_t stream,
+                                 int64_t first_real, double rho, const double* W1, double* Z, int64_t ldz) {
+  if (!p) return -1;
+  gsp_ctx* ctx = p->ctx;
+  std::lock_guard<std::mutex> lk(p->mu_lock);
+  if (R < 0) return set_err(ctx, -2, "R < 0");
+  if (W && ldw < p->Ns) return set_err(ctx, -4, "ldw < Ns");
+  if (!Z || ldz < p->N) return set_err(ctx, -10, "Z is NULL or ldz < N");
+  const bool mix = !std::isnan(rho);
+  if (mix && !(rho >= -1.0 && rho <= 1.0)) return set_err(ctx, -8, "rho must be in [-1, 1] (or NaN for the first variable)");
+  if (mix && W && !W1) return set_err(ctx, -9, "W1 is required when W is given and rho is set");
+  LuDev* d = p->dev[0].get();
+  cudaSetDevice(d->dc->dev);
+  const long long chunk = std::min<long long>(std::max<long long>(R, 1), 1024);
+  GSP_TRY(ensure_chunk(ctx, p, d, chunk, mix));
+  GSP_CUDA_OK(ctx, cudaEventRecord(d->ev0, d->dc->stream));
+  for (long long c0 = 0; c0 < R; c0 += chunk) {
+    const long long cols = std::min(chunk, R - c0);
+    GSP_TRY(sample_core(ctx, p, d, cols, W ? W + c0 * ldw : nullptr, ldw, seed, stream, first_real + c0, rho,
+                        (mix && W1) ? W1 + c0 * ldw : nullptr, Z + c0 * ldz, ldz));
+  }
+  GSP_CUDA_OK(ctx, cudaEventRecord(d->ev1, d->dc->stream));
+  GSP_CUDA_OK(ctx, cudaStreamSynchronize(d->dc->stream));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, d->ev0, d->ev1);
+  ctx->last_sample_ms = ms;
+  return GSP_OK;
+}
+
+extern "C" int gsp_lu_sample(gsp_lu_plan* p, int64_t R, const double* W, uint64_t seed, int32_t stream, int64_t first_real,
+                             double rho, const double* W1, double* Z) {
+  if (!p) return -1;
+  gsp_ctx* ctx = p->ctx;
+  std::lock_guard<std::mutex> lk(p->mu_lock);
+  if (R < 0) return set_err(ctx, -2, "R < 0");
+  if (!Z) return set_err(ctx, -9, "Z is NULL");
+  const bool mix = !std::isnan(rho);
+  if (mix && !(rho >= -1.0 && rho <= 1.0)) return set_err(ctx, -7, "rho must be in [-1, 1] (or NaN for the first variable)");
+  if (mix && W && !W1) return set_err(ctx, -8, "W1 is required when W is given and rho is set");
+  const int ndev = (int)p->dev.size();
+  std::vector<long long> r0(ndev + 1, 0);
+  for (int i = 0; i < ndev; ++i) r0[i + 1] = r0[i] + (R / ndev) + (i < R % ndev ? 1 : 0);
+  long long maxshard = 0;
+  for (int i = 0; i < ndev; ++i) maxshard = std::max(maxshard, r0[i + 1] - r0[i]);
+  const long long chunk = std::min<long long>(std::max<long long>(maxshard, 1), 512);
+  for (int i = 0; i < ndev; ++i) {
+    cudaSetDevice(p->dev[i]->dc->dev);
+    GSP_TRY(ensure_chunk(ctx, p, p->dev[i].get(), chunk, mix));
+  }
+  {
+    LuDev* d0 = p->dev[0].get();
+    cudaSetDevice(d0->dc->dev);
+    cudaEventRecord(d0->ev0, d0->dc->stream);
+  }
+  int rc = GSP_OK;
+  // chunks are issued round-robin over the devices; each device runs H2D -> compute -> D2H in stream order
+  for (long long c0 = 0; c0 < maxshard && rc == GSP_OK; c0 += chunk) {
+    for (int i = 0; i < ndev && rc == GSP_OK; ++i) {
+      const long long nloc = r0[i + 1] - r0[i];
+      if (c0 >= nloc) continue;
+      LuDev* d = p->dev[i].get();
+      cudaSetDevice(d->dc->dev);
+      cudaStream_t st = d->dc->stream;
+      const long long cols = std::min(chunk, nloc - c0);
+      const long long ra = r0[i] + c0;  // absolute first realization of this chunk
+      const double* Wd = nullptr;
+      const double* W1d = nullptr;
+      cudaError_t e = cudaSuccess;
+      if (W) {
+        e = cudaMemcpyAsync(d->Wraw.p, W + ra * p->Ns, (size_t)p->Ns * cols * sizeof(double), cudaMemcpyHostToDevice, st);
+        Wd = d->Wraw.as<double>();
+        if (e == cudaSuccess && mix) {
+          e = cudaMemcpyAsync(d->W1raw.p, W1 + ra * p->Ns, (size_t)p->Ns * cols * sizeof(double), cudaMemcpyHostToDevice, st);
+          W1d = d->W1raw.as<double>();
+        }
+      }
+      if (e != cudaSuccess) { rc = set_err(ctx, GSP_E_CUDA, cudaGetErrorString(e)); break; }
+      rc = sample_core(ctx, p, d, cols, Wd, p->Ns, seed, stream, first_real + ra, rho, W1d, d->Zc.as<double>(), p->N);
+      if (rc != GSP_OK) break;
+      e = cudaMemcpyAsync(Z + ra * p->N, d->Zc.p, (size_t)p->N * cols * sizeof(double), cudaMemcpyDeviceToHost, st);
+      if (e != cudaSuccess) { rc = set_err(ctx, GSP_E_CUDA, cudaGetErrorString(e)); break; }
+    }
+  }
+  {
+    LuDev* d0 = p->dev[0].get();
+    cudaSetDevice(d0->dc->dev);
+    cudaEventRecord(d0->ev1, d0->dc->stream);
+  }
+  for (int i = 0; i < ndev; ++i) {
+    cudaSetDevice(p->dev[i]->dc->dev);
+    cudaError_t e = cudaStreamSynchronize(p->dev[i]->dc->stream);
+    if (rc == GSP_OK && e != cudaSuccess) rc = set_err(ctx, GSP_E_CUDA, std::string("lu_sample: ") + cudaGetErrorString(e));
+  }
+  if (rc == GSP_OK) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, p->dev[0]->ev0, p->dev[0]->ev1);
+    ctx->last_sample_ms = ms;
+  }
+  return rc;
+}

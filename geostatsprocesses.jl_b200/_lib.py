@@ -73,6 +73,8 @@ SIGNATURES = {
     "gsp_fft_plan_get": (C.c_int, [_vp, _vp]),
     "gsp_fft_sample": (C.c_int, [_vp, C.c_int64, _vp, C.c_uint64, C.c_int64, C.c_double, C.c_double, C.c_int64, _vp, _vp]),
     "gsp_fft_sample_dev": (C.c_int, [_vp, C.c_int64, _vp, C.c_uint64, C.c_int64, C.c_double, C.c_double, C.c_int64, _vp, _vp]),
+    "gsp_profile_enable": (C.c_int, [_vp, C.c_int32]),
+    "gsp_profile_read": (C.c_int64, [_vp, C.c_char_p, C.c_int64]),
     "gsp_kernel_launches": (C.c_int64, []),
     "gsp_last_sample_ms": (C.c_double, [_vp]),
 }
@@ -172,6 +174,17 @@ class Library:
 
     def kernel_launches(self) -> int:
         return int(self.lib.gsp_kernel_launches())
+
+    def profile_enable(self, on: bool = True):
+        self.check(self.lib.gsp_profile_enable(self.ctx, 1 if on else 0))
+
+    def profile_read(self) -> dict:
+        import json
+        buf = C.create_string_buffer(1 << 16)
+        n = self.lib.gsp_profile_read(self.ctx, buf, len(buf))
+        if n < 0:
+            raise GspError(int(n), "profile buffer too small")
+        return json.loads(buf.value.decode())
 
     def last_sample_ms(self) -> float:
         return float(self.lib.gsp_last_sample_ms(self.ctx))

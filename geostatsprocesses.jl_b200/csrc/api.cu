@@ -1,5 +1,6 @@
 // Context management, argument marshalling and the small standalone entry points of the C ABI.
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 
 #include "chol.h"
@@ -8,6 +9,29 @@
 namespace gsp {
 
 long long g_launches = 0;
+Prof g_prof;
+
+void Prof::add(const std::string& n, double ms) {
+  for (auto& a : acc)
+    if (a.first == n) {
+      a.second.first += ms;
+      a.second.second += 1;
+      return;
+    }
+  acc.push_back({n, {ms, 1}});
+}
+
+void Prof::flush() {
+  for (auto& p : pending) {
+    cudaEventSynchronize(p.e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, p.e0, p.e1);
+    add(p.name, ms);
+    cudaEventDestroy(p.e0);
+    cudaEventDestroy(p.e1);
+  }
+  pending.clear();
+}
 
 int set_err(gsp_ctx* ctx, int code, const std::string& msg) {
   if (ctx) ctx->err = msg;
@@ -132,6 +156,34 @@ extern "C" const char* gsp_last_error(gsp_ctx* ctx) { return ctx ? ctx->err.c_st
 extern "C" int gsp_ctx_ndev(gsp_ctx* ctx) { return ctx ? (int)ctx->devs.size() : 0; }
 extern "C" int64_t gsp_kernel_launches(void) { return g_launches; }
 extern "C" double gsp_last_sample_ms(gsp_ctx* ctx) { return ctx ? ctx->last_sample_ms : 0.0; }
+
+extern "C" int gsp_profile_enable(gsp_ctx* ctx, int32_t on) {
+  if (!ctx) return -1;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  g_prof.flush();
+  g_prof.on = on != 0;
+  if (on) g_prof.acc.clear();
+  return GSP_OK;
+}
+
+extern "C" int64_t gsp_profile_read(gsp_ctx* ctx, char* buf, int64_t buflen) {
+  if (!ctx || !buf || buflen < 2) return -1;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  g_prof.flush();
+  std::string js = "{";
+  bool first = true;
+  for (auto& a : g_prof.acc) {
+    char tmp[256];
+    snprintf(tmp, sizeof(tmp), "%s\"%s\": {\"ms\": %.6f, \"launches\": %lld}", first ? "" : ", ", a.first.c_str(), a.second.first,
+             a.second.second);
+    js += tmp;
+    first = false;
+  }
+  js += "}";
+  if ((int64_t)js.size() + 1 > buflen) return -(int64_t)js.size() - 1;
+  std::memcpy(buf, js.c_str(), js.size() + 1);
+  return (int64_t)js.size();
+}
 
 extern "C" int gsp_host_alloc(void** out, int64_t bytes) {
   if (!out || bytes < 0) return -1;

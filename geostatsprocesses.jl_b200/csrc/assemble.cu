@@ -68,6 +68,7 @@ void launch_assemble(cudaStream_t st, const CovDev& m, const DomDev& drow, const
                      const long long* colmap, long long nrow, long long ncol, double* out, long long ld, bool lower_only) {
   dim3 grid((unsigned)((nrow + AT - 1) / AT), (unsigned)((ncol + AT - 1) / AT));
   int vec_ok = (ld % 2 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  ProfScope prof_("assemble", st);
   GSP_LAUNCH(assemble_kernel, grid, dim3(256), 0, st, m, drow, dcol, rowmap, colmap, nrow, ncol, out, ld, lower_only ? 1 : 0,
              vec_ok);
   g_launches++;
@@ -88,6 +89,7 @@ __global__ void __launch_bounds__(256) cov_to_center_kernel(CovDev m, DomDev d, 
 void launch_cov_to_center(cudaStream_t st, int sms, const CovDev& m, const DomDev& d, long long eref, double* out) {
   long long blocks = (d.nelems + 255) / 256;
   if (blocks > (long long)sms * 16) blocks = (long long)sms * 16;
+  ProfScope prof_("cov_to_center", st);
   GSP_LAUNCH(cov_to_center_kernel, dim3((unsigned)blocks), dim3(256), 0, st, m, d, eref, out);
   g_launches++;
 }

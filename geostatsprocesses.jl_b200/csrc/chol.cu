@@ -232,6 +232,7 @@ struct Chol {
     if (n == 1) {
       auto kfn = potrf_diag_kernel;
       check(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM));
+      ProfScope prof_("potrf_diag", st);
       GSP_LAUNCH(kfn, dim3(1), dim3(256), (size_t)DIAG_SMEM, st, A, ld, (long long)o, invD, info);
       g_launches++;
       check(cudaGetLastError());
@@ -262,6 +263,7 @@ cudaError_t chol_factor(cudaStream_t st, double* A, long long ld, int nblocks, d
 
 cudaError_t chol_forward_solve(cudaStream_t st, const double* L, long long ld, const double* invD, int nblocks, double* z) {
   if (nblocks <= 0) return cudaSuccess;
+  ProfScope prof_("trsv_blocks", st);
   GSP_LAUNCH(trsv_blocks_kernel, dim3(1), dim3(256), 0, st, L, ld, invD, nblocks, z);
   g_launches++;
   return cudaGetLastError();
@@ -270,6 +272,7 @@ cudaError_t chol_forward_solve(cudaStream_t st, const double* L, long long ld, c
 cudaError_t chol_gemv_rows(cudaStream_t st, const double* L, long long ld, long long row0, long long nrows, int kn,
                            const double* y, double* out) {
   if (nrows <= 0) return cudaSuccess;
+  ProfScope prof_("gemv_rows", st);
   GSP_LAUNCH(gemv_rows_kernel, dim3((unsigned)((nrows + 255) / 256)), dim3(256), 0, st, L, ld, row0, nrows, kn, y, out);
   g_launches++;
   return cudaGetLastError();

@@ -2,6 +2,7 @@
 #pragma once
 #include <mutex>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/gsp_b200.h"
@@ -10,6 +11,36 @@
 namespace gsp {
 
 extern long long g_launches;  // kernels launched by this library (gsp_kernel_launches)
+
+// Optional per-kernel-class timing with CUDA events on the launching stream (gsp_profile_enable).
+// Off by default: the timed paths carry no events besides the per-call pair.
+struct Prof {
+  struct Pending { std::string name; cudaEvent_t e0, e1; };
+  bool on = false;
+  std::vector<Pending> pending;
+  std::vector<std::pair<std::string, std::pair<double, long long>>> acc;  // name -> (ms, launches)
+  void add(const std::string& n, double ms);
+  void flush();
+};
+extern Prof g_prof;
+struct ProfScope {
+  cudaStream_t st;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  const char* name;
+  ProfScope(const char* n, cudaStream_t s) : st(s), name(n) {
+    if (g_prof.on) {
+      cudaEventCreate(&e0);
+      cudaEventCreate(&e1);
+      cudaEventRecord(e0, st);
+    }
+  }
+  ~ProfScope() {
+    if (e0) {
+      cudaEventRecord(e1, st);
+      g_prof.pending.push_back({name, e0, e1});
+    }
+  }
+};
 
 struct DevCtx {
   int dev = 0;

@@ -344,6 +344,7 @@ cudaError_t run_xfwd(FftDev* d, gsp_fft_plan* p, const double* in, cplx* H) {
   auto kfn = xpass_fwd_kernel;
   cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.smem);
   if (e != cudaSuccess) return e;
+  ProfScope prof_("fft_xpass_fwd", d->dc->stream);
   GSP_LAUNCH(kfn, dim3((unsigned)((nrows + a.B - 1) / a.B)), dim3(256), a.smem, d->dc->stream, a.lp, (int)p->dims[0], p->hx, nrows,
              a.B, a.packed, in, H);
   g_launches++;
@@ -356,6 +357,7 @@ cudaError_t run_xinv(FftDev* d, gsp_fft_plan* p, const cplx* H, double* out, dou
   auto kfn = xpass_inv_kernel;
   cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.smem);
   if (e != cudaSuccess) return e;
+  ProfScope prof_("fft_xpass_inv", d->dc->stream);
   GSP_LAUNCH(kfn, dim3((unsigned)((nrows + a.B - 1) / a.B)), dim3(256), a.smem, d->dc->stream, a.lp, (int)p->dims[0], p->hx, nrows,
              a.B, a.packed, H, out, scale, mu);
   g_launches++;
@@ -379,6 +381,8 @@ cudaError_t run_strided(FftDev* d, gsp_fft_plan* p, int axis, cplx* H, int flags
   cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.smem);
   if (e != cudaSuccess) return e;
   dim3 grid((unsigned)((hx + a.B - 1) / a.B), (unsigned)nother);
+  ProfScope prof_((flags & PASS_MUL) ? "fft_strided_fwd_mul_inv" : ((flags & PASS_FWD) ? "fft_strided_fwd" : "fft_strided_inv"),
+                  d->dc->stream);
   GSP_LAUNCH(kfn, grid, dim3(256), a.smem, d->dc->stream, a.lp, H, es, (int)hx, a.B, other_stride, flags, Fh, s);
   g_launches++;
   return cudaGetLastError();

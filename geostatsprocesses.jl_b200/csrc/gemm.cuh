@@ -186,6 +186,7 @@ inline cudaError_t launch_gemm(cudaStream_t st, const GemmArgs& g) {
   if (e != cudaSuccess) return e;
   long long tiles = g.tri ? (long long)g.mt * (g.mt + 1) / 2 : (long long)g.mt * g.nt;
   if (tiles <= 0 || g.K <= 0) return cudaSuccess;
+  ProfScope prof_(MODE == GEMM_SAMPLE ? "gemm_dmma_sample" : (MODE == GEMM_SET ? "gemm_dmma_trsm" : "gemm_dmma_update"), st);
   GSP_LAUNCH(kfn, dim3((unsigned)tiles), dim3(G_THREADS), (size_t)G_SMEM_BYTES, st, g);
   g_launches++;
   return cudaGetLastError();

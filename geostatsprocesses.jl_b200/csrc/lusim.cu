@@ -110,6 +110,7 @@ int stage_noise(gsp_ctx* ctx, gsp_lu_plan* p, LuDev* d, double* Wp, const double
                 unsigned long long seed, unsigned stream, long long real0) {
   cudaStream_t st = d->dc->stream;
   if (src) {
+    ProfScope prof_("pad_copy", st);
     GSP_LAUNCH(pad_copy_kernel, dim3(grid_for(p->Nsp * cpad, d->dc->sms)), dim3(256), 0, st, Wp, p->Nsp, p->Nsp, cpad, src, lds, p->Ns, cols);
     g_launches++;
   } else {

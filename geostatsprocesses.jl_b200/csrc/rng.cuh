@@ -71,6 +71,7 @@ inline cudaError_t launch_rng_fill(cudaStream_t st, int sms, double* out, long l
   if (total <= 0) return cudaSuccess;
   long long blocks = (total + 255) / 256;
   if (blocks > (long long)sms * 32) blocks = (long long)sms * 32;
+  ProfScope prof_("rng_fill", st);
   GSP_LAUNCH(rng_fill_kernel, dim3((unsigned)blocks), dim3(256), 0, st, out, n, ld, R, seed, stream, first_real, normal ? 1 : 0);
   g_launches++;
   return cudaGetLastError();

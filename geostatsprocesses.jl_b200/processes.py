@@ -1,0 +1,304 @@
+"""Reference-facing host API for the GPU methods: GaussianProcess, LUSIM, FFTSIM, rand, Ensemble.
+
+Mirrors (same names, argument meaning and error behaviour):
+  src/processes/field/gaussian.jl:22-48   GaussianProcess, defaultschema
+  src/processes/field.jl:43-58            initialize
+  src/initialization/nearest.jl:12-34, explicit.jl:12-46   NearestInit / ExplicitInit
+  src/simulation/field.jl:47-124,152-166  rand, defaultsimulation
+  src/simulation/field/lusim.jl:38-126    LUSIM preprocess / randsingle (validity checks here, math on the GPU)
+  src/simulation/field/fftsim.jl:54-139   FFTSIM preprocess / randsingle (unconditional path)
+  src/ensembles.jl:10-85                  Ensemble
+Everything numerical is a call into libgspb200 through _lib.py; nothing here computes fields on the CPU.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Dict, Optional, Sequence, Union
+
+import numpy as np
+
+from . import _lib
+from .domains import CartesianGrid, GeoTable, GridView, PointSet, georef
+from .functions import GeoStatsFunction
+
+_default_library: Optional[_lib.Library] = None
+
+
+def default_library() -> _lib.Library:
+    """The process-wide CUDA library/context (device 0 unless `set_devices` was called)."""
+    global _default_library
+    if _default_library is None:
+        _default_library = _lib.Library()
+    return _default_library
+
+
+def set_devices(devices: Sequence[int]) -> _lib.Library:
+    """Use these CUDA ordinals for subsequent `rand` calls (realizations are sharded over them)."""
+    global _default_library
+    if _default_library is not None:
+        _default_library.close()
+    _default_library = _lib.Library(devices=list(devices))
+    return _default_library
+
+
+# ------------------------------------------------------------------ process
+class GaussianProcess:
+    """GaussianProcess(func, mean=0) - gaussian.jl:22-35."""
+
+    def __init__(self, func: GeoStatsFunction, mean=None):
+        nf = func.nvariables()
+        if mean is None:
+            mean = np.zeros(nf) if nf > 1 else 0.0
+        nm = np.size(mean)
+        assert nm == nf, f"mean must have {nf} components, received {nm}"
+        self.func = func
+        self.mean = mean
+
+    def mean_of(self, j: int) -> float:
+        return float(np.atleast_1d(self.mean)[j])
+
+    def defaultschema(self):
+        nv = self.func.nvariables()
+        return tuple(f"field{i + 1}" for i in range(nv)) if nv > 1 else ("field",)
+
+
+# ------------------------------------------------------------------ initialization
+class NearestInit:
+    """nearest.jl:10-34: each datum goes to the nearest element, later data overwrite, NaN = missing."""
+
+    def apply(self, real, mask, dom, data: GeoTable):
+        dcoords = data.domain.centroids()
+        for i in range(dcoords.shape[0]):
+            j = dom.nearest(dcoords[i])
+            for var in real:
+                v = data[var][i]
+                if v is not None and not (isinstance(v, float) and math.isnan(v)):
+                    real[var][j] = v
+                    mask[var][j] = True
+
+
+class ExplicitInit:
+    """explicit.jl:12-46 with 1-based `orig` / `dest` like the reference."""
+
+    def __init__(self, *args):
+        if len(args) == 1:
+            self.orig, self.dest = None, args[0]
+        else:
+            self.orig, self.dest = args
+
+    def apply(self, real, mask, dom, data: GeoTable):
+        dest = list(self.dest)
+        orig = list(range(1, data.domain.nelements() + 1)) if self.orig is None else list(self.orig)
+        assert len(orig) == len(dest), "invalid explicit initialization"
+        for i, j in zip(orig, dest):
+            for var in real:
+                v = data[var][i - 1]
+                if v is not None and not (isinstance(v, float) and math.isnan(v)):
+                    real[var][j - 1] = v
+                    mask[var][j - 1] = True
+
+
+def initialize(process: GaussianProcess, domain, data: Optional[GeoTable], init):
+    """field.jl:43-58 -> (real, mask) dicts keyed by variable name."""
+    names = process.defaultschema() if data is None else data.names()
+    n = domain.nelements()
+    real = {v: np.zeros(n) for v in names}
+    mask = {v: np.zeros(n, dtype=bool) for v in names}
+    if data is not None:
+        init.apply(real, mask, domain, data)
+    return real, mask
+
+
+# ------------------------------------------------------------------ methods
+class FieldSimulationMethod:
+    pass
+
+
+@dataclass
+class LUSIM(FieldSimulationMethod):
+    """GPU LUSIM (lusim.jl:36).  `library` selects the context (default: device 0)."""
+    library: Optional[_lib.Library] = None
+
+
+@dataclass
+class FFTSIM(FieldSimulationMethod):
+    """GPU FFTSIM (fftsim.jl:47-52); neighbour options only matter for conditional simulation."""
+    minneighbors: int = 1
+    maxneighbors: int = 26
+    neighborhood: object = None
+    distance: object = None
+    library: Optional[_lib.Library] = None
+
+
+def defaultsimulation(process: GaussianProcess, domain, data=None):
+    """field.jl:152-166 (SEQSIM is outside this engine's scope)."""
+    f = process.func
+    p = domain.parent()
+    if isinstance(p, CartesianGrid) and f.isstationary() and f.nvariables() == 1 and f.range() <= min(p.sides()) / 3 and data is None:
+        return FFTSIM()
+    if domain.nelements() < 100 * 100 and f.isstationary() and f.issymmetric() and f.isbanded():
+        return LUSIM()
+    raise NotImplementedError("the reference would pick SEQSIM here; this engine provides LUSIM and FFTSIM only - pass method=")
+
+
+def _domain_handle(domain):
+    if isinstance(domain, CartesianGrid):
+        return (_lib.make_grid_domain(domain.dims, domain.origin, domain.spacing), None)
+    return _lib.make_point_domain(domain.centroids())
+
+
+class _LUPre:
+    def __init__(self, plans, names, rho):
+        self.plans, self.names, self.rho = plans, names, rho
+
+
+def preprocess_lusim(process: GaussianProcess, method: LUSIM, init, domain, data) -> _LUPre:
+    """lusim.jl:38-110."""
+    f = process.func
+    if not (f.isstationary() and f.issymmetric() and f.isbanded()):
+        raise ValueError("LUSIM requires a geostatistical function that is stationary, symmetric and banded. "
+                         "Covariances or composite functions of covariances satisfy these properties.")
+    real, mask = initialize(process, domain, data, init)
+    names = tuple(real.keys())
+    assert len(names) == f.nvariables(), "incompatible number of variables for geostatistical function"
+    assert len(names) in (1, 2), "LUSIM only supports univariate and bivariate simulation"
+    lib = method.library or default_library()
+    dom = _domain_handle(domain)
+    plans = []
+    for j, var in enumerate(names):
+        dinds0 = np.flatnonzero(mask[var])
+        z1 = real[var][dinds0]
+        plans.append(_lib.LUPlan(lib, f.marginal(j), dom, dinds0 + 1 if len(dinds0) else None, z1 if len(dinds0) else None,
+                                 process.mean_of(j)))
+    if len(plans) == 2 and plans[0].Ns != plans[1].Ns:
+        raise ValueError("DimensionMismatch: both variables must have the same number of simulation nodes (lusim.jl:164)")
+    rho = f.rho() if len(names) == 2 else math.nan
+    return _LUPre(plans, names, rho)
+
+
+def rand_lusim(pre: _LUPre, nreals: int, rng, seed: int) -> Dict[str, np.ndarray]:
+    """randsingle + _lusim (lusim.jl:112-175) for all realizations at once.  Returns var -> (N, R) arrays."""
+    p1 = pre.plans[0]
+    out = {}
+    if rng is not None:
+        # the reference's draw order: per realization w1 (Ns normals), then w2 (lusim.jl:160, randsingle :114-119)
+        nv = len(pre.plans)
+        W = rng.standard_normal((nreals, nv, p1.Ns))
+        W1 = np.asfortranarray(W[:, 0, :].T)
+        out[pre.names[0]] = p1.sample(nreals, W1)
+        if nv == 2:
+            W2 = np.asfortranarray(W[:, 1, :].T)
+            out[pre.names[1]] = pre.plans[1].sample(nreals, W2, rho=pre.rho, W1=W1)
+    else:
+        out[pre.names[0]] = p1.sample(nreals, None, seed=seed, stream=0)
+        if len(pre.plans) == 2:
+            out[pre.names[1]] = pre.plans[1].sample(nreals, None, seed=seed, stream=1, rho=pre.rho)
+    return out
+
+
+class _FFTPre:
+    def __init__(self, plan, var, inds1, sill):
+        self.plan, self.var, self.inds1, self.sill = plan, var, inds1, sill
+
+
+def preprocess_fftsim(process: GaussianProcess, method: FFTSIM, init, domain, data) -> _FFTPre:
+    """fftsim.jl:54-107 (unconditional part)."""
+    f = process.func
+    assert f.isstationary(), "geostatistical function must be stationary"
+    real, mask = initialize(process, domain, data, init)
+    assert len(real) == 1, "FFTSIM does not support multivariate simulation"
+    var = next(iter(real))
+    grid = domain.parent()
+    if not isinstance(grid, CartesianGrid):
+        raise ValueError("FFTSIM requires a (view of a) CartesianGrid")
+    if data is not None:
+        raise NotImplementedError("conditional FFTSIM (Kriging of residuals, fftsim.jl:94-101,140-153) is not built yet; "
+                                  "use LUSIM for conditional simulation")
+    lib = method.library or default_library()
+    plan = _lib.FFTPlan(lib, f.flat(), grid.dims, grid.origin, grid.spacing)
+    return _FFTPre(plan, var, domain.parentindices(), float(f.sill()))
+
+
+def rand_fftsim(pre: _FFTPre, process: GaussianProcess, nreals: int, rng, seed: int) -> Dict[str, np.ndarray]:
+    """fftsim.jl:109-139 for all realizations.  Returns var -> (n, R)."""
+    w = None
+    if rng is not None:
+        w = rng.random((nreals, pre.plan.N))  # rand(rng, Float64, dims) per realization (fftsim.jl:124), column-major dims
+    Z = pre.plan.sample(nreals, w, seed=seed, sill=pre.sill, mu=process.mean_of(0), inds1=pre.inds1)
+    return {pre.var: Z.T}
+
+
+# ------------------------------------------------------------------ ensemble
+class Ensemble:
+    """ensembles.jl:10-85.  `reals[var]` is an (n, R) array; `e[i]` is the i-th realization (0-based) as a GeoTable."""
+
+    def __init__(self, domain, reals: Dict[str, np.ndarray]):
+        self.domain = domain
+        self.reals = reals
+
+    def __len__(self):
+        return next(iter(self.reals.values())).shape[1]
+
+    def __getitem__(self, i):
+        if isinstance(i, (list, tuple, np.ndarray, range)):
+            return [self[k] for k in i]
+        if i < 0 or i >= len(self):
+            raise IndexError(i)
+        return georef({v: a[:, i] for v, a in self.reals.items()}, self.domain)
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+    def variables(self):
+        return tuple(self.reals.keys())
+
+    def _reduce(self, fn):
+        return georef({v: fn(a) for v, a in self.reals.items()}, self.domain)
+
+    def mean(self):
+        return self._reduce(lambda a: a.mean(axis=1))
+
+    def var(self):
+        return self._reduce(lambda a: a.var(axis=1, ddof=1))
+
+    def cdf(self, x: float):
+        return self._reduce(lambda a: (a <= x).mean(axis=1))
+
+    def ccdf(self, x: float):
+        return self._reduce(lambda a: (a > x).mean(axis=1))
+
+    def quantile(self, p):
+        if np.ndim(p) > 0:
+            return [self.quantile(q) for q in p]
+        return self._reduce(lambda a: np.quantile(a, p, axis=1))
+
+    def __repr__(self):
+        return f"{self.domain.ndim}D Ensemble\n  domain:    {self.domain}\n  variables: {', '.join(self.variables())}\n  N° reals:  {len(self)}"
+
+
+def rand(process: GaussianProcess, domain, nreals: Optional[int] = None, *, rng: Union[None, int, np.random.Generator] = None,
+         data: Optional[GeoTable] = None, method: Optional[FieldSimulationMethod] = None, init=None):
+    """rand([rng], process, domain, [n]; data, method, init) - field.jl:47-124.
+
+    rng: a numpy Generator -> noise is drawn on the host in the reference's order and injected
+    (parity mode); None or an int seed -> on-device counter RNG (throughput mode).
+    Without `nreals` a single GeoTable is returned, with it an Ensemble."""
+    init = init or NearestInit()
+    smethod = method if method is not None else defaultsimulation(process, domain, data)
+    gen = rng if isinstance(rng, np.random.Generator) else None
+    seed = int(rng) if isinstance(rng, (int, np.integer)) else 0
+    n = 1 if nreals is None else int(nreals)
+    if isinstance(smethod, LUSIM):
+        pre = preprocess_lusim(process, smethod, init, domain, data)
+        reals = rand_lusim(pre, n, gen, seed)
+        for p in pre.plans:
+            p.close()
+    elif isinstance(smethod, FFTSIM):
+        pre = preprocess_fftsim(process, smethod, init, domain, data)
+        reals = rand_fftsim(pre, process, n, gen, seed)
+        pre.plan.close()
+    else:
+        raise TypeError(f"unsupported simulation method {smethod!r}")
+    ens = Ensemble(domain, reals)
+    return ens[0] if nreals is None else ens

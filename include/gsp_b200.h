@@ -148,6 +148,12 @@ int gsp_fft_sample(gsp_fft_plan* plan, int64_t R, const double* w, uint64_t seed
 int gsp_fft_sample_dev(gsp_fft_plan* plan, int64_t R, const double* w, uint64_t seed, int64_t first_real, double sill,
                        double mu, int64_t n_inds, const int64_t* inds_dev, double* out);
 
+/* Optional per-kernel-class device timing (CUDA events on the launching stream around every launch of
+ * this library).  Off by default.  gsp_profile_read writes a JSON object {"kernel": {"ms": total, "launches": n}, ...}
+ * accumulated since the last enable into buf and returns its length (or -needed if buflen is too small). */
+int gsp_profile_enable(gsp_ctx* ctx, int32_t on);
+int64_t gsp_profile_read(gsp_ctx* ctx, char* buf, int64_t buflen);
+
 /* counters for harnesses: kernels launched by this library in this process since load */
 int64_t gsp_kernel_launches(void);
 /* device-time (ms, CUDA events on the library's stream) of the last gsp_*_sample* call on device 0 */

@@ -1,0 +1,169 @@
+"""Kernel logic (index math, barrier structure, host orchestration) of the SAME .cu sources, executed by the
+test-only CPU emulator at toy sizes and compared with the oracle.  The real parity tests are -m gpu."""
+import math
+
+import numpy as np
+import pytest
+import scipy.linalg
+
+import gsp_b200 as gsp
+import gsp_oracle as O
+from helpers import aniso3, iso, ostructs, relerr
+
+TOL = 1e-9  # north_star tolerance (relative, normwise, Float64)
+
+
+def test_pairwise(emu_lib):
+    rng = np.random.default_rng(0)
+    st = iso(O.SPHERICAL, 0.8, 7.0, 2) + [(O.NUGGET, 0.2, np.eye(3))]
+    X1, X2 = rng.uniform(0, 30, (150, 2)), rng.uniform(0, 30, (71, 2))
+    assert relerr(emu_lib.pairwise(st, X1, X2), O.pairwise(ostructs(st), X1, X2)) < 1e-14
+    assert relerr(emu_lib.pairwise(st, X1), O.pairwise(ostructs(st), X1)) < 1e-14
+    for kind in (O.EXPONENTIAL, O.GAUSSIAN, O.CUBIC, O.PENTASPHERICAL):
+        st = aniso3(kind, 1.3, (9.0, 4.0, 2.0), 30.0)
+        X = rng.uniform(0, 12, (65, 3))
+        assert relerr(emu_lib.pairwise(st, X), O.pairwise(ostructs(st), X)) < 1e-14
+
+
+@pytest.mark.parametrize("n", [1, 7, 128, 200])
+def test_potrf(emu_lib, n):
+    rng = np.random.default_rng(n)
+    M = rng.standard_normal((n, n))
+    S = M @ M.T + n * np.eye(n)
+    L = emu_lib.potrf(S)
+    assert relerr(L, scipy.linalg.cholesky(S, lower=True)) < 1e-13
+    assert np.all(np.triu(L, 1) == 0.0)
+
+
+def _lu_case(lib, dims, nd, R, kind=O.SPHERICAL, rang=6.0, mu=0.7, points=False, seed=0):
+    rng = np.random.default_rng(seed)
+    ndim = len(dims)
+    st = iso(kind, 1.3, rang, ndim)
+    coords = O.grid_centroids(dims, [0.0] * ndim, [1.0] * ndim)
+    N = coords.shape[0]
+    dinds = np.sort(rng.choice(N, nd, replace=False)) if nd else np.zeros(0, dtype=np.int64)
+    z1 = rng.standard_normal(nd)
+    dom = gsp._lib.make_point_domain(coords) if points else (gsp._lib.make_grid_domain(dims, [0.0] * ndim, [1.0] * ndim), None)
+    plan = gsp.LUPlan(lib, st, dom, dinds + 1 if nd else None, z1 if nd else None, mu)
+    pre = O.lusim_preprocess(ostructs(st), coords, dinds, z1, mu)
+    d2, L22 = plan.get()
+    assert relerr(L22, pre.L22) < 1e-12
+    assert np.abs(d2 - pre.d2).max() < 1e-12
+    W = rng.standard_normal((plan.Ns, R))
+    Z = plan.sample(R, W)
+    assert relerr(Z, O.lusim_sample(pre, W)) < TOL
+    if nd:
+        assert np.array_equal(Z[dinds], np.repeat(z1[:, None], R, 1))  # data honoured exactly
+    W2 = rng.standard_normal((plan.Ns, R))
+    Z2 = plan.sample(R, W2, rho=0.7, W1=W)
+    assert relerr(Z2, O.lusim_sample(pre, W2, 0.7, W)) < TOL
+    plan.close()
+
+
+def test_lusim_unconditional(emu_lib):
+    _lu_case(emu_lib, (10, 10), 0, 5)
+
+
+def test_lusim_conditional_grid_and_points(emu_lib):
+    _lu_case(emu_lib, (10, 10), 7, 3, kind=O.EXPONENTIAL)
+    _lu_case(emu_lib, (20,), 3, 2, points=True)
+
+
+def test_lusim_multi_tile(emu_lib):
+    """more than one 128-block of data AND of realizations (tile boundaries, padded rows/cols)."""
+    _lu_case(emu_lib, (12, 12, 2), 140, 130, seed=3)
+
+
+def test_lusim_device_rng_reproducible_and_shard_invariant(emu_lib):
+    st = iso(O.SPHERICAL, 1.0, 4.0, 2)
+    dom = (gsp._lib.make_grid_domain((9, 7), (0, 0), (1, 1)), None)
+    plan = gsp.LUPlan(emu_lib, st, dom, None, None, 0.0)
+    Z = plan.sample(6, None, seed=42)
+    assert np.array_equal(Z, plan.sample(6, None, seed=42))
+    Zb = np.concatenate([plan.sample(2, None, seed=42, first_real=0), plan.sample(4, None, seed=42, first_real=2)], axis=1)
+    assert np.array_equal(Z, Zb)  # counter-based: independent of how realizations are split
+    assert not np.array_equal(Z, plan.sample(6, None, seed=43))
+    plan.close()
+
+
+@pytest.mark.parametrize("dims,kind", [((16,), O.SPHERICAL), ((30,), O.EXPONENTIAL), ((15,), O.SPHERICAL), ((16, 8), O.EXPONENTIAL),
+                                       ((10, 6), O.SPHERICAL), ((9, 5), O.SPHERICAL), ((8, 4, 6), O.EXPONENTIAL),
+                                       ((32, 16, 4), O.EXPONENTIAL), ((7, 6, 5), O.SPHERICAL), ((26, 22), O.SPHERICAL)])
+def test_fftsim(emu_lib, dims, kind):
+    rng = np.random.default_rng(len(dims))
+    nd = len(dims)
+    st = iso(kind, 1.7, 3.0, nd)
+    plan = gsp.FFTPlan(emu_lib, st, dims, [0.0] * nd, [1.0] * nd)
+    Fo = O.fftsim_preprocess(ostructs(st), dims, [0.0] * nd, [1.0] * nd)
+    assert relerr(plan.spectrum(), Fo) < 1e-12
+    N = int(np.prod(dims))
+    w = rng.random((2, N))
+    Z = plan.sample(2, w, sill=1.7, mu=0.3)
+    Zo = np.stack([O.fftsim_sample(Fo, w[r], 1.7, 0.3) for r in range(2)])
+    assert relerr(Z, Zo) < TOL
+    assert np.abs(Z.mean(axis=1) - 0.3).max() < 1e-12                       # DC bin zeroed (fftsim.jl:91)
+    assert np.abs(((Z - 0.3) ** 2).sum(axis=1) / (N - 1) - 1.7).max() < 1e-12  # var(mean=0), N-1 (fftsim.jl:131)
+    plan.close()
+
+
+def test_fftsim_view_subset_and_rng(emu_lib):
+    dims = (16, 8)
+    st = iso(O.SPHERICAL, 1.0, 3.0, 2)
+    plan = gsp.FFTPlan(emu_lib, st, dims, [0.0, 0.0], [1.0, 1.0])
+    w = np.random.default_rng(5).random((1, 128))
+    full = plan.sample(1, w, sill=1.0, mu=0.0)
+    inds1 = np.array([1, 5, 128, 64, 17])
+    sub = plan.sample(1, w, sill=1.0, mu=0.0, inds1=inds1)
+    assert np.array_equal(sub[0], full[0][inds1 - 1])  # Z[parentindices] after the full-grid variance scaling
+    a = plan.sample(3, None, seed=9)
+    b = np.concatenate([plan.sample(1, None, seed=9, first_real=0), plan.sample(2, None, seed=9, first_real=1)])
+    assert np.array_equal(a, b)
+    plan.close()
+
+
+def test_two_device_context_shards_realizations(emu_lib):
+    """host sharding logic of a multi-device context, exercised with the emulated device listed twice."""
+    lib2 = gsp.Library(emu_lib.path, devices=[0, 0])
+    st = iso(O.EXPONENTIAL, 1.0, 3.0, 2)
+    w = np.random.default_rng(2).random((5, 96))
+    p1 = gsp.FFTPlan(emu_lib, st, (12, 8), [0.0, 0.0], [1.0, 1.0])
+    p2 = gsp.FFTPlan(lib2, st, (12, 8), [0.0, 0.0], [1.0, 1.0])
+    assert np.array_equal(p1.sample(5, w), p2.sample(5, w))
+    assert np.array_equal(p1.sample(5, None, seed=3), p2.sample(5, None, seed=3))
+    dom = (gsp._lib.make_grid_domain((8, 6), (0, 0), (1, 1)), None)
+    q1 = gsp.LUPlan(emu_lib, st, dom, np.array([3, 9]), np.array([0.5, -0.5]), 0.0)
+    q2 = gsp.LUPlan(lib2, st, dom, np.array([3, 9]), np.array([0.5, -0.5]), 0.0)
+    W = np.random.default_rng(3).standard_normal((46, 5))
+    assert np.array_equal(q1.sample(5, W), q2.sample(5, W))
+    assert np.array_equal(q1.sample(5, None, seed=8), q2.sample(5, None, seed=8))
+    for p in (p1, p2, q1, q2):
+        p.close()
+    lib2.close()
+
+
+def test_philox_matches_restatement(emu_lib):
+    """device uniforms == a NumPy restatement of Philox4x32-10 with the documented counter layout."""
+    def philox(ctr, key):
+        M0, M1, W0, W1 = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85
+        c = [int(x) for x in ctr]
+        k = [int(x) for x in key]
+        for _ in range(10):
+            p0, p1 = M0 * c[0], M1 * c[2]
+            c = [(p1 >> 32) ^ c[1] ^ k[0], p1 & 0xFFFFFFFF, (p0 >> 32) ^ c[3] ^ k[1], p0 & 0xFFFFFFFF]
+            k = [(k[0] + W0) & 0xFFFFFFFF, (k[1] + W1) & 0xFFFFFFFF]
+        return c
+
+    st = iso(O.SPHERICAL, 1.0, 3.0, 1)
+    plan = gsp.FFTPlan(emu_lib, st, (8,), [0.0], [1.0])
+    # recover the uniforms through linearity-free route: sample with inds on a plan is nonlinear, so
+    # instead compare LUSIM normals?  Simplest: FFTSIM is deterministic in w, so compare fields.
+    seed, real = 0x1234567890, 5
+    w = np.zeros(8)
+    for pair in range(4):
+        o = philox([pair, 0, real, 0], [seed & 0xFFFFFFFF, seed >> 32])
+        a = (o[1] << 32) | o[0]
+        b = (o[3] << 32) | o[2]
+        w[2 * pair] = (a >> 11) / 2.0 ** 53
+        w[2 * pair + 1] = (b >> 11) / 2.0 ** 53
+    assert np.array_equal(plan.sample(1, None, seed=seed, first_real=real), plan.sample(1, w[None, :]))
+    plan.close()

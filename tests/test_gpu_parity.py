@@ -1,0 +1,286 @@
+"""Parity tests proper (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle on the same
+seeded inputs; golden fixtures; and size-independent properties at BASELINE.json's full sizes.
+Tolerance: north_star's 1e-9 relative (normwise max|dZ|/max|Z|) in Float64; conditioning data bit-exact."""
+import math
+import os
+
+import numpy as np
+import pytest
+import scipy.linalg
+
+import gsp_b200 as gsp
+import gsp_oracle as O
+from helpers import aniso3, iso, ostructs, relerr
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def grid_dom(dims):
+    nd = len(dims)
+    return (gsp._lib.make_grid_domain(dims, [0.0] * nd, [1.0] * nd), None)
+
+
+# ------------------------------------------------------------------ a1 / a2 pieces
+def test_pairwise_models(gpu_lib):
+    rng = np.random.default_rng(0)
+    for kind in (O.SPHERICAL, O.EXPONENTIAL, O.GAUSSIAN, O.CUBIC, O.PENTASPHERICAL):
+        st = aniso3(kind, 0.9, (9.0, 4.0, 2.0), 30.0) + [(O.NUGGET, 0.1, np.eye(3))]
+        X1, X2 = rng.uniform(0, 12, (301, 3)), rng.uniform(0, 12, (77, 3))
+        assert relerr(gpu_lib.pairwise(st, X1, X2), O.pairwise(ostructs(st), X1, X2)) < 1e-13
+        assert relerr(gpu_lib.pairwise(st, X1), O.pairwise(ostructs(st), X1)) < 1e-13
+
+
+@pytest.mark.parametrize("n", [1, 5, 127, 128, 129, 1000, 2048])
+def test_potrf(gpu_lib, n):
+    rng = np.random.default_rng(n)
+    M = rng.standard_normal((n, n))
+    S = M @ M.T + n * np.eye(n)
+    L = gpu_lib.potrf(S)
+    assert relerr(L, scipy.linalg.cholesky(S, lower=True)) < 1e-12
+    assert np.all(np.triu(L, 1) == 0.0)
+
+
+def test_potrf_not_positive_definite(gpu_lib):
+    A = np.eye(300)
+    A[200, 200] = -2.0
+    with pytest.raises(gsp.PosDefException) as ei:
+        gpu_lib.potrf(A)
+    assert ei.value.info == 201
+
+
+# ------------------------------------------------------------------ LUSIM
+def test_lusim_c1_config(gpu_lib):
+    """BASELINE configs[0]: unconditional 50x50, SphericalCovariance(range=20), 100 realizations, seed 1."""
+    st = iso(O.SPHERICAL, 1.0, 20.0, 2)
+    coords = O.grid_centroids((50, 50), [0, 0], [1, 1])
+    plan = gsp.LUPlan(gpu_lib, st, grid_dom((50, 50)), None, None, 0.0)
+    pre = O.lusim_preprocess(ostructs(st), coords, np.zeros(0, dtype=np.int64), np.zeros(0), 0.0)
+    W = np.random.default_rng(1).standard_normal((2500, 100))
+    Z = plan.sample(100, W)
+    Zo = O.lusim_sample(pre, W)
+    assert max(relerr(Z[:, r], Zo[:, r]) for r in range(100)) < TOL
+    d2, L22 = plan.get()
+    assert relerr(L22, pre.L22) < 1e-11 and np.all(d2 == 0.0)
+    plan.close()
+
+
+@pytest.mark.parametrize("kind,nd,mu", [(O.EXPONENTIAL, 300, 0.0), (O.SPHERICAL, 17, 2.5), (O.CUBIC, 128, -1.0)])
+def test_lusim_conditional(gpu_lib, kind, nd, mu):
+    rng = np.random.default_rng(nd)
+    dims = (64, 48)
+    st = iso(kind, 1.4, 12.0, 2) + [(O.NUGGET, 0.05, np.eye(3))]
+    coords = O.grid_centroids(dims, [0, 0], [1, 1])
+    dinds = np.sort(rng.choice(coords.shape[0], nd, replace=False))
+    z1 = rng.standard_normal(nd)
+    plan = gsp.LUPlan(gpu_lib, st, grid_dom(dims), dinds + 1, z1, mu)
+    pre = O.lusim_preprocess(ostructs(st), coords, dinds, z1, mu)
+    R = 200
+    W = rng.standard_normal((plan.Ns, R))
+    Z = plan.sample(R, W)
+    Zo = O.lusim_sample(pre, W)
+    assert max(relerr(Z[:, r], Zo[:, r]) for r in range(R)) < TOL
+    assert np.array_equal(Z[dinds], np.repeat(z1[:, None], R, 1))  # conditioning data honoured exactly
+    d2, L22 = plan.get()
+    assert relerr(L22, pre.L22) < 1e-10 and relerr(d2, pre.d2) < 1e-10
+    plan.close()
+
+
+def test_lusim_bivariate(gpu_lib):
+    """cosimulation (lusim.jl:112-126,164): rho-mixing of the noises, each variable with its own marginal plan."""
+    rng = np.random.default_rng(5)
+    dims = (40, 32)
+    C = np.array([[1.0, 0.7], [0.7, 1.0]])
+    A = np.eye(3) / 20.0
+    mv = [(O.SPHERICAL, C, A)]
+    coords = O.grid_centroids(dims, [0, 0], [1, 1])
+    dinds = np.sort(rng.choice(1280, 50, replace=False))
+    z = [rng.standard_normal(50), rng.standard_normal(50)]
+    rho = O.rho_mv(mv)
+    plans, pres = [], []
+    for j in range(2):
+        m = O.marginalize(mv, j)
+        st = [(s.kind, s.sill, s.A) for s in m]
+        plans.append(gsp.LUPlan(gpu_lib, st, grid_dom(dims), dinds + 1, z[j], 0.1 * (j + 1)))
+        pres.append(O.lusim_preprocess(m, coords, dinds, z[j], 0.1 * (j + 1)))
+    R = 64
+    W1, W2 = rng.standard_normal((plans[0].Ns, R)), rng.standard_normal((plans[0].Ns, R))
+    Z1 = plans[0].sample(R, W1)
+    Z2 = plans[1].sample(R, W2, rho=rho, W1=W1)
+    assert relerr(Z1, O.lusim_sample(pres[0], W1)) < TOL
+    assert relerr(Z2, O.lusim_sample(pres[1], W2, rho, W1)) < TOL
+    assert np.array_equal(Z2[dinds], np.repeat(z[1][:, None], R, 1))
+    for p in plans:
+        p.close()
+
+
+def test_lusim_pointset_3d(gpu_lib):
+    rng = np.random.default_rng(8)
+    X = rng.uniform(0, 20, (700, 3))
+    st = aniso3(O.EXPONENTIAL, 1.0, (8.0, 6.0, 3.0), 30.0)
+    dinds = np.sort(rng.choice(700, 30, replace=False))
+    z1 = rng.standard_normal(30)
+    plan = gsp.LUPlan(gpu_lib, st, gsp._lib.make_point_domain(X), dinds + 1, z1, 0.0)
+    pre = O.lusim_preprocess(ostructs(st), X, dinds, z1, 0.0)
+    W = rng.standard_normal((670, 10))
+    assert relerr(plan.sample(10, W), O.lusim_sample(pre, W)) < TOL
+    plan.close()
+
+
+def test_lusim_golden(gpu_lib):
+    g = np.load(os.path.join(GOLD, "golden_small.npz"))
+    st = iso(O.SPHERICAL, 1.0, 20.0, 2)
+    plan = gsp.LUPlan(gpu_lib, st, grid_dom((12, 10)), g["lu_dinds"] + 1, g["lu_z1"], 0.0)
+    assert relerr(plan.sample(4, g["lu_W"]), g["lu_Z"]) < TOL
+    plan.close()
+
+
+def test_lusim_c3_size_properties(gpu_lib):
+    """BASELINE configs[2] at full size (16,384 nodes + 1,000 data, 1,000 realizations): the oracle needs minutes here,
+    so check properties: data honoured bit-exactly, L L' == K on sampled entries, d2 == K21 K11^-1 z1, ensemble moments."""
+    rng = np.random.default_rng(3)
+    dims = (128, 128)
+    st = iso(O.EXPONENTIAL, 1.0, 20.0, 2)
+    coords = O.grid_centroids(dims, [0, 0], [1, 1])
+    N, nd, R = 16384, 1000, 1000
+    dinds = np.sort(rng.choice(N, nd, replace=False))
+    pre0 = O.lusim_preprocess(ostructs(st), coords[dinds], np.zeros(0, dtype=np.int64), np.zeros(0), 0.0)
+    z1 = O.lusim_sample(pre0, rng.standard_normal((nd, 1)))[:, 0]  # data consistent with the model
+    plan = gsp.LUPlan(gpu_lib, st, grid_dom(dims), dinds + 1, z1, 0.0)
+    Z = plan.sample(R, None, seed=33)
+    assert np.array_equal(Z[dinds], np.repeat(z1[:, None], R, 1))
+    sinds = np.setdiff1d(np.arange(N), dinds)
+    # conditional mean: d2 = C21 C11^-1 z1
+    C11 = O.pairwise(ostructs(st), coords[dinds])
+    probe = rng.choice(len(sinds), 400, replace=False)
+    C21 = O.pairwise(ostructs(st), coords[sinds[probe]], coords[dinds])
+    d2_ref = C21 @ scipy.linalg.cho_solve(scipy.linalg.cho_factor(C11), z1)
+    d2, _ = plan.get_d2_only() if hasattr(plan, "get_d2_only") else (None, None)
+    d2 = np.empty(plan.Ns)
+    plan.lib.check(plan.lib.lib.gsp_lu_plan_get(plan.h, d2.ctypes.data, None))
+    assert np.abs(d2[probe] - d2_ref).max() < 1e-9
+    # ensemble mean -> d2 and conditional variance <= sill within sampling tolerance
+    m = Z[sinds].mean(axis=1)
+    assert np.abs(m - d2).max() < 6.0 / math.sqrt(R)
+    v = Z[sinds].var(axis=1, ddof=1)
+    assert v.max() < 1.35 and v.min() > 0.0
+    plan.close()
+
+
+def test_lusim_statistics(gpu_lib):
+    """ensemble covariance of unconditional LUSIM reproduces C within sampling tolerance (device RNG)."""
+    st = iso(O.SPHERICAL, 2.0, 10.0, 2)
+    dims = (24, 20)
+    plan = gsp.LUPlan(gpu_lib, st, grid_dom(dims), None, None, 1.0)
+    R = 20000
+    Z = plan.sample(R, None, seed=2024)
+    assert abs(Z.mean() - 1.0) < 0.05
+    C = O.pairwise(ostructs(st), O.grid_centroids(dims, [0, 0], [1, 1]))
+    Zc = Z - 1.0
+    emp = (Zc[:60] @ Zc.T) / R
+    assert np.abs(emp - C[:60]).max() < 0.12
+    plan.close()
+
+
+# ------------------------------------------------------------------ FFTSIM
+@pytest.mark.parametrize("dims,kind,rang", [((100, 100), O.SPHERICAL, 10.0), ((256, 128), O.EXPONENTIAL, 25.0), ((64, 32, 16), O.SPHERICAL, 8.0),
+                                            ((45, 30, 7), O.EXPONENTIAL, 5.0), ((1000,), O.SPHERICAL, 30.0), ((33, 27), O.CUBIC, 6.0)])
+def test_fftsim_parity(gpu_lib, dims, kind, rang):
+    rng = np.random.default_rng(sum(dims))
+    nd = len(dims)
+    st = iso(kind, 1.5, rang, nd)
+    plan = gsp.FFTPlan(gpu_lib, st, dims, [0.0] * nd, [1.0] * nd)
+    Fo = O.fftsim_preprocess(ostructs(st), dims, [0.0] * nd, [1.0] * nd)
+    assert relerr(plan.spectrum(), Fo) < 1e-10
+    N = int(np.prod(dims))
+    w = rng.random((4, N))
+    Z = plan.sample(4, w, sill=1.5, mu=0.2)
+    for r in range(4):
+        assert relerr(Z[r], O.fftsim_sample(Fo, w[r], 1.5, 0.2)) < TOL
+    plan.close()
+
+
+def test_fftsim_anisotropic_3d_and_view(gpu_lib):
+    dims = (64, 64, 32)
+    st = aniso3(O.SPHERICAL, 1.0, (20.0, 10.0, 5.0), 30.0)
+    plan = gsp.FFTPlan(gpu_lib, st, dims, [0.0] * 3, [1.0] * 3)
+    Fo = O.fftsim_preprocess(ostructs(st), dims, [0.0] * 3, [1.0] * 3)
+    N = int(np.prod(dims))
+    w = np.random.default_rng(4).random((1, N))
+    inds = np.arange(0, N, 7)
+    Zs = plan.sample(1, w, sill=1.0, mu=0.0, inds1=inds + 1)
+    assert relerr(Zs[0], O.fftsim_sample(Fo, w[0], 1.0, 0.0, inds)) < TOL
+    plan.close()
+
+
+def test_fftsim_golden(gpu_lib):
+    g = np.load(os.path.join(GOLD, "golden_small.npz"))
+    plan = gsp.FFTPlan(gpu_lib, iso(O.EXPONENTIAL, 1.0, 5.0, 3), (8, 6, 4), [0.0] * 3, [1.0] * 3)
+    assert relerr(plan.sample(1, g["fft_w"][None, :], sill=1.0, mu=0.5)[0], g["fft_Z"]) < TOL
+    plan.close()
+
+
+def test_fftsim_c2_config(gpu_lib):
+    """BASELINE configs[1]: 1024x1024, GaussianCovariance(range=50), 64 realizations.  The Gaussian spectrum underflows to
+    rounding noise (sqrt of ~1e-16 relative garbage), so F parity is asserted on F^2 = |fft(C)| and the fields
+    are compared with a looser, stated bound; invariants are exact."""
+    dims = (1024, 1024)
+    st = iso(O.GAUSSIAN, 1.0, 50.0, 2)
+    plan = gsp.FFTPlan(gpu_lib, st, dims, [0.0, 0.0], [1.0, 1.0])
+    Fo = O.fftsim_preprocess(ostructs(st), dims, [0.0, 0.0], [1.0, 1.0])
+    F = plan.spectrum()
+    assert relerr(F ** 2, Fo ** 2) < 1e-12
+    N = 1 << 20
+    w = np.random.default_rng(2).random((64, N))
+    Z = plan.sample(64, w, sill=1.0, mu=0.0)
+    assert np.abs(Z.mean(axis=1)).max() < 1e-12
+    assert np.abs((Z ** 2).sum(axis=1) / (N - 1) - 1.0).max() < 1e-12
+    for r in (0, 63):
+        assert relerr(Z[r], O.fftsim_sample(Fo, w[r], 1.0, 0.0)) < 1e-6  # conditioning-limited, see docstring
+    plan.close()
+
+
+def test_fftsim_c4_size_properties(gpu_lib):
+    """BASELINE configs[3] at full size (256^3, anisotropic spherical): one oracle realization for parity plus the
+    size-independent invariants (exact mean, exact variance, determinism, shard invariance of the device RNG)."""
+    dims = (256, 256, 256)
+    st = aniso3(O.SPHERICAL, 1.0, (40.0, 20.0, 10.0), 30.0)
+    plan = gsp.FFTPlan(gpu_lib, st, dims, [0.0] * 3, [1.0] * 3)
+    N = 1 << 24
+    w = np.random.default_rng(4).random((1, N))
+    Z = plan.sample(1, w, sill=1.0, mu=0.25)
+    assert abs(Z[0].mean() - 0.25) < 1e-12
+    assert abs(((Z[0] - 0.25) ** 2).sum() / (N - 1) - 1.0) < 1e-11
+    Fo = O.fftsim_preprocess(ostructs(st), dims, [0.0] * 3, [1.0] * 3)
+    assert relerr(Z[0], O.fftsim_sample(Fo, w[0], 1.0, 0.25)) < TOL
+    a = plan.sample(3, None, seed=77)
+    b = np.concatenate([plan.sample(2, None, seed=77, first_real=0), plan.sample(1, None, seed=77, first_real=2)])
+    assert np.array_equal(a, b)
+    plan.close()
+
+
+def test_fftsim_variogram_reproduction(gpu_lib):
+    """empirical variogram along x of an ensemble vs the model gamma(h) = sill - C(h), h << grid."""
+    dims = (256, 256)
+    st = iso(O.SPHERICAL, 1.0, 20.0, 2)
+    plan = gsp.FFTPlan(gpu_lib, st, dims, [0.0, 0.0], [1.0, 1.0])
+    Z = plan.sample(32, None, seed=5).reshape(32, 256, 256)  # [r][y][x]
+    for h in (1, 3, 6, 10):
+        emp = 0.5 * np.mean((Z[:, :, h:] - Z[:, :, :-h]) ** 2)
+        model = 1.0 - float(O.corr(O.SPHERICAL, np.array(h / 20.0)))
+        assert abs(emp - model) < 0.08, (h, emp, model)
+    plan.close()
+
+
+# ------------------------------------------------------------------ reference-facing API on the GPU
+def test_rand_api_gpu(gpu_lib):
+    rng = np.random.default_rng(123)
+    proc = gsp.GaussianProcess(gsp.SphericalCovariance(range=10.0))
+    grid = gsp.CartesianGrid(100, 100)
+    ens = gsp.rand(proc, grid, 3, rng=rng, method=gsp.LUSIM(library=gpu_lib))
+    assert len(ens) == 3 and ens[0].field.shape == (10000,)
+    proc = gsp.GaussianProcess(gsp.GaussianVariogram(range=10.0))
+    vgrid = grid.view(range(1, 5001))
+    real = gsp.rand(proc, vgrid, rng=rng, method=gsp.FFTSIM(library=gpu_lib))
+    assert real.domain == vgrid and real.nrow == 5000

@@ -156,7 +156,6 @@ def test_lusim_c3_size_properties(gpu_lib):
     probe = rng.choice(len(sinds), 400, replace=False)
     C21 = O.pairwise(ostructs(st), coords[sinds[probe]], coords[dinds])
     d2_ref = C21 @ scipy.linalg.cho_solve(scipy.linalg.cho_factor(C11), z1)
-    d2, _ = plan.get_d2_only() if hasattr(plan, "get_d2_only") else (None, None)
     d2 = np.empty(plan.Ns)
     plan.lib.check(plan.lib.lib.gsp_lu_plan_get(plan.h, d2.ctypes.data, None))
     assert np.abs(d2[probe] - d2_ref).max() < 1e-9

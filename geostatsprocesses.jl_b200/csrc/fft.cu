@@ -8,11 +8,13 @@
 // sigma^2 = var(Z, mean=0) (fftsim.jl:131) does not depend on the noise: |P_k| = F_k, so by Parseval
 // sigma^2 = sum(F^2) / (N (N-1)); it is computed once per plan and folded into the scalar s.
 #include <cmath>
+#include <cstdlib>
 #include <memory>
 
 #include "cov.cuh"
 #include "chol.h"
 #include "fft_kernels.cuh"
+#include "fft_pow2.cuh"
 #include "rng.cuh"
 
 namespace gsp {
@@ -255,6 +257,7 @@ struct AxisPlan {
   int B = 1;         // bundle width
   size_t smem = 0;
   int packed = 0;    // x axis only
+  bool fast = false; // power-of-two register-resident kernels (fft_pow2.cuh)
 };
 
 struct FftDev {
@@ -289,6 +292,69 @@ namespace gsp {
 namespace {
 
 const size_t kMaxSmem = 200 * 1024;
+bool g_force_generic = false;  // GSP_FFT_GENERIC=1: use the mixed-radix kernels for every extent (A/B checks)
+
+template <int HN>
+cudaError_t launch_p2_xfwd(cudaStream_t st, const double* in, cplx* H, const cplx* tw, long long nrows) {
+  using C = XCfg<HN, false>;
+  auto kfn = p2_xfwd_kernel<HN>;
+  cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+  if (e != cudaSuccess) return e;
+  ProfScope prof_("fft_xpass_fwd", st);
+  GSP_LAUNCH(kfn, dim3((unsigned)((nrows + C::ROWS - 1) / C::ROWS)), dim3(C::THREADS), C::SMEM, st, in, H, tw, nrows);
+  g_launches++;
+  return cudaGetLastError();
+}
+
+template <int HN>
+cudaError_t launch_p2_xinv(cudaStream_t st, const cplx* H, double* out, const cplx* tw, long long nrows, double scale, double mu) {
+  using C = XCfg<HN, true>;
+  auto kfn = p2_xinv_kernel<HN>;
+  cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+  if (e != cudaSuccess) return e;
+  ProfScope prof_("fft_xpass_inv", st);
+  GSP_LAUNCH(kfn, dim3((unsigned)((nrows + C::ROWS - 1) / C::ROWS)), dim3(C::THREADS), C::SMEM, st, H, out, tw, nrows, scale, mu);
+  g_launches++;
+  return cudaGetLastError();
+}
+
+template <int N, int FLAGS>
+cudaError_t launch_p2_strided_f(cudaStream_t st, cplx* H, const cplx* tw, long long es, int hx, long long nother, long long other_stride,
+                                const double* Fh, double s) {
+  constexpr int B = p2_bundle(N), U = p2_units(N), TPU = (N / p2_slots(N)) * B;
+  const size_t smem = (size_t)(N + U * N * B) * sizeof(cplx);
+  auto kfn = p2_strided_kernel<N, B, U, FLAGS>;
+  cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const int nbundles = (hx + B - 1) / B;
+  const long long nunits = (long long)nbundles * nother;
+  ProfScope prof_((FLAGS & P2_MUL) ? "fft_strided_fwd_mul_inv" : ((FLAGS & P2_FWD) ? "fft_strided_fwd" : "fft_strided_inv"), st);
+  GSP_LAUNCH(kfn, dim3((unsigned)((nunits + U - 1) / U)), dim3(TPU * U), smem, st, H, tw, es, hx, nbundles, nunits, other_stride, Fh, s);
+  g_launches++;
+  return cudaGetLastError();
+}
+
+template <int N>
+cudaError_t launch_p2_strided(cudaStream_t st, int flags, cplx* H, const cplx* tw, long long es, int hx, long long nother,
+                              long long other_stride, const double* Fh, double s) {
+  if (flags == P2_FWD) return launch_p2_strided_f<N, P2_FWD>(st, H, tw, es, hx, nother, other_stride, Fh, s);
+  if (flags == P2_INV) return launch_p2_strided_f<N, P2_INV>(st, H, tw, es, hx, nother, other_stride, Fh, s);
+  return launch_p2_strided_f<N, P2_FWD | P2_MUL | P2_INV>(st, H, tw, es, hx, nother, other_stride, Fh, s);
+}
+
+#define GSP_P2_SWITCH(n, CALL)        \
+  switch (n) {                        \
+    case 16: return CALL(16);         \
+    case 32: return CALL(32);         \
+    case 64: return CALL(64);         \
+    case 128: return CALL(128);       \
+    case 256: return CALL(256);       \
+    case 512: return CALL(512);       \
+    case 1024: return CALL(1024);     \
+    case 2048: return CALL(2048);     \
+    case 4096: return CALL(4096);     \
+    default: return cudaErrorInvalidValue; \
+  }
 
 int setup_axes(gsp_ctx* ctx, gsp_fft_plan* p, FftDev* d) {
   const int nx = (int)p->dims[0];
@@ -315,7 +381,8 @@ int setup_axes(gsp_ctx* ctx, gsp_fft_plan* p, FftDev* d) {
     if (B < 1) B = 1;
     a.B = B;
     a.smem = 2 * L * B * sizeof(cplx);
-    if (a.smem > kMaxSmem) return set_err(ctx, GSP_E_UNSUPPORTED, "x extent too large for one shared-memory line");
+    a.fast = a.packed && p2_supported(nx / 2) && !g_force_generic;
+    if (!a.fast && a.smem > kMaxSmem) return set_err(ctx, GSP_E_UNSUPPORTED, "x extent too large for one shared-memory line");
   }
   for (int axis = 1; axis < p->ndim; ++axis) {
     AxisPlan& a = d->ax[axis];
@@ -333,7 +400,8 @@ int setup_axes(gsp_ctx* ctx, gsp_fft_plan* p, FftDev* d) {
     if (B > p->hx) B = p->hx;
     a.B = B;
     a.smem = 2 * (size_t)n * B * sizeof(cplx);
-    if (a.smem > kMaxSmem) return set_err(ctx, GSP_E_UNSUPPORTED, "grid extent too large for one shared-memory line");
+    a.fast = p2_supported(n) && !g_force_generic;
+    if (!a.fast && a.smem > kMaxSmem) return set_err(ctx, GSP_E_UNSUPPORTED, "grid extent too large for one shared-memory line");
   }
   return GSP_OK;
 }
@@ -341,6 +409,11 @@ int setup_axes(gsp_ctx* ctx, gsp_fft_plan* p, FftDev* d) {
 cudaError_t run_xfwd(FftDev* d, gsp_fft_plan* p, const double* in, cplx* H) {
   const AxisPlan& a = d->ax[0];
   const long long nrows = p->dims[1] * p->dims[2];
+  if (a.fast) {
+#define GSP_CALL(HN) launch_p2_xfwd<HN>(d->dc->stream, in, H, a.lp.tw, nrows)
+    GSP_P2_SWITCH((int)p->dims[0] / 2, GSP_CALL)
+#undef GSP_CALL
+  }
   auto kfn = xpass_fwd_kernel;
   cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.smem);
   if (e != cudaSuccess) return e;
@@ -354,6 +427,11 @@ cudaError_t run_xfwd(FftDev* d, gsp_fft_plan* p, const double* in, cplx* H) {
 cudaError_t run_xinv(FftDev* d, gsp_fft_plan* p, const cplx* H, double* out, double scale, double mu) {
   const AxisPlan& a = d->ax[0];
   const long long nrows = p->dims[1] * p->dims[2];
+  if (a.fast) {
+#define GSP_CALL(HN) launch_p2_xinv<HN>(d->dc->stream, H, out, a.lp.tw, nrows, scale, mu)
+    GSP_P2_SWITCH((int)p->dims[0] / 2, GSP_CALL)
+#undef GSP_CALL
+  }
   auto kfn = xpass_inv_kernel;
   cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.smem);
   if (e != cudaSuccess) return e;
@@ -376,6 +454,11 @@ cudaError_t run_strided(FftDev* d, gsp_fft_plan* p, int axis, cplx* H, int flags
     es = hx * p->dims[1];
     other_stride = hx;
     nother = p->dims[1];
+  }
+  if (a.fast) {
+#define GSP_CALL(NN) launch_p2_strided<NN>(d->dc->stream, flags, H, a.lp.tw, es, (int)hx, nother, other_stride, Fh, s)
+    GSP_P2_SWITCH(a.len, GSP_CALL)
+#undef GSP_CALL
   }
   auto kfn = strided_pass_kernel;
   cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.smem);
@@ -461,6 +544,10 @@ extern "C" int gsp_fft_plan_create(gsp_ctx* ctx, const gsp_cov_model* cov, const
   if (!out) return set_err(ctx, -4, "out is NULL");
   *out = nullptr;
   if (!grid || grid->kind != 1) return set_err(ctx, -3, "FFTSIM needs a CartesianGrid domain (kind 1)");
+  {
+    const char* env = getenv("GSP_FFT_GENERIC");
+    g_force_generic = env && env[0] == '1';
+  }
   DomDev dom;
   GSP_TRY(make_dom_dev(ctx, grid, 3, &dom));
   CovDev cd;

@@ -126,7 +126,7 @@ GSP_DEV double2 ld_stream2(const double* p) {
   return double2{p[0], p[1]};
 #else
   double2 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  asm volatile("ld.global.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
   return v;
 #endif
 }

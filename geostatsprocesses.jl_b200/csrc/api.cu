@@ -33,6 +33,40 @@ void Prof::flush() {
   pending.clear();
 }
 
+int make_tensor_map_f64(TensorMap* out, const void* base, const unsigned long long dims[3], unsigned long long stride1_bytes,
+                        unsigned long long stride2_bytes, const unsigned box[3]) {
+#ifdef GSP_EMU
+  out->base = (const unsigned char*)base;
+  out->esize = 8;
+  for (int i = 0; i < 3; ++i) {
+    out->dims[i] = dims[i];
+    out->box[i] = box[i];
+  }
+  out->strides[0] = 8;
+  out->strides[1] = stride1_bytes;
+  out->strides[2] = stride2_bytes;
+  return 0;
+#else
+  // resolved at run time so that the library carries no link-time dependency on libcuda
+  typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static encode_fn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) != cudaSuccess || !sym) return -1;
+    fn = (encode_fn)sym;
+  }
+  cuuint64_t gdim[3] = {dims[0], dims[1], dims[2]};
+  cuuint64_t gstr[2] = {stride1_bytes, stride2_bytes};
+  cuuint32_t bx[3] = {box[0], box[1], box[2]};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<void*>(base), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : (int)r;
+#endif
+}
+
 int set_err(gsp_ctx* ctx, int code, const std::string& msg) {
   if (ctx) ctx->err = msg;
   return code;

@@ -118,7 +118,7 @@ enum { PASS_FWD = 1, PASS_MUL = 2, PASS_INV = 4 };
 // P = s * F * W/|W| (angle(0) = 0 => P = s*F) between the forward and inverse transforms (fftsim.jl:125).
 __global__ void __launch_bounds__(256) strided_pass_kernel(LinePlan lp, cplx* __restrict__ H, long long es, int hx, int B,
                                                            long long other_stride, int flags, const double* __restrict__ Fh,
-                                                           double s) {
+                                                           long long esF, long long other_strideF, double s) {
   GSP_DYN_SMEM(smem);
   const int n = lp.n;
   cplx* X = reinterpret_cast<cplx*>(smem);
@@ -126,6 +126,7 @@ __global__ void __launch_bounds__(256) strided_pass_kernel(LinePlan lp, cplx* __
   const int b0 = blockIdx.x * B;
   const int nb = (hx - b0 < B) ? hx - b0 : B;
   const long long base = (long long)blockIdx.y * other_stride + b0;
+  const long long baseF = (long long)blockIdx.y * other_strideF + b0;
   for (int idx = threadIdx.x; idx < n * B; idx += blockDim.x) {
     const int j = idx / B, b = idx - j * B;
     X[idx] = (b < nb) ? H[base + (long long)j * es + b] : cplx{0.0, 0.0};
@@ -141,7 +142,7 @@ __global__ void __launch_bounds__(256) strided_pass_kernel(LinePlan lp, cplx* __
     for (int idx = threadIdx.x; idx < n * B; idx += blockDim.x) {
       const int j = idx / B, b = idx - j * B;
       if (b < nb) {
-        const double f = s * Fh[base + (long long)j * es + b];
+        const double f = s * Fh[baseF + (long long)j * esF + b];
         const cplx w = cur[idx];
         const double m2 = w.re * w.re + w.im * w.im;
         if (m2 > 0.0) {
@@ -176,7 +177,7 @@ __global__ void __launch_bounds__(256) spectral_mul_kernel(cplx* __restrict__ H,
 // F = sqrt(|H|), F[0] = 0 (fftsim.jl:90-91); partial[blockIdx.x] = sum of w_k F_k^2 over the block's
 // elements, w_k = 1 on the self-conjugate planes kx = 0 and (nx even) kx = nx/2, else 2.
 __global__ void __launch_bounds__(256) spectrum_finalize_kernel(const cplx* __restrict__ H, double* __restrict__ Fh, long long nh,
-                                                                int hx, int nx, double* __restrict__ partial) {
+                                                                int hx, int hxF, int nx, double* __restrict__ partial) {
   __shared__ double red[256];
   double acc = 0.0;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -184,8 +185,8 @@ __global__ void __launch_bounds__(256) spectrum_finalize_kernel(const cplx* __re
     const cplx h = H[i];
     double f2 = sqrt(h.re * h.re + h.im * h.im);  // F^2 = |fft(C)|
     if (i == 0) f2 = 0.0;
-    Fh[i] = sqrt(f2);
     const int kx = (int)(i % hx);
+    Fh[(i / hx) * hxF + kx] = sqrt(f2);
     const double w = (kx == 0 || ((nx & 1) == 0 && kx == nx / 2)) ? 1.0 : 2.0;
     acc += w * f2;
   }
@@ -258,6 +259,7 @@ struct AxisPlan {
   size_t smem = 0;
   int packed = 0;    // x axis only
   bool fast = false; // power-of-two register-resident kernels (fft_pow2.cuh)
+  TensorMap tmH, tmF; // strided fast passes: TMA tiles of the work spectrum / of F along this axis
 };
 
 struct FftDev {
@@ -281,8 +283,8 @@ struct gsp_fft_plan {
   gsp_ctx* ctx = nullptr;
   int ndim = 1;
   long long dims[3] = {1, 1, 1};
-  long long N = 1, nh = 1;
-  int hx = 1;
+  long long N = 1, nh = 1, nhF = 1;
+  int hx = 1, hxF = 2;  // F rows are padded to an even length: 16-byte aligned rows for the bulk copies
   double sumF2 = 0.0;  // full-spectrum sum of F^2
   std::vector<std::unique_ptr<FftDev>> dev;
   std::mutex mu;
@@ -294,52 +296,66 @@ namespace {
 const size_t kMaxSmem = 200 * 1024;
 bool g_force_generic = false;  // GSP_FFT_GENERIC=1: use the mixed-radix kernels for every extent (A/B checks)
 
+// persistent grid: as many CTAs as fit per SM by shared memory (at most 4), never more than there are items
+inline unsigned persistent_grid(int sms, size_t smem, long long items) {
+  long long per_sm = (long long)((220 * 1024) / (smem + 1024));
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 4) per_sm = 4;
+  long long g = per_sm * sms;
+  if (g > items) g = items;
+  if (g < 1) g = 1;
+  return (unsigned)g;
+}
+
 template <int HN>
-cudaError_t launch_p2_xfwd(cudaStream_t st, const double* in, cplx* H, const cplx* tw, long long nrows) {
+cudaError_t launch_p2_xfwd(cudaStream_t st, int sms, const double* in, cplx* H, const cplx* tw, long long nrows) {
   using C = XCfg<HN, false>;
   auto kfn = p2_xfwd_kernel<HN>;
   cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
   if (e != cudaSuccess) return e;
+  const long long ngroups = (nrows + C::ROWS - 1) / C::ROWS;
   ProfScope prof_("fft_xpass_fwd", st);
-  GSP_LAUNCH(kfn, dim3((unsigned)((nrows + C::ROWS - 1) / C::ROWS)), dim3(C::THREADS), C::SMEM, st, in, H, tw, nrows);
+  GSP_LAUNCH(kfn, dim3(persistent_grid(sms, C::SMEM, ngroups)), dim3(C::THREADS), C::SMEM, st, in, H, tw, nrows);
   g_launches++;
   return cudaGetLastError();
 }
 
 template <int HN>
-cudaError_t launch_p2_xinv(cudaStream_t st, const cplx* H, double* out, const cplx* tw, long long nrows, double scale, double mu) {
+cudaError_t launch_p2_xinv(cudaStream_t st, int sms, const cplx* H, double* out, const cplx* tw, long long nrows, double scale, double mu) {
   using C = XCfg<HN, true>;
   auto kfn = p2_xinv_kernel<HN>;
   cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
   if (e != cudaSuccess) return e;
+  const long long ngroups = (nrows + C::ROWS - 1) / C::ROWS;
   ProfScope prof_("fft_xpass_inv", st);
-  GSP_LAUNCH(kfn, dim3((unsigned)((nrows + C::ROWS - 1) / C::ROWS)), dim3(C::THREADS), C::SMEM, st, H, out, tw, nrows, scale, mu);
+  GSP_LAUNCH(kfn, dim3(persistent_grid(sms, C::SMEM, ngroups)), dim3(C::THREADS), C::SMEM, st, H, out, tw, nrows, scale, mu);
   g_launches++;
   return cudaGetLastError();
 }
 
 template <int N, int FLAGS>
-cudaError_t launch_p2_strided_f(cudaStream_t st, cplx* H, const cplx* tw, long long es, int hx, long long nother, long long other_stride,
-                                const double* Fh, double s) {
-  constexpr int B = p2_bundle(N), U = p2_units(N), TPU = (N / p2_slots(N)) * B;
-  const size_t smem = (size_t)(N + U * N * B) * sizeof(cplx);
-  auto kfn = p2_strided_kernel<N, B, U, FLAGS>;
-  cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+cudaError_t launch_p2_strided_f(cudaStream_t st, int sms, const TensorMap& tmH, const TensorMap& tmF, int axis, cplx* H, const cplx* tw,
+                                long long es, int hx, long long nother, long long other_stride, double s) {
+  constexpr int B = p2_bundle(N);
+  using C = StridedCfg<N, B, FLAGS>;
+  auto kfn = p2_strided_kernel<N, B, FLAGS>;
+  cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
   if (e != cudaSuccess) return e;
   const int nbundles = (hx + B - 1) / B;
   const long long nunits = (long long)nbundles * nother;
   ProfScope prof_((FLAGS & P2_MUL) ? "fft_strided_fwd_mul_inv" : ((FLAGS & P2_FWD) ? "fft_strided_fwd" : "fft_strided_inv"), st);
-  GSP_LAUNCH(kfn, dim3((unsigned)((nunits + U - 1) / U)), dim3(TPU * U), smem, st, H, tw, es, hx, nbundles, nunits, other_stride, Fh, s);
+  GSP_LAUNCH(kfn, dim3(persistent_grid(sms, C::SMEM, nunits)), dim3(C::THREADS), C::SMEM, st, tmH, tmF, axis, H, tw, es, hx, nbundles, nunits,
+             other_stride, s);
   g_launches++;
   return cudaGetLastError();
 }
 
 template <int N>
-cudaError_t launch_p2_strided(cudaStream_t st, int flags, cplx* H, const cplx* tw, long long es, int hx, long long nother,
-                              long long other_stride, const double* Fh, double s) {
-  if (flags == P2_FWD) return launch_p2_strided_f<N, P2_FWD>(st, H, tw, es, hx, nother, other_stride, Fh, s);
-  if (flags == P2_INV) return launch_p2_strided_f<N, P2_INV>(st, H, tw, es, hx, nother, other_stride, Fh, s);
-  return launch_p2_strided_f<N, P2_FWD | P2_MUL | P2_INV>(st, H, tw, es, hx, nother, other_stride, Fh, s);
+cudaError_t launch_p2_strided(cudaStream_t st, int sms, int flags, const TensorMap& tmH, const TensorMap& tmF, int axis, cplx* H,
+                              const cplx* tw, long long es, int hx, long long nother, long long other_stride, double s) {
+  if (flags == P2_FWD) return launch_p2_strided_f<N, P2_FWD>(st, sms, tmH, tmF, axis, H, tw, es, hx, nother, other_stride, s);
+  if (flags == P2_INV) return launch_p2_strided_f<N, P2_INV>(st, sms, tmH, tmF, axis, H, tw, es, hx, nother, other_stride, s);
+  return launch_p2_strided_f<N, P2_FWD | P2_MUL | P2_INV>(st, sms, tmH, tmF, axis, H, tw, es, hx, nother, other_stride, s);
 }
 
 #define GSP_P2_SWITCH(n, CALL)        \
@@ -410,7 +426,7 @@ cudaError_t run_xfwd(FftDev* d, gsp_fft_plan* p, const double* in, cplx* H) {
   const AxisPlan& a = d->ax[0];
   const long long nrows = p->dims[1] * p->dims[2];
   if (a.fast) {
-#define GSP_CALL(HN) launch_p2_xfwd<HN>(d->dc->stream, in, H, a.lp.tw, nrows)
+#define GSP_CALL(HN) launch_p2_xfwd<HN>(d->dc->stream, d->dc->sms, in, H, a.lp.tw, nrows)
     GSP_P2_SWITCH((int)p->dims[0] / 2, GSP_CALL)
 #undef GSP_CALL
   }
@@ -428,7 +444,7 @@ cudaError_t run_xinv(FftDev* d, gsp_fft_plan* p, const cplx* H, double* out, dou
   const AxisPlan& a = d->ax[0];
   const long long nrows = p->dims[1] * p->dims[2];
   if (a.fast) {
-#define GSP_CALL(HN) launch_p2_xinv<HN>(d->dc->stream, H, out, a.lp.tw, nrows, scale, mu)
+#define GSP_CALL(HN) launch_p2_xinv<HN>(d->dc->stream, d->dc->sms, H, out, a.lp.tw, nrows, scale, mu)
     GSP_P2_SWITCH((int)p->dims[0] / 2, GSP_CALL)
 #undef GSP_CALL
   }
@@ -445,18 +461,23 @@ cudaError_t run_xinv(FftDev* d, gsp_fft_plan* p, const cplx* H, double* out, dou
 cudaError_t run_strided(FftDev* d, gsp_fft_plan* p, int axis, cplx* H, int flags, const double* Fh, double s) {
   const AxisPlan& a = d->ax[axis];
   const long long hx = p->hx;
-  long long es, other_stride, nother;
+  long long es, other_stride, nother, esF, other_strideF;
+  const long long hxF = p->hxF;
   if (axis == 1) {
     es = hx;
     other_stride = hx * p->dims[1];
     nother = p->dims[2];
+    esF = hxF;
+    other_strideF = hxF * p->dims[1];
   } else {
     es = hx * p->dims[1];
     other_stride = hx;
     nother = p->dims[1];
+    esF = hxF * p->dims[1];
+    other_strideF = hxF;
   }
   if (a.fast) {
-#define GSP_CALL(NN) launch_p2_strided<NN>(d->dc->stream, flags, H, a.lp.tw, es, (int)hx, nother, other_stride, Fh, s)
+#define GSP_CALL(NN) launch_p2_strided<NN>(d->dc->stream, d->dc->sms, flags, a.tmH, a.tmF, axis, H, a.lp.tw, es, (int)hx, nother, other_stride, s)
     GSP_P2_SWITCH(a.len, GSP_CALL)
 #undef GSP_CALL
   }
@@ -466,7 +487,7 @@ cudaError_t run_strided(FftDev* d, gsp_fft_plan* p, int axis, cplx* H, int flags
   dim3 grid((unsigned)((hx + a.B - 1) / a.B), (unsigned)nother);
   ProfScope prof_((flags & PASS_MUL) ? "fft_strided_fwd_mul_inv" : ((flags & PASS_FWD) ? "fft_strided_fwd" : "fft_strided_inv"),
                   d->dc->stream);
-  GSP_LAUNCH(kfn, grid, dim3(256), a.smem, d->dc->stream, a.lp, H, es, (int)hx, a.B, other_stride, flags, Fh, s);
+  GSP_LAUNCH(kfn, grid, dim3(256), a.smem, d->dc->stream, a.lp, H, es, (int)hx, a.B, other_stride, flags, Fh, esF, other_strideF, s);
   g_launches++;
   return cudaGetLastError();
 }
@@ -503,10 +524,24 @@ cudaError_t realization(FftDev* d, gsp_fft_plan* p, const double* w, double* out
 int build_device(gsp_ctx* ctx, gsp_fft_plan* p, FftDev* d, const CovDev& cov, const DomDev& dom, long long eref) {
   cudaSetDevice(d->dc->dev);
   GSP_TRY(setup_axes(ctx, p, d));
-  GSP_CUDA_OK(ctx, d->Fh.alloc(d->dc->dev, (size_t)p->nh * sizeof(double)));
+  GSP_CUDA_OK(ctx, d->Fh.alloc(d->dc->dev, (size_t)p->nhF * sizeof(double)));
+  GSP_CUDA_OK(ctx, cudaMemsetAsync(d->Fh.p, 0, (size_t)p->nhF * sizeof(double), d->dc->stream));
   GSP_CUDA_OK(ctx, d->H.alloc(d->dc->dev, (size_t)p->nh * sizeof(cplx)));
   GSP_CUDA_OK(ctx, cudaEventCreate(&d->ev0));
   GSP_CUDA_OK(ctx, cudaEventCreate(&d->ev1));
+  for (int axis = 1; axis < p->ndim; ++axis) {
+    AxisPlan& a = d->ax[axis];
+    if (!a.fast) continue;
+    const unsigned B = (unsigned)p2_bundle(a.len);
+    const unsigned long long dH[3] = {2ull * p->hx, (unsigned long long)p->dims[1], (unsigned long long)p->dims[2]};
+    const unsigned long long dF[3] = {(unsigned long long)p->hxF, (unsigned long long)p->dims[1], (unsigned long long)p->dims[2]};
+    const unsigned lbox = a.len < 256 ? (unsigned)a.len : 256u;
+    const unsigned boxH[3] = {2 * B, axis == 1 ? lbox : 1u, axis == 2 ? lbox : 1u};
+    const unsigned boxF[3] = {B, boxH[1], boxH[2]};
+    int r1 = make_tensor_map_f64(&a.tmH, d->H.p, dH, 16ull * p->hx, 16ull * p->hx * p->dims[1], boxH);
+    int r2 = make_tensor_map_f64(&a.tmF, d->Fh.p, dF, 8ull * p->hxF, 8ull * p->hxF * p->dims[1], boxF);
+    if (r1 != 0 || r2 != 0) return set_err(ctx, GSP_E_CUDA, "cuTensorMapEncodeTiled failed for an FFT pass (code " + std::to_string(r1 ? r1 : r2) + ")");
+  }
   DevBuf C, partial, total;
   GSP_CUDA_OK(ctx, C.alloc(d->dc->dev, (size_t)p->N * sizeof(double)));
   const int nblocks = d->dc->sms * 4;
@@ -516,7 +551,7 @@ int build_device(gsp_ctx* ctx, gsp_fft_plan* p, FftDev* d, const CovDev& cov, co
   GSP_CUDA_OK(ctx, cudaGetLastError());
   GSP_CUDA_OK(ctx, forward_all(d, p, C.as<double>()));
   GSP_LAUNCH(spectrum_finalize_kernel, dim3((unsigned)nblocks), dim3(256), 0, d->dc->stream, d->H.as<cplx>(), d->Fh.as<double>(),
-             p->nh, p->hx, (int)p->dims[0], partial.as<double>());
+             p->nh, p->hx, p->hxF, (int)p->dims[0], partial.as<double>());
   g_launches++;
   GSP_LAUNCH(sum_partials_kernel, dim3(1), dim3(256), 0, d->dc->stream, partial.as<double>(), nblocks, total.as<double>());
   g_launches++;
@@ -569,7 +604,9 @@ extern "C" int gsp_fft_plan_create(gsp_ctx* ctx, const gsp_cov_model* cov, const
     stride *= p->dims[a];
   }
   p->hx = (int)(p->dims[0] / 2 + 1);
+  p->hxF = (p->hx + 1) & ~1;
   p->nh = (long long)p->hx * p->dims[1] * p->dims[2];
+  p->nhF = (long long)p->hxF * p->dims[1] * p->dims[2];
   for (auto& dc : ctx->devs) {
     std::unique_ptr<FftDev> d(new FftDev);
     d->dc = &dc;
@@ -599,18 +636,18 @@ extern "C" int gsp_fft_plan_get(gsp_fft_plan* p, double* F) {
   if (!F) return set_err(ctx, -2, "F is NULL");
   FftDev* d = p->dev[0].get();
   cudaSetDevice(d->dc->dev);
-  std::vector<double> Fh((size_t)p->nh);
+  std::vector<double> Fh((size_t)p->nhF);
   GSP_CUDA_OK(ctx, cudaMemcpyAsync(Fh.data(), d->Fh.p, Fh.size() * sizeof(double), cudaMemcpyDeviceToHost, d->dc->stream));
   GSP_CUDA_OK(ctx, cudaStreamSynchronize(d->dc->stream));
-  const long long nx = p->dims[0], ny = p->dims[1], nz = p->dims[2], hx = p->hx;
+  const long long nx = p->dims[0], ny = p->dims[1], nz = p->dims[2], hx = p->hx, hxF = p->hxF;
   for (long long z = 0; z < nz; ++z)
     for (long long y = 0; y < ny; ++y)
       for (long long x = 0; x < nx; ++x) {
         double v;
         if (x < hx)
-          v = Fh[(size_t)(x + hx * (y + ny * z))];
+          v = Fh[(size_t)(x + hxF * (y + ny * z))];
         else
-          v = Fh[(size_t)((nx - x) + hx * (((ny - y) % ny) + ny * ((nz - z) % nz)))];
+          v = Fh[(size_t)((nx - x) + hxF * (((ny - y) % ny) + ny * ((nz - z) % nz)))];
         F[x + nx * (y + ny * z)] = v;
       }
   return GSP_OK;

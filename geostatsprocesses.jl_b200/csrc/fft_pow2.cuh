@@ -135,206 +135,284 @@ struct RowLay {  // x passes: one padded row per line, one extra element every 2
 enum { P2_FWD = 1, P2_MUL = 2, P2_INV = 4 };
 
 GSP_HD constexpr int p2_bundle(int N) { return N <= 512 ? 8 : (N <= 2048 ? 4 : 2); }
-GSP_HD constexpr int p2_units(int N) {
-  return ((N / p2_slots(N)) * p2_bundle(N) >= 256) ? 1 : 256 / ((N / p2_slots(N)) * p2_bundle(N));
-}
+
+// All three pass kernels are PERSISTENT and software-pipelined: a CTA walks over its work items
+// (line bundles / row groups); while it transforms item i out of shared-memory stage i&1, the TMA
+// engine (cp.async.bulk, completing on an mbarrier) is already filling stage (i+1)&1 with item i+1.
+// Results leave straight from registers with 16-byte streaming stores.
 
 // ------------------------------------------------------------------------------------------------
-// strided pass (y or z axis) over the half spectrum, in place.  One "unit" = B adjacent kx times the
-// whole line; a CTA holds U units.  FLAGS: FWD only / INV only / FWD|MUL|INV (last axis, fused).
-template <int N, int B, int U, int FLAGS>
-__global__ void __launch_bounds__((N / p2_slots(N)) * B * U) p2_strided_kernel(cplx* __restrict__ H, const cplx* __restrict__ twg, long long es,
-                                                                              int hx, int nbundles, long long nunits, long long other_stride,
-                                                                              const double* __restrict__ Fh, double s) {
-  constexpr int SL = p2_slots(N);
-  constexpr int TPL = N / SL;
-  constexpr int TPU = TPL * B;
+// strided pass (y or z axis) over the half spectrum, in place.  One item = B adjacent kx times the
+// whole line.  FLAGS: FWD only / INV only / FWD|MUL|INV (last axis: spectral multiply fused in).
+// F is stored with an even leading dimension (hxF) so that its 8-byte rows are 16-byte aligned (TMA global strides).
+template <int N, int B, int FLAGS>
+struct StridedCfg {
+  static constexpr int SL = p2_slots(N);
+  static constexpr int TPL = N / SL;
+  static constexpr int THREADS = TPL * B;
+  static constexpr bool MUL = (FLAGS & P2_MUL) != 0;
+  static constexpr size_t IN_BYTES = (size_t)N * B * sizeof(cplx);
+  static constexpr size_t F_BYTES = MUL ? (size_t)N * B * sizeof(double) : 0;
+  static constexpr size_t SMEM = (size_t)N * sizeof(cplx) + 2 * (IN_BYTES + F_BYTES) + 2 * sizeof(mbar_t) + 16;
+};
+
+template <int N, int B, int FLAGS>
+__global__ void __launch_bounds__(StridedCfg<N, B, FLAGS>::THREADS) p2_strided_kernel(const GSP_GRID_CONSTANT TensorMap tmH,
+                                                                                     const GSP_GRID_CONSTANT TensorMap tmF, int line_axis,
+                                                                                     cplx* __restrict__ H, const cplx* __restrict__ twg,
+                                                                                     long long es, int hx, int nbundles, long long nunits,
+                                                                                     long long other_stride, double s) {
+  using C = StridedCfg<N, B, FLAGS>;
+  constexpr int SL = C::SL, TPU = C::THREADS;
+  constexpr bool MUL = C::MUL;
   GSP_DYN_SMEM(smem);
   cplx* tw = reinterpret_cast<cplx*>(smem);
-  cplx* bufs = tw + N;
-  for (int i = threadIdx.x; i < N; i += TPU * U) tw[i] = twg[i];
-  const int u = threadIdx.x / TPU;
-  const int lt = threadIdx.x - u * TPU;
-  const int b = lt % B, t = lt / B;
-  cplx* buf = bufs + (size_t)u * N * B;
-  const long long unit = (long long)blockIdx.x * U + u;
-  const bool live = unit < nunits;
-  const long long o = live ? unit / nbundles : 0;
-  const int bx = live ? (int)(unit - o * nbundles) : 0;
-  const bool valid = live && (bx * B + b < hx);
-  const long long base = o * other_stride + (long long)bx * B + b;
-  const BundleLay lay{B, b};
-  constexpr bool FIRST_INV = (FLAGS & P2_FWD) == 0;
-  constexpr int R0 = p2_radix(N, FIRST_INV, 0);
-  cplx v[SL];
-#pragma unroll
-  for (int q = 0; q < SL / R0; ++q)
-#pragma unroll
-    for (int r = 0; r < R0; ++r) {
-      const int m = p2_in_pos<N, FIRST_INV, 0>(t, q, r);
-      cplx x{0.0, 0.0};
-      if (valid) {
-        const double2 d = ld_stream2(reinterpret_cast<const double*>(H + base + (long long)m * es));
-        x = cplx{d.x, d.y};
-      }
-      v[q * R0 + r] = x;
-    }
-  __syncthreads();  // twiddle table ready
-  if constexpr ((FLAGS & P2_FWD) != 0) p2_fft<N, false, 1>(v, t, buf, lay, tw);
-  if constexpr ((FLAGS & P2_MUL) != 0) {
-    // slot (q, r) now holds frequency f = p2_in_pos<N, true, 0>(t, q, r)
-    constexpr int RI = p2_radix(N, true, 0);
-#pragma unroll
-    for (int q = 0; q < SL / RI; ++q)
-#pragma unroll
-      for (int r = 0; r < RI; ++r) {
-        const int f = p2_in_pos<N, true, 0>(t, q, r);
-        const double fv = valid ? s * Fh[base + (long long)f * es] : 0.0;
-        const cplx w = v[q * RI + r];
-        const double m2 = w.re * w.re + w.im * w.im;
-        if (m2 > 0.0) {
-          const double g = fv * rsqrt(m2);
-          v[q * RI + r] = cplx{g * w.re, g * w.im};
-        } else {
-          v[q * RI + r] = cplx{fv, 0.0};
-        }
-      }
+  unsigned char* stage0 = smem + (size_t)N * sizeof(cplx);
+  mbar_t* full = reinterpret_cast<mbar_t*>(stage0 + 2 * (C::IN_BYTES + C::F_BYTES));
+  const int tid = threadIdx.x;
+  const int b = tid % B, t = tid / B;
+  if (tid == 0) {
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    fence_mbar_init();
   }
-  if constexpr ((FLAGS & P2_INV) != 0) p2_fft<N, true, 1>(v, t, buf, lay, tw);
-  // results: slot (q, r) of the LAST executed direction's opposite input mapping
-  constexpr bool LAST_INV = (FLAGS & P2_INV) != 0;
-  constexpr int RO = p2_radix(N, !LAST_INV, 0);
-  if (valid) {
+  for (int i = tid; i < N; i += TPU) tw[i] = twg[i];
+  __syncthreads();
+
+  auto stage_in = [&](int sg) { return reinterpret_cast<cplx*>(stage0 + (size_t)sg * (C::IN_BYTES + C::F_BYTES)); };
+  auto stage_f = [&](int sg) { return reinterpret_cast<double*>(stage0 + (size_t)sg * (C::IN_BYTES + C::F_BYTES) + C::IN_BYTES); };
+  // one TMA tensor copy per item and operand: box = (B kx as 2B doubles) x (whole line), zero-filled past hx
+  auto issue = [&](long long unit, int sg) {
+    if (tid == 0) {
+      const long long o = unit / nbundles;
+      const int bx = (int)(unit - o * nbundles);
+      const int c1 = line_axis == 1 ? 0 : (int)o, c2 = line_axis == 1 ? (int)o : 0;
+      mbar_arrive_expect_tx(&full[sg], (uint32_t)(C::IN_BYTES + C::F_BYTES));
+      constexpr int LBOX = N < 256 ? N : 256;  // TMA boxes are limited to 256 elements per dimension
 #pragma unroll
-    for (int q = 0; q < SL / RO; ++q)
-#pragma unroll
-      for (int r = 0; r < RO; ++r) {
-        const int m = p2_in_pos<N, !LAST_INV, 0>(t, q, r);
-        st_stream2(reinterpret_cast<double*>(H + base + (long long)m * es), make_double2(v[q * RO + r].re, v[q * RO + r].im));
+      for (int k = 0; k < N; k += LBOX) {
+        tma_load_3d(stage_in(sg) + (size_t)k * B, &tmH, bx * 2 * B, line_axis == 1 ? k : c1, line_axis == 1 ? c2 : k, &full[sg]);
+        if (MUL) tma_load_3d(stage_f(sg) + (size_t)k * B, &tmF, bx * B, line_axis == 1 ? k : c1, line_axis == 1 ? c2 : k, &full[sg]);
       }
+    }
+  };
+
+  long long unit = blockIdx.x;
+  if (unit < nunits) issue(unit, 0);
+  for (int it = 0; unit < nunits; unit += gridDim.x, ++it) {
+    const int cur = it & 1;
+    if (unit + gridDim.x < nunits) issue(unit + gridDim.x, cur ^ 1);
+    const long long o = unit / nbundles;
+    const int bx = (int)(unit - o * nbundles);
+    const bool valid = bx * B + b < hx;
+    const long long base = o * other_stride + (long long)bx * B + b;
+    cplx* buf = stage_in(cur);
+    const double* fb = stage_f(cur);
+    const BundleLay lay{B, b};
+    mbar_wait(&full[cur], (uint32_t)((it >> 1) & 1));
+    constexpr bool FIRST_INV = (FLAGS & P2_FWD) == 0;
+    constexpr int R0 = p2_radix(N, FIRST_INV, 0);
+    cplx v[SL];
+#pragma unroll
+    for (int q = 0; q < SL / R0; ++q)
+#pragma unroll
+      for (int r = 0; r < R0; ++r) v[q * R0 + r] = buf[lay(p2_in_pos<N, FIRST_INV, 0>(t, q, r))];
+    if constexpr ((FLAGS & P2_FWD) != 0) p2_fft<N, false, 1>(v, t, buf, lay, tw);
+    if constexpr (MUL) {
+      // slot (q, r) holds frequency f = p2_in_pos<N, true, 0>(t, q, r): P = s*F*W/|W|, angle(0) = 0 (fftsim.jl:125)
+      constexpr int RI = p2_radix(N, true, 0);
+#pragma unroll
+      for (int q = 0; q < SL / RI; ++q)
+#pragma unroll
+        for (int r = 0; r < RI; ++r) {
+          const double fv = s * fb[lay(p2_in_pos<N, true, 0>(t, q, r))];
+          const cplx w = v[q * RI + r];
+          const double m2 = w.re * w.re + w.im * w.im;
+          if (m2 > 0.0) {
+            const double g = fv * rsqrt(m2);
+            v[q * RI + r] = cplx{g * w.re, g * w.im};
+          } else {
+            v[q * RI + r] = cplx{fv, 0.0};
+          }
+        }
+    }
+    if constexpr ((FLAGS & P2_INV) != 0) p2_fft<N, true, 1>(v, t, buf, lay, tw);
+    constexpr bool LAST_INV = (FLAGS & P2_INV) != 0;
+    constexpr int RO = p2_radix(N, !LAST_INV, 0);
+    if (valid) {
+#pragma unroll
+      for (int q = 0; q < SL / RO; ++q)
+#pragma unroll
+        for (int r = 0; r < RO; ++r) {
+          const int m = p2_in_pos<N, !LAST_INV, 0>(t, q, r);
+          st_stream2(reinterpret_cast<double*>(H + base + (long long)m * es), make_double2(v[q * RO + r].re, v[q * RO + r].im));
+        }
+    }
+    fence_proxy_async();  // generic-proxy traffic on this stage is ordered before the next bulk fill
+    __syncthreads();
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// x-axis forward pass, even nx = 2*HN: real rows -> half spectrum rows (packed real-to-complex).
+// x-axis passes, even nx = 2*HN (packed real <-> complex).  One item = ROWS consecutive rows.
 template <int HN, bool INV>
 struct XCfg {
+  static constexpr int NX = 2 * HN, HX = HN + 1;
   static constexpr int SL = p2_slots(HN);
   static constexpr int TPL = HN / SL;                       // threads per row
-  static constexpr int ROWS = (TPL >= 256) ? 1 : 256 / TPL; // rows per CTA
+  static constexpr int ROWS = (TPL >= 128) ? 1 : 128 / TPL; // rows per item
   static constexpr int THREADS = TPL * ROWS;
   static constexpr int SH = p2_log2(p2_radix(HN, INV, 0));  // pad one element every R0: first exchange conflict-free
-  static constexpr int ROWLEN = HN + 1 + ((HN + 1) >> SH) + 1;  // padded row (holds k = 0..HN)
-  static constexpr size_t SMEM = (size_t)(2 * HN + ROWS * ROWLEN) * sizeof(cplx);
+  static constexpr int ROWLEN = HN + 1 + ((HN + 1) >> SH) + 1;
+  static constexpr size_t IN_BYTES = INV ? (size_t)ROWS * HX * sizeof(cplx) : (size_t)ROWS * NX * sizeof(double);
+  static constexpr size_t EX_BYTES = (size_t)ROWS * ROWLEN * sizeof(cplx);
+  static constexpr size_t SMEM = (size_t)NX * sizeof(cplx) + 2 * IN_BYTES + EX_BYTES + 2 * sizeof(mbar_t) + 16;
 };
 
 template <int HN>
 __global__ void __launch_bounds__(XCfg<HN, false>::THREADS) p2_xfwd_kernel(const double* __restrict__ in, cplx* __restrict__ H,
-                                                                   const cplx* __restrict__ twg, long long nrows) {
+                                                                          const cplx* __restrict__ twg, long long nrows) {
   using C = XCfg<HN, false>;
-  constexpr int NX = 2 * HN, HX = HN + 1, SL = C::SL, TPL = C::TPL;
+  constexpr int NX = C::NX, HX = C::HX, SL = C::SL, TPL = C::TPL;
   GSP_DYN_SMEM(smem);
   cplx* tw = reinterpret_cast<cplx*>(smem);  // exp(-2*pi*i*t/NX), t < NX
-  cplx* bufs = tw + NX;
-  for (int i = threadIdx.x; i < NX; i += C::THREADS) tw[i] = twg[i];
-  const int rl = threadIdx.x / TPL, t = threadIdx.x - rl * TPL;
-  const long long row = (long long)blockIdx.x * C::ROWS + rl;
-  const bool valid = row < nrows;
-  const RowLay<C::SH> lay{rl * C::ROWLEN};
-  constexpr int R0 = p2_radix(HN, false, 0);
-  cplx v[SL];
-  const double* src = in + row * NX;
-#pragma unroll
-  for (int q = 0; q < SL / R0; ++q)
-#pragma unroll
-    for (int r = 0; r < R0; ++r) {
-      const int m = p2_in_pos<HN, false, 0>(t, q, r);
-      cplx x{0.0, 0.0};
-      if (valid) {
-        const double2 d = ld_stream2(src + 2 * m);
-        x = cplx{d.x, d.y};
-      }
-      v[q * R0 + r] = x;
+  unsigned char* stage0 = smem + (size_t)NX * sizeof(cplx);
+  cplx* ex = reinterpret_cast<cplx*>(stage0 + 2 * C::IN_BYTES);
+  mbar_t* full = reinterpret_cast<mbar_t*>(stage0 + 2 * C::IN_BYTES + C::EX_BYTES);
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    fence_mbar_init();
+  }
+  for (int i = tid; i < NX; i += C::THREADS) tw[i] = twg[i];
+  __syncthreads();
+  const long long ngroups = (nrows + C::ROWS - 1) / C::ROWS;
+  auto issue = [&](long long g, int sg) {
+    if (tid == 0) {
+      const long long r0 = g * C::ROWS;
+      const long long nv = (nrows - r0 < C::ROWS) ? nrows - r0 : C::ROWS;
+      const uint32_t bytes = (uint32_t)(nv * NX * sizeof(double));
+      mbar_arrive_expect_tx(&full[sg], bytes);
+      bulk_g2s(stage0 + (size_t)sg * C::IN_BYTES, in + r0 * NX, bytes, &full[sg]);
     }
-  __syncthreads();
-  p2_fft<HN, false, 2>(v, t, bufs, lay, tw);
-  // untangle: X[f] = E + w^f * O with E = (Z[f] + conj Z[h-f])/2, O = -i (Z[f] - conj Z[h-f])/2
-  constexpr int RI = p2_radix(HN, true, 0);
-  __syncthreads();
+  };
+  const int rl = tid / TPL, t = tid - rl * TPL;
+  const RowLay<C::SH> lay{rl * C::ROWLEN};
+  long long g = blockIdx.x;
+  if (g < ngroups) issue(g, 0);
+  for (int it = 0; g < ngroups; g += gridDim.x, ++it) {
+    const int cur = it & 1;
+    if (g + gridDim.x < ngroups) issue(g + gridDim.x, cur ^ 1);
+    const long long row = g * C::ROWS + rl;
+    const bool valid = row < nrows;
+    const cplx* src = reinterpret_cast<const cplx*>(stage0 + (size_t)cur * C::IN_BYTES) + (size_t)rl * HN;
+    mbar_wait(&full[cur], (uint32_t)((it >> 1) & 1));
+    constexpr int R0 = p2_radix(HN, false, 0);
+    cplx v[SL];
 #pragma unroll
-  for (int q = 0; q < SL / RI; ++q)
+    for (int q = 0; q < SL / R0; ++q)
 #pragma unroll
-    for (int r = 0; r < RI; ++r) bufs[lay(p2_in_pos<HN, true, 0>(t, q, r))] = v[q * RI + r];
-  __syncthreads();
-  if (valid) {
-    cplx* dst = H + row * HX;
+      for (int r = 0; r < R0; ++r) v[q * R0 + r] = src[p2_in_pos<HN, false, 0>(t, q, r)];
+    p2_fft<HN, false, 2>(v, t, ex, lay, tw);
+    // untangle: X[f] = E + w^f * O with E = (Z[f] + conj Z[h-f])/2, O = -i (Z[f] - conj Z[h-f])/2
+    constexpr int RI = p2_radix(HN, true, 0);
+    __syncthreads();
 #pragma unroll
     for (int q = 0; q < SL / RI; ++q)
 #pragma unroll
-      for (int r = 0; r < RI; ++r) {
-        const int f = p2_in_pos<HN, true, 0>(t, q, r);
-        const cplx zk = v[q * RI + r];
-        const cplx zc = cconj(bufs[lay((HN - f) & (HN - 1))]);
-        const cplx e = cplx{0.5 * (zk.re + zc.re), 0.5 * (zk.im + zc.im)};
-        const cplx d = csub(zk, zc);
-        const cplx od = cplx{0.5 * d.im, -0.5 * d.re};
-        const cplx o = cadd(e, cmul(tw[f], od));
-        st_stream2(reinterpret_cast<double*>(dst + f), make_double2(o.re, o.im));
-        if (f == 0) st_stream2(reinterpret_cast<double*>(dst + HN), make_double2(zk.re - zk.im, 0.0));
-      }
+      for (int r = 0; r < RI; ++r) ex[lay(p2_in_pos<HN, true, 0>(t, q, r))] = v[q * RI + r];
+    __syncthreads();
+    if (valid) {
+      cplx* dst = H + row * HX;
+#pragma unroll
+      for (int q = 0; q < SL / RI; ++q)
+#pragma unroll
+        for (int r = 0; r < RI; ++r) {
+          const int f = p2_in_pos<HN, true, 0>(t, q, r);
+          const cplx zk = v[q * RI + r];
+          const cplx zc = cconj(ex[lay((HN - f) & (HN - 1))]);
+          const cplx e = cplx{0.5 * (zk.re + zc.re), 0.5 * (zk.im + zc.im)};
+          const cplx d = csub(zk, zc);
+          const cplx od = cplx{0.5 * d.im, -0.5 * d.re};
+          const cplx o = cadd(e, cmul(tw[f], od));
+          st_stream2(reinterpret_cast<double*>(dst + f), make_double2(o.re, o.im));
+          if (f == 0) st_stream2(reinterpret_cast<double*>(dst + HN), make_double2(zk.re - zk.im, 0.0));
+        }
+    }
+    fence_proxy_async();
+    __syncthreads();
   }
 }
 
 // x-axis inverse pass: half spectrum rows -> real rows; out = scale * (unnormalised inverse DFT) + mu
 template <int HN>
 __global__ void __launch_bounds__(XCfg<HN, true>::THREADS) p2_xinv_kernel(const cplx* __restrict__ H, double* __restrict__ out,
-                                                                   const cplx* __restrict__ twg, long long nrows, double scale, double mu) {
+                                                                         const cplx* __restrict__ twg, long long nrows, double scale, double mu) {
   using C = XCfg<HN, true>;
-  constexpr int NX = 2 * HN, HX = HN + 1, SL = C::SL, TPL = C::TPL;
+  constexpr int NX = C::NX, HX = C::HX, SL = C::SL, TPL = C::TPL;
   GSP_DYN_SMEM(smem);
   cplx* tw = reinterpret_cast<cplx*>(smem);
-  cplx* bufs = tw + NX;
-  for (int i = threadIdx.x; i < NX; i += C::THREADS) tw[i] = twg[i];
-  const int rl = threadIdx.x / TPL, t = threadIdx.x - rl * TPL;
-  const long long row = (long long)blockIdx.x * C::ROWS + rl;
-  const bool valid = row < nrows;
-  const RowLay<C::SH> lay{rl * C::ROWLEN};
-  const cplx* src = H + row * HX;
-  // stage the row (k = 0..HN) in shared memory: the pre-processing pairs k with HN-k
-  for (int k = t; k < HX; k += TPL) {
-    cplx x{0.0, 0.0};
-    if (valid) {
-      const double2 d = ld_stream2(reinterpret_cast<const double*>(src + k));
-      x = cplx{d.x, d.y};
-    }
-    bufs[lay(k)] = x;
+  unsigned char* stage0 = smem + (size_t)NX * sizeof(cplx);
+  cplx* ex = reinterpret_cast<cplx*>(stage0 + 2 * C::IN_BYTES);
+  mbar_t* full = reinterpret_cast<mbar_t*>(stage0 + 2 * C::IN_BYTES + C::EX_BYTES);
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    fence_mbar_init();
   }
+  for (int i = tid; i < NX; i += C::THREADS) tw[i] = twg[i];
   __syncthreads();
-  constexpr int R0 = p2_radix(HN, true, 0);
-  cplx v[SL];
-#pragma unroll
-  for (int q = 0; q < SL / R0; ++q)
-#pragma unroll
-    for (int r = 0; r < R0; ++r) {
-      const int m = p2_in_pos<HN, true, 0>(t, q, r);
-      const cplx xk = bufs[lay(m)];
-      const cplx xc = cconj(bufs[lay(HN - m)]);
-      const cplx sm = cadd(xk, xc);
-      const cplx d = csub(xk, xc);
-      const cplx tt = cmul(cconj(tw[m]), d);
-      v[q * R0 + r] = cplx{sm.re - tt.im, sm.im + tt.re};
+  const long long ngroups = (nrows + C::ROWS - 1) / C::ROWS;
+  auto issue = [&](long long g, int sg) {
+    if (tid == 0) {
+      const long long r0 = g * C::ROWS;
+      const long long nv = (nrows - r0 < C::ROWS) ? nrows - r0 : C::ROWS;
+      const uint32_t bytes = (uint32_t)(nv * HX * sizeof(cplx));
+      mbar_arrive_expect_tx(&full[sg], bytes);
+      bulk_g2s(stage0 + (size_t)sg * C::IN_BYTES, H + r0 * HX, bytes, &full[sg]);
     }
-  p2_fft<HN, true, 2>(v, t, bufs, lay, tw);
-  constexpr int RO = p2_radix(HN, false, 0);
-  if (valid) {
-    double* dst = out + row * NX;
+  };
+  const int rl = tid / TPL, t = tid - rl * TPL;
+  const RowLay<C::SH> lay{rl * C::ROWLEN};
+  long long g = blockIdx.x;
+  if (g < ngroups) issue(g, 0);
+  for (int it = 0; g < ngroups; g += gridDim.x, ++it) {
+    const int cur = it & 1;
+    if (g + gridDim.x < ngroups) issue(g + gridDim.x, cur ^ 1);
+    const long long row = g * C::ROWS + rl;
+    const bool valid = row < nrows;
+    const cplx* X = reinterpret_cast<const cplx*>(stage0 + (size_t)cur * C::IN_BYTES) + (size_t)rl * HX;
+    mbar_wait(&full[cur], (uint32_t)((it >> 1) & 1));
+    constexpr int R0 = p2_radix(HN, true, 0);
+    cplx v[SL];
 #pragma unroll
-    for (int q = 0; q < SL / RO; ++q)
+    for (int q = 0; q < SL / R0; ++q)
 #pragma unroll
-      for (int r = 0; r < RO; ++r) {
-        const int j = p2_in_pos<HN, false, 0>(t, q, r);
-        st_stream2(dst + 2 * j, make_double2(v[q * RO + r].re * scale + mu, v[q * RO + r].im * scale + mu));
+      for (int r = 0; r < R0; ++r) {
+        const int m = p2_in_pos<HN, true, 0>(t, q, r);
+        const cplx xk = X[m];
+        const cplx xc = cconj(X[HN - m]);
+        const cplx sm = cadd(xk, xc);
+        const cplx d = csub(xk, xc);
+        const cplx tt = cmul(cconj(tw[m]), d);
+        v[q * R0 + r] = cplx{sm.re - tt.im, sm.im + tt.re};
       }
+    p2_fft<HN, true, 2>(v, t, ex, lay, tw);
+    constexpr int RO = p2_radix(HN, false, 0);
+    if (valid) {
+      double* dst = out + row * NX;
+#pragma unroll
+      for (int q = 0; q < SL / RO; ++q)
+#pragma unroll
+        for (int r = 0; r < RO; ++r) {
+          const int j = p2_in_pos<HN, false, 0>(t, q, r);
+          st_stream2(dst + 2 * j, make_double2(v[q * RO + r].re * scale + mu, v[q * RO + r].im * scale + mu));
+        }
+    }
+    fence_proxy_async();
+    __syncthreads();
   }
 }
 

@@ -120,6 +120,53 @@ GSP_DEV void bulk_g2s(void* dst, const void* src, uint32_t bytes, mbar_t* b) {
 }
 #endif
 
+// ------------------------------------------------------------------ TMA tensor copies (3-D tiled, no swizzle)
+#ifdef GSP_EMU
+struct TensorMap {
+  const unsigned char* base;
+  unsigned long long dims[3];     // extents in elements, dim 0 fastest
+  unsigned long long strides[3];  // byte strides (strides[0] = element size)
+  unsigned box[3];
+  unsigned esize;
+};
+#define GSP_GRID_CONSTANT
+// dst (shared, dense box, dim 0 fastest) <- tile at element coordinates (c0, c1, c2); out-of-bounds elements are zero
+GSP_DEV void tma_load_3d(void* dst, const TensorMap* tm, int c0, int c1, int c2, mbar_t* b) {
+  unsigned char* d = (unsigned char*)dst;
+  size_t bytes = 0;
+  for (unsigned k = 0; k < tm->box[2]; ++k)
+    for (unsigned j = 0; j < tm->box[1]; ++j)
+      for (unsigned i = 0; i < tm->box[0]; ++i) {
+        const long long x = c0 + (long long)i, y = c1 + (long long)j, z = c2 + (long long)k;
+        const bool in = x >= 0 && y >= 0 && z >= 0 && (unsigned long long)x < tm->dims[0] && (unsigned long long)y < tm->dims[1] &&
+                        (unsigned long long)z < tm->dims[2];
+        if (in)
+          memcpy(d + bytes, tm->base + x * tm->strides[0] + y * tm->strides[1] + z * tm->strides[2], tm->esize);
+        else
+          memset(d + bytes, 0, tm->esize);
+        bytes += tm->esize;
+      }
+  b->tx -= (int)bytes;
+  mbar_check_(b);
+}
+#else
+}  // namespace gsp
+#include <cuda.h>
+namespace gsp {
+typedef CUtensorMap TensorMap;
+#define GSP_GRID_CONSTANT __grid_constant__
+GSP_DEV void tma_load_3d(void* dst, const TensorMap* tm, int c0, int c1, int c2, mbar_t* b) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(tm), "r"(smem_u32(b)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+#endif
+// host: FP64 tensor `base` with extents dims[3] (elements), byte strides of dims 1 and 2, tile box[3].  Returns 0 on success.
+int make_tensor_map_f64(TensorMap* out, const void* base, const unsigned long long dims[3], unsigned long long stride1_bytes,
+                        unsigned long long stride2_bytes, const unsigned box[3]);
+
 // streaming (read-once / write-once) 16-byte global accesses
 GSP_DEV double2 ld_stream2(const double* p) {
 #ifdef GSP_EMU

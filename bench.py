@@ -207,11 +207,13 @@ def run_gpu(args):
         plan.sample_dev(Rg, w.data_ptr(), 0, r0, 1.0, 0.0, 0, None, z.data_ptr())
         return lib.last_sample_ms()
 
-    for _ in range(max(args.warmup, 3)):
-        step()
     sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.start()  # started before the warm-up so that nvidia-smi is already sampling when the timed region begins
+    step()
+    time.sleep(0.5 if rank == 0 else 0.0)
+    for _ in range(max(args.warmup, 3)):
+        step()
     launches0 = lib.kernel_launches()
     barrier()
     t0 = time.perf_counter()

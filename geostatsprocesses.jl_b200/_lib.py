@@ -65,6 +65,7 @@ SIGNATURES = {
     "gsp_lu_plan_create": (C.c_int, [_vp, C.POINTER(_CovModel), C.POINTER(_Domain), C.c_int64, _vp, _vp, C.c_double, C.POINTER(_vp)]),
     "gsp_lu_plan_destroy": (C.c_int, [_vp]),
     "gsp_lu_plan_sizes": (C.c_int, [_vp, C.POINTER(C.c_int64 * 3)]),
+    "gsp_lu_plan_times": (C.c_int, [_vp, C.POINTER(C.c_double * 3)]),
     "gsp_lu_plan_get": (C.c_int, [_vp, _vp, _vp]),
     "gsp_lu_sample": (C.c_int, [_vp, C.c_int64, _vp, C.c_uint64, C.c_int32, C.c_int64, C.c_double, _vp, _vp]),
     "gsp_lu_sample_dev": (C.c_int, [_vp, C.c_int64, _vp, C.c_int64, C.c_uint64, C.c_int32, C.c_int64, C.c_double, _vp, _vp, C.c_int64]),
@@ -222,6 +223,12 @@ class LUPlan:
         sizes = (C.c_int64 * 3)()
         lib.check(lib.lib.gsp_lu_plan_sizes(h, C.byref(sizes)))
         self.N, self.Nd, self.Ns = int(sizes[0]), int(sizes[1]), int(sizes[2])
+
+    def times(self):
+        """device ms of (assembly, Cholesky, d2 solve)"""
+        ms = (C.c_double * 3)()
+        self.lib.check(self.lib.lib.gsp_lu_plan_times(self.h, C.byref(ms)))
+        return float(ms[0]), float(ms[1]), float(ms[2])
 
     def get(self):
         d2 = np.empty(self.Ns)

@@ -158,7 +158,10 @@ extern "C" int gsp_ctx_create(int32_t ndev, const int32_t* devs, gsp_ctx** out) 
   }
   for (auto& dc : ctx->devs) {
     cudaError_t e = cudaSetDevice(dc.dev);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&dc.stream, cudaStreamNonBlocking);
+    int prio_lo = 0, prio_hi = 0;
+    if (e == cudaSuccess) e = cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&dc.stream, cudaStreamNonBlocking, prio_hi);
+    for (int k = 0; k < DevCtx::kSide && e == cudaSuccess; ++k) e = cudaStreamCreateWithPriority(&dc.side[k], cudaStreamNonBlocking, prio_lo);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&dc.h2d, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&dc.d2h, cudaStreamNonBlocking);
     cudaDeviceProp prop;
@@ -179,6 +182,8 @@ extern "C" int gsp_ctx_destroy(gsp_ctx* ctx) {
   for (auto& dc : ctx->devs) {
     cudaSetDevice(dc.dev);
     if (dc.stream) cudaStreamDestroy(dc.stream);
+    for (int k = 0; k < DevCtx::kSide; ++k)
+      if (dc.side[k]) cudaStreamDestroy(dc.side[k]);
     if (dc.h2d) cudaStreamDestroy(dc.h2d);
     if (dc.d2h) cudaStreamDestroy(dc.d2h);
   }
@@ -277,7 +282,7 @@ extern "C" int gsp_potrf(gsp_ctx* ctx, int64_t n, double* A) {
     else pad[(size_t)j * np + j] = 1.0;
   }
   GSP_CUDA_OK(ctx, cudaMemcpyAsync(dA.p, pad.data(), pad.size() * sizeof(double), cudaMemcpyHostToDevice, dc.stream));
-  GSP_CUDA_OK(ctx, chol_factor(dc.stream, dA.as<double>(), np, nb, dinv.as<double>(), dinfo.as<int>()));
+  GSP_CUDA_OK(ctx, chol_factor(dc.stream, dc.side, DevCtx::kSide, dA.as<double>(), np, nb, dinv.as<double>(), dinfo.as<int>()));
   int info = 0;
   GSP_CUDA_OK(ctx, cudaMemcpyAsync(&info, dinfo.p, sizeof(int), cudaMemcpyDeviceToHost, dc.stream));
   GSP_CUDA_OK(ctx, cudaMemcpyAsync(pad.data(), dA.p, pad.size() * sizeof(double), cudaMemcpyDeviceToHost, dc.stream));

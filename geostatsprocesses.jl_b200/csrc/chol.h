@@ -7,13 +7,15 @@ namespace gsp {
 // A: (nblocks*128)^2 column-major, lower triangle read; on return lower = L, diagonal blocks have
 // zero strict-upper part.  invD: nblocks * 128*128 doubles (inverse of every diagonal block of L).
 // *info (device int): 0 or 1-based index of the first non-positive pivot.
-cudaError_t chol_factor(cudaStream_t st, double* A, long long ld, int nblocks, double* invD, int* info);
+// `side[nside]`: low-priority streams used for look-ahead (the bulk of every trailing update runs there while
+// the next diagonal block / panel proceeds on `st`); everything is joined back into `st` before returning.
+cudaError_t chol_factor(cudaStream_t st, cudaStream_t* side, int nside, double* A, long long ld, int nblocks, double* invD, int* info);
 // z[0 : nblocks*128] <- L^{-1} z  for the leading nblocks diagonal blocks
 cudaError_t chol_forward_solve(cudaStream_t st, const double* L, long long ld, const double* invD, int nblocks, double* z);
 // out[i] = sum_{k<kn} L[row0+i][k] y[k]
 cudaError_t chol_gemv_rows(cudaStream_t st, const double* L, long long ld, long long row0, long long nrows, int kn,
                            const double* y, double* out);
-// Z[sinds[i] + r*ldz] = d2[i] + addmu + sum_k L22[i][k] Wp[k + r*ldw]   (lusim.jl:162)
+// Z[sinds[i] + r*ldz] = d2[i] + addmu + sum_k L22[i][k] Wt[r + k*ldw]   (lusim.jl:162; Wt = realization-major noise)
 cudaError_t sample_gemm(cudaStream_t st, const double* L22, long long ld, int mt, const double* Wp, long long ldw, int nt,
                         double* Z, long long ldz, const double* d2, const long long* sinds, double addmu, long long Ns,
                         long long R);

@@ -44,9 +44,11 @@ struct ProfScope {
 
 struct DevCtx {
   int dev = 0;
-  cudaStream_t stream = nullptr;   // compute
+  cudaStream_t stream = nullptr;   // compute (highest priority: carries the critical path)
   cudaStream_t h2d = nullptr;      // copy-in
   cudaStream_t d2h = nullptr;      // copy-out
+  static constexpr int kSide = 8;
+  cudaStream_t side[kSide] = {};   // low-priority streams for look-ahead work (one per recursion depth)
   int sms = 148;
   size_t smem_optin = 227 * 1024;
 };

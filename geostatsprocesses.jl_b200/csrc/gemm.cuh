@@ -8,22 +8,32 @@
 // doubles (ld = 4 mod 16) which makes every 8-byte fragment load bank-conflict-free.
 // All matrices are column-major with extents padded to multiples of 128 (K to 16) by the callers.
 #pragma once
+#include <cstdlib>
+
 #include "common.h"
 
 namespace gsp {
 
-constexpr int GT = 128;        // C tile edge
+constexpr int GT = 128;        // block granularity of all callers (matrices are padded to multiples of 128)
 constexpr int GKC = 16;        // K chunk per stage
 constexpr int GSTAGES = 4;
-constexpr int GLDA = GT + 4;   // smem leading dim of [k][m] operand tiles (132 = 4 mod 16)
 constexpr int GLDBK = GKC + 4; // smem leading dim of [n][k] operand tiles (20 = 4 mod 16)
-constexpr int G_A_BYTES = GKC * GLDA * 8;                         // 16896
-constexpr int G_B_BYTES = (GT * GLDBK * 8 > G_A_BYTES) ? GT * GLDBK * 8 : G_A_BYTES;  // 20480
-constexpr int G_STAGE_BYTES = G_A_BYTES + G_B_BYTES;              // 37376
-constexpr int G_SMEM_BYTES = GSTAGES * G_STAGE_BYTES + 2 * GSTAGES * 16 + 128;
-constexpr int G_THREADS = 288;  // 8 consumer warps + 1 producer warp
 
 enum GemmMode { GEMM_SET = 0, GEMM_SUB = 1, GEMM_SAMPLE = 2 };
+
+// tile shapes: TM x TN per CTA, WM x WN consumer warps, each warp owns (TM/WM) x (TN/WN)
+template <int TM, int TN, int WM, int WN>
+struct GemmCfg {
+  static constexpr int LDA = TM + 4;  // = 4 mod 16: conflict-free 8-byte fragment loads
+  static constexpr int LDB = TN + 4;
+  static constexpr int A_BYTES = GKC * LDA * 8;
+  static constexpr int B_BYTES = (TN * GLDBK * 8 > GKC * LDB * 8) ? TN * GLDBK * 8 : GKC * LDB * 8;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int SMEM_BYTES = GSTAGES * STAGE_BYTES + 2 * GSTAGES * 16 + 128;
+  static constexpr int CWARPS = WM * WN;
+  static constexpr int THREADS = (CWARPS + 1) * 32;  // + 1 producer warp
+  static constexpr int FM = TM / WM / 8, FN = TN / WN / 8;  // DMMA fragments per warp
+};
 
 struct GemmArgs {
   const double* A;   // M x K, A[i + k*lda]
@@ -32,10 +42,10 @@ struct GemmArgs {
   long long ldb;
   double* C;         // M x N, C[i + j*ldc]
   long long ldc;
-  int mt, nt;        // tiles along M and N
+  int mt, nt;        // tiles along M and N (in units of TM / TN)
   int K;             // multiple of GKC
-  int tri;           // 1: only tiles with ti >= tj (mt == nt)
-  int klimit;        // 1: A is lower triangular -> k < (ti+1)*GT only
+  int tri;           // 1: only tiles with ti >= tj (TM == TN)
+  int klimit;        // 1: A is lower triangular -> k < (ti+1)*TM only
   // GEMM_SAMPLE epilogue: Z[sinds[i] + r*ldz] = acc + d2[i] + addmu for i < Ns, r < R
   const double* d2;
   const long long* sinds;
@@ -43,12 +53,13 @@ struct GemmArgs {
   long long Ns, R;
 };
 
-template <int MODE, bool BK>
-__global__ void __launch_bounds__(G_THREADS, 1) gemm_dmma_kernel(GemmArgs g) {
+template <int MODE, bool BK, int TM, int TN, int WM, int WN>
+__global__ void __launch_bounds__(GemmCfg<TM, TN, WM, WN>::THREADS, 1) gemm_dmma_kernel(GemmArgs g) {
+  using C_ = GemmCfg<TM, TN, WM, WN>;
+  constexpr int LDA = C_::LDA, LDB = C_::LDB, FM = C_::FM, FN = C_::FN, CW = C_::CWARPS;
   GSP_DYN_SMEM(smem);
-  // carve: stages first (16-byte aligned), then barriers
   unsigned char* stage_base = smem;
-  mbar_t* full = reinterpret_cast<mbar_t*>(smem + GSTAGES * G_STAGE_BYTES);
+  mbar_t* full = reinterpret_cast<mbar_t*>(smem + GSTAGES * C_::STAGE_BYTES);
   mbar_t* empty = full + GSTAGES;
 
   // tile coordinates
@@ -61,15 +72,18 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_dmma_kernel(GemmArgs g) {
       while ((long long)i * (i + 1) / 2 > t) --i;
       ti = i;
       tj = (int)(t - (long long)i * (i + 1) / 2);
+    } else if (g.klimit) {
+      // lower-triangular A: row tile ti costs (ti+1) chunks -> heaviest rows first, columns fastest (LPT order)
+      tj = (int)(t % g.nt);
+      ti = g.mt - 1 - (int)(t / g.nt);
     } else {
       ti = (int)(t % g.mt);
       tj = (int)(t / g.mt);
-      if (g.klimit) ti = g.mt - 1 - ti;  // heaviest row tiles first
     }
   }
   int kend = g.K;
   if (g.klimit) {
-    long long lim = (long long)(ti + 1) * GT;
+    long long lim = (long long)(ti + 1) * TM;
     if (lim < kend) kend = (int)lim;
   }
   const int nchunks = kend / GKC;
@@ -78,34 +92,34 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_dmma_kernel(GemmArgs g) {
   if (threadIdx.x == 0) {
     for (int s = 0; s < GSTAGES; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 8);
+      mbar_init(&empty[s], CW);
     }
     fence_mbar_init();
   }
   __syncthreads();
 
-  if (warp == 8) {
+  if (warp == CW) {
     // ------------------------------------------------------------ producer
-    const double* Abase = g.A + (long long)ti * GT;
-    const double* Bbase = BK ? g.B + (long long)tj * GT * g.ldb : g.B + (long long)tj * GT;
+    const double* Abase = g.A + (long long)ti * TM;
+    const double* Bbase = BK ? g.B + (long long)tj * TN * g.ldb : g.B + (long long)tj * TN;
     for (int c = 0; c < nchunks; ++c) {
       const int s = c % GSTAGES;
       const uint32_t ph = (uint32_t)((c / GSTAGES) & 1);
       mbar_wait(&empty[s], ph ^ 1u);
-      unsigned char* sa = stage_base + s * G_STAGE_BYTES;
-      unsigned char* sb = sa + G_A_BYTES;
+      unsigned char* sa = stage_base + s * C_::STAGE_BYTES;
+      unsigned char* sb = sa + C_::A_BYTES;
       const long long k0 = (long long)c * GKC;
-      if (lane == 0) mbar_arrive_expect_tx(&full[s], (uint32_t)(2 * GKC * GT * 8));
+      if (lane == 0) mbar_arrive_expect_tx(&full[s], (uint32_t)(GKC * (TM + TN) * 8));
       __syncwarp();
       if (lane < GKC) {
-        bulk_g2s(sa + lane * GLDA * 8, Abase + (k0 + lane) * g.lda, GT * 8, &full[s]);
+        bulk_g2s(sa + lane * LDA * 8, Abase + (k0 + lane) * g.lda, TM * 8, &full[s]);
       } else if (!BK) {
         const int l = lane - GKC;
-        bulk_g2s(sb + l * GLDA * 8, Bbase + (k0 + l) * g.ldb, GT * 8, &full[s]);
+        bulk_g2s(sb + l * LDB * 8, Bbase + (k0 + l) * g.ldb, TN * 8, &full[s]);
       }
       if (BK) {
 #pragma unroll
-        for (int i = 0; i < GT / 32; ++i) {
+        for (int i = 0; i < TN / 32; ++i) {
           const int n = lane + 32 * i;
           bulk_g2s(sb + n * GLDBK * 8, Bbase + k0 + (long long)n * g.ldb, GKC * 8, &full[s]);
         }
@@ -115,48 +129,48 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_dmma_kernel(GemmArgs g) {
   }
 
   // -------------------------------------------------------------- consumers
-  const int wm = warp & 1, wn = warp >> 1;  // 2 x 4 warps -> 64 x 32 sub-tiles
+  const int wm = warp % WM, wn = warp / WM;
   const int lr = lane >> 2, lk = lane & 3;
-  double acc[8][4][2];
+  double acc[FM][FN][2];
 #pragma unroll
-  for (int a = 0; a < 8; ++a)
+  for (int a = 0; a < FM; ++a)
 #pragma unroll
-    for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+    for (int b = 0; b < FN; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
 
   for (int c = 0; c < nchunks; ++c) {
     const int s = c % GSTAGES;
     const uint32_t ph = (uint32_t)((c / GSTAGES) & 1);
     mbar_wait(&full[s], ph);
-    const double* sa = reinterpret_cast<const double*>(stage_base + s * G_STAGE_BYTES);
-    const double* sb = reinterpret_cast<const double*>(stage_base + s * G_STAGE_BYTES + G_A_BYTES);
+    const double* sa = reinterpret_cast<const double*>(stage_base + s * C_::STAGE_BYTES);
+    const double* sb = reinterpret_cast<const double*>(stage_base + s * C_::STAGE_BYTES + C_::A_BYTES);
 #pragma unroll
     for (int k4 = 0; k4 < GKC / 4; ++k4) {
       const int k = k4 * 4 + lk;
-      double af[8], bf[4];
+      double af[FM], bf[FN];
 #pragma unroll
-      for (int a = 0; a < 8; ++a) af[a] = sa[k * GLDA + wm * 64 + a * 8 + lr];
+      for (int a = 0; a < FM; ++a) af[a] = sa[k * LDA + wm * (TM / WM) + a * 8 + lr];
 #pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        const int n = wn * 32 + b * 8 + lr;
-        bf[b] = BK ? sb[n * GLDBK + k] : sb[k * GLDA + n];
+      for (int b = 0; b < FN; ++b) {
+        const int n = wn * (TN / WN) + b * 8 + lr;
+        bf[b] = BK ? sb[n * GLDBK + k] : sb[k * LDB + n];
       }
 #pragma unroll
-      for (int a = 0; a < 8; ++a)
+      for (int a = 0; a < FM; ++a)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) dmma884(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+        for (int b = 0; b < FN; ++b) dmma884(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[s]);
   }
 
   // -------------------------------------------------------------- epilogue
-  const long long row0 = (long long)ti * GT + wm * 64 + lr;
-  const long long col0 = (long long)tj * GT + wn * 32 + 2 * lk;
+  const long long row0 = (long long)ti * TM + wm * (TM / WM) + lr;
+  const long long col0 = (long long)tj * TN + wn * (TN / WN) + 2 * lk;
 #pragma unroll
-  for (int a = 0; a < 8; ++a) {
+  for (int a = 0; a < FM; ++a) {
     const long long i = row0 + a * 8;
 #pragma unroll
-    for (int b = 0; b < 4; ++b) {
+    for (int b = 0; b < FN; ++b) {
       const long long j = col0 + b * 8;
       if (MODE == GEMM_SET) {
         g.C[i + j * g.ldc] = acc[a][b][0];
@@ -178,18 +192,44 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_dmma_kernel(GemmArgs g) {
   }
 }
 
-template <int MODE, bool BK>
-inline cudaError_t launch_gemm(cudaStream_t st, const GemmArgs& g) {
-  auto kfn = gemm_dmma_kernel<MODE, BK>;
+template <int MODE, bool BK, int TM, int TN, int WM, int WN>
+inline cudaError_t launch_gemm_cfg(cudaStream_t st, const GemmArgs& g) {
+  using C_ = GemmCfg<TM, TN, WM, WN>;
+  auto kfn = gemm_dmma_kernel<MODE, BK, TM, TN, WM, WN>;
   // per-device attribute, cheap host-side call: set it on every launch (multi-device contexts)
-  cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM_BYTES);
+  cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM_BYTES);
   if (e != cudaSuccess) return e;
   long long tiles = g.tri ? (long long)g.mt * (g.mt + 1) / 2 : (long long)g.mt * g.nt;
   if (tiles <= 0 || g.K <= 0) return cudaSuccess;
   ProfScope prof_(MODE == GEMM_SAMPLE ? "gemm_dmma_sample" : (MODE == GEMM_SET ? "gemm_dmma_trsm" : "gemm_dmma_update"), st);
-  GSP_LAUNCH(kfn, dim3((unsigned)tiles), dim3(G_THREADS), (size_t)G_SMEM_BYTES, st, g);
+  GSP_LAUNCH(kfn, dim3((unsigned)tiles), dim3(C_::THREADS), (size_t)C_::SMEM_BYTES, st, g);
   g_launches++;
   return cudaGetLastError();
+}
+
+// `g.mt`, `g.nt` are given in 128-blocks.  Problems with too few 128x128 tiles to fill the GPU are
+// retiled to 64-row (in-place TRSM: the C tile must span all 128 columns) or 64x64 tiles: 2-4x more CTAs
+// on the latency-bound small GEMMs of the factorisation's critical path.
+template <int MODE, bool BK>
+inline cudaError_t launch_gemm(cudaStream_t st, const GemmArgs& g0) {
+  const long long tiles128 = g0.tri ? (long long)g0.mt * (g0.mt + 1) / 2 : (long long)g0.mt * g0.nt;
+  static long long kSmall = -1;  // GSP_GEMM_SMALL_TILES overrides the retiling threshold (tests force either path)
+  if (kSmall < 0) {
+    const char* env = getenv("GSP_GEMM_SMALL_TILES");
+    kSmall = env ? atoll(env) : 100;
+  }
+  if (MODE == GEMM_SET && !BK && tiles128 < kSmall) {
+    GemmArgs g = g0;
+    g.mt = 2 * g0.mt;
+    return launch_gemm_cfg<MODE, BK, 64, 128, 2, 4>(st, g);
+  }
+  if (MODE == GEMM_SUB && !BK && tiles128 < kSmall) {
+    GemmArgs g = g0;
+    g.mt = 2 * g0.mt;
+    g.nt = 2 * g0.nt;
+    return launch_gemm_cfg<MODE, BK, 64, 64, 2, 2>(st, g);
+  }
+  return launch_gemm_cfg<MODE, BK, 128, 128, 2, 4>(st, g0);
 }
 
 }  // namespace gsp

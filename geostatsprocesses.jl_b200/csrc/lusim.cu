@@ -36,14 +36,21 @@ __global__ void __launch_bounds__(256) scatter_data_kernel(double* __restrict__ 
   }
 }
 
-// dst[i + r*ldd] = (i < rows && r < cols) ? src[i + r*lds] : 0   for i < rows_pad, r < cols_pad
-__global__ void __launch_bounds__(256) pad_copy_kernel(double* __restrict__ dst, long long ldd, long long rows_pad, long long cols_pad,
-                                                       const double* __restrict__ src, long long lds, long long rows, long long cols) {
-  const long long total = rows_pad * cols_pad;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
-    const long long r = t / rows_pad, i = t - r * rows_pad;
-    dst[i + r * ldd] = (i < rows && r < cols) ? src[i + r * lds] : 0.0;
+// realization-major staging of the noise: dst[r + i*ldd] = (i < rows && r < cols) ? src[i + r*lds] : 0
+// for i < rows_pad, r < cols_pad (32x32 shared-memory transpose; both sides coalesced)
+__global__ void __launch_bounds__(256) pad_transpose_kernel(double* __restrict__ dst, long long ldd, long long rows_pad, long long cols_pad,
+                                                            const double* __restrict__ src, long long lds, long long rows, long long cols) {
+  __shared__ double tile[32][33];
+  const long long i0 = (long long)blockIdx.x * 32, r0 = (long long)blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int rr = ty; rr < 32; rr += 8) {
+    const long long i = i0 + tx, r = r0 + rr;
+    tile[rr][tx] = (i < rows && r < cols) ? src[i + r * lds] : 0.0;
+  }
+  __syncthreads();
+  for (int ii = ty; ii < 32; ii += 8) {
+    const long long i = i0 + ii, r = r0 + tx;
+    if (i < rows_pad && r < cols_pad) dst[r + i * ldd] = tile[tx][ii];
   }
 }
 
@@ -80,6 +87,7 @@ struct gsp_lu_plan {
   gsp_ctx* ctx = nullptr;
   long long N = 0, Nd = 0, Ns = 0, Ndp = 0, Nsp = 0, Np = 0;
   double mu = 0.0;
+  double t_assemble_ms = 0.0, t_factor_ms = 0.0, t_solve_ms = 0.0;  // device times of the plan stages (CUDA events)
   std::vector<std::unique_ptr<LuDev>> dev;
   std::mutex mu_lock;
 };
@@ -104,18 +112,19 @@ int ensure_chunk(gsp_ctx* ctx, gsp_lu_plan* p, LuDev* d, long long cols, bool ne
   return GSP_OK;
 }
 
-// Build padded noise Wp (Nsp x cpad) for `cols` realizations starting at absolute index `real0`.
+// Build the padded, realization-major noise Wt (cpad x Nsp, ld = cpad) for `cols` realizations starting at `real0`.
 // src: device pointer (ld = lds) or NULL => Philox stream `stream`.
 int stage_noise(gsp_ctx* ctx, gsp_lu_plan* p, LuDev* d, double* Wp, const double* src, long long lds, long long cols, long long cpad,
                 unsigned long long seed, unsigned stream, long long real0) {
   cudaStream_t st = d->dc->stream;
   if (src) {
-    ProfScope prof_("pad_copy", st);
-    GSP_LAUNCH(pad_copy_kernel, dim3(grid_for(p->Nsp * cpad, d->dc->sms)), dim3(256), 0, st, Wp, p->Nsp, p->Nsp, cpad, src, lds, p->Ns, cols);
+    ProfScope prof_("pad_transpose", st);
+    GSP_LAUNCH(pad_transpose_kernel, dim3((unsigned)(p->Nsp / 32), (unsigned)(cpad / 32)), dim3(256), 0, st, Wp, cpad, p->Nsp, cpad, src, lds, p->Ns,
+               cols);
     g_launches++;
   } else {
     GSP_CUDA_OK(ctx, cudaMemsetAsync(Wp, 0, (size_t)p->Nsp * cpad * sizeof(double), st));
-    GSP_CUDA_OK(ctx, launch_rng_fill(st, d->dc->sms, Wp, p->Ns, p->Nsp, cols, seed, stream, (unsigned long long)real0, true));
+    GSP_CUDA_OK(ctx, launch_rng_fill(st, d->dc->sms, Wp, p->Ns, cpad, cols, seed, stream, (unsigned long long)real0, true, true));
   }
   GSP_CUDA_OK(ctx, cudaGetLastError());
   return GSP_OK;
@@ -139,7 +148,7 @@ int sample_core(gsp_ctx* ctx, gsp_lu_plan* p, LuDev* d, long long cols, const do
   }
   const double* L22 = d->A.as<double>() + p->Ndp * (p->Np + 1);
   const double addmu = (p->Nd == 0) ? p->mu : 0.0;  // lusim.jl:172
-  GSP_CUDA_OK(ctx, sample_gemm(st, L22, p->Np, (int)(p->Nsp / 128), Wp, p->Nsp, (int)(cpad / 128), Z, ldz, d->d2.as<double>(),
+  GSP_CUDA_OK(ctx, sample_gemm(st, L22, p->Np, (int)(p->Nsp / 128), Wp, cpad, (int)(cpad / 128), Z, ldz, d->d2.as<double>(),
                                d->sinds.as<long long>(), addmu, p->Ns, cols));
   if (p->Nd > 0) {
     GSP_LAUNCH(scatter_data_kernel, dim3(grid_for(p->Nd * cols, d->dc->sms)), dim3(256), 0, st, Z, ldz, (const long long*)d->dinds.as<long long>(),
@@ -225,11 +234,16 @@ extern "C" int gsp_lu_plan_create(gsp_ctx* ctx, const gsp_cov_model* cov, const 
     GSP_CUDA_OK(ctx, cudaMemcpyAsync(dcoords.p, dom->coords, (size_t)N * dd.dim * sizeof(double), cudaMemcpyHostToDevice, st));
     dd.coords = dcoords.as<double>();
   }
+  cudaEvent_t tev[4];
+  for (auto& e : tev) GSP_CUDA_OK(ctx, cudaEventCreate(&e));
+  GSP_CUDA_OK(ctx, cudaEventRecord(tev[0], st));
   // a1: joint covariance, lower tiles only (lusim.jl:88,95,96)
   launch_assemble(st, cd, dd, dd, dperm.as<long long>(), dperm.as<long long>(), p->Np, p->Np, d->A.as<double>(), p->Np, true);
   GSP_CUDA_OK(ctx, cudaGetLastError());
+  GSP_CUDA_OK(ctx, cudaEventRecord(tev[1], st));
   // a2/a3: one joint Cholesky (lusim.jl:92 or 98-103)
-  GSP_CUDA_OK(ctx, chol_factor(st, d->A.as<double>(), p->Np, (int)(p->Np / 128), d->invD.as<double>(), d->info.as<int>()));
+  GSP_CUDA_OK(ctx, chol_factor(st, dc.side, DevCtx::kSide, d->A.as<double>(), p->Np, (int)(p->Np / 128), d->invD.as<double>(), d->info.as<int>()));
+  GSP_CUDA_OK(ctx, cudaEventRecord(tev[2], st));
   // d2 = A21 * (L11 \ z1)   (lusim.jl:102); zero when unconditional (lusim.jl:91)
   GSP_CUDA_OK(ctx, cudaMemsetAsync(d->d2.p, 0, (size_t)p->Nsp * sizeof(double), st));
   if (nd > 0) {
@@ -239,9 +253,17 @@ extern "C" int gsp_lu_plan_create(gsp_ctx* ctx, const gsp_cov_model* cov, const 
     GSP_CUDA_OK(ctx, chol_forward_solve(st, d->A.as<double>(), p->Np, d->invD.as<double>(), (int)(p->Ndp / 128), y.as<double>()));
     GSP_CUDA_OK(ctx, chol_gemv_rows(st, d->A.as<double>(), p->Np, p->Ndp, p->Nsp, (int)p->Ndp, y.as<double>(), d->d2.as<double>()));
   }
+  GSP_CUDA_OK(ctx, cudaEventRecord(tev[3], st));
   int info = 0;
   GSP_CUDA_OK(ctx, cudaMemcpyAsync(&info, d->info.p, sizeof(int), cudaMemcpyDeviceToHost, st));
   GSP_CUDA_OK(ctx, cudaStreamSynchronize(st));
+  {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, tev[0], tev[1]); p->t_assemble_ms = ms;
+    cudaEventElapsedTime(&ms, tev[1], tev[2]); p->t_factor_ms = ms;
+    cudaEventElapsedTime(&ms, tev[2], tev[3]); p->t_solve_ms = ms;
+    for (auto& e : tev) cudaEventDestroy(e);
+  }
   if (info > 0) {
     // map the padded position back to the reference ordering [dinds; sinds] (1-based)
     long long pos = info - 1;
@@ -293,6 +315,14 @@ extern "C" int gsp_lu_plan_sizes(gsp_lu_plan* p, int64_t sizes[3]) {
   sizes[0] = p->N;
   sizes[1] = p->Nd;
   sizes[2] = p->Ns;
+  return GSP_OK;
+}
+
+extern "C" int gsp_lu_plan_times(gsp_lu_plan* p, double ms[3]) {
+  if (!p || !ms) return -1;
+  ms[0] = p->t_assemble_ms;
+  ms[1] = p->t_factor_ms;
+  ms[2] = p->t_solve_ms;
   return GSP_OK;
 }
 

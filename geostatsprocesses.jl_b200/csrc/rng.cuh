@@ -45,34 +45,43 @@ GSP_DEV void philox_normal2(unsigned long long seed, unsigned stream, unsigned l
   n1 = r * s;
 }
 
-// out[e + r*ld] for e < n, r < R;  normal != 0 -> N(0,1) else U[0,1)
+// tr == 0: out[e + r*ld];  tr != 0 (realization-major): out[r + e*ld];  e < n, r < R;  normal != 0 -> N(0,1) else U[0,1)
 static __global__ void __launch_bounds__(256) rng_fill_kernel(double* __restrict__ out, long long n, long long ld, long long R,
                                                        unsigned long long seed, unsigned stream, unsigned long long first_real,
-                                                       int normal) {
+                                                       int normal, int tr) {
   const long long npairs = (n + 1) / 2;
   const long long total = npairs * R;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
-    const long long r = t / npairs, p = t - r * npairs;
+    const long long r = tr ? t % R : t / npairs;
+    const long long p = tr ? t / R : t - r * npairs;
     double a, b;
     if (normal)
       philox_normal2(seed, stream, first_real + (unsigned long long)r, (unsigned long long)p, a, b);
     else
       philox_uniform2(seed, stream, first_real + (unsigned long long)r, (unsigned long long)p, a, b);
-    double* o = out + r * ld + 2 * p;
-    o[0] = a;
-    if (2 * p + 1 < n) o[1] = b;
+    if (tr) {
+      double* o = out + r + 2 * p * ld;
+      o[0] = a;
+      if (2 * p + 1 < n) o[ld] = b;
+    } else {
+      double* o = out + r * ld + 2 * p;
+      o[0] = a;
+      if (2 * p + 1 < n) o[1] = b;
+    }
   }
 }
 
 inline cudaError_t launch_rng_fill(cudaStream_t st, int sms, double* out, long long n, long long ld, long long R,
-                                   unsigned long long seed, unsigned stream, unsigned long long first_real, bool normal) {
+                                   unsigned long long seed, unsigned stream, unsigned long long first_real, bool normal,
+                                   bool transposed = false) {
   long long total = ((n + 1) / 2) * R;
   if (total <= 0) return cudaSuccess;
   long long blocks = (total + 255) / 256;
   if (blocks > (long long)sms * 32) blocks = (long long)sms * 32;
   ProfScope prof_("rng_fill", st);
-  GSP_LAUNCH(rng_fill_kernel, dim3((unsigned)blocks), dim3(256), 0, st, out, n, ld, R, seed, stream, first_real, normal ? 1 : 0);
+  GSP_LAUNCH(rng_fill_kernel, dim3((unsigned)blocks), dim3(256), 0, st, out, n, ld, R, seed, stream, first_real, normal ? 1 : 0,
+             transposed ? 1 : 0);
   g_launches++;
   return cudaGetLastError();
 }

@@ -111,6 +111,8 @@ int gsp_lu_plan_create(gsp_ctx* ctx, const gsp_cov_model* cov, const gsp_domain*
 int gsp_lu_plan_destroy(gsp_lu_plan* plan);
 /* sizes[0] = N, sizes[1] = Nd, sizes[2] = Ns */
 int gsp_lu_plan_sizes(gsp_lu_plan* plan, int64_t sizes[3]);
+/* device time (ms, CUDA events) of the plan's stages: ms[0] covariance assembly, ms[1] Cholesky, ms[2] d2 solve */
+int gsp_lu_plan_times(gsp_lu_plan* plan, double ms[3]);
 /* inspection (tests / debugging): d2 (Ns) and L22 (Ns x Ns column-major, lower) of lusim.jl:106; either may be NULL */
 int gsp_lu_plan_get(gsp_lu_plan* plan, double* d2, double* L22);
 

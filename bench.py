@@ -76,7 +76,7 @@ class ClockSampler:
             self.p = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.dev),
                  "--query-gpu=clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap", "--format=csv,noheader,nounits", "-lms", "100"],
+                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap", "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None

@@ -15,6 +15,7 @@
 #include "chol.h"
 #include "fft_kernels.cuh"
 #include "fft_pow2.cuh"
+#include "fft_plane.cuh"
 #include "rng.cuh"
 
 namespace gsp {
@@ -270,6 +271,9 @@ struct FftDev {
   DevBuf win[2], zout[2];  // staging for host-pointer sampling
   DevBuf inds;
   long long inds_cap = 0;
+  DevBuf cnt;              // plane counters of the fused x+y kernels: [0, nz) forward, [nz, 2nz) inverse
+  int epoch_fwd = 0, epoch_inv = 0;
+  bool fused_xy = false;   // 3-D grids whose x and y extents are covered by p2_plane_kernel
   AxisPlan ax[3];
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
@@ -356,6 +360,48 @@ cudaError_t launch_p2_strided(cudaStream_t st, int sms, int flags, const TensorM
   if (flags == P2_FWD) return launch_p2_strided_f<N, P2_FWD>(st, sms, tmH, tmF, axis, H, tw, es, hx, nother, other_stride, s);
   if (flags == P2_INV) return launch_p2_strided_f<N, P2_INV>(st, sms, tmH, tmF, axis, H, tw, es, hx, nother, other_stride, s);
   return launch_p2_strided_f<N, P2_FWD | P2_MUL | P2_INV>(st, sms, tmH, tmF, axis, H, tw, es, hx, nother, other_stride, s);
+}
+
+template <int HN, int NY, bool INV>
+cudaError_t launch_plane(cudaStream_t st, int sms, const TensorMap& tmHy, const double* in, double* out, cplx* H, const cplx* twx,
+                         const cplx* twy, int nz, int* cnt, int epoch, double scale, double mu) {
+  using C = PlaneCfg<HN, NY, INV>;
+  if constexpr (!C::OK) {
+    return cudaErrorInvalidValue;
+  } else {
+    auto kfn = p2_plane_kernel<HN, NY, INV>;
+    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, PLANE_THREADS, C::SMEM);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorInvalidValue;
+    if (per_sm > 4) per_sm = 4;
+    // every CTA must be resident: CTAs wait on each other's planes
+    constexpr int NBUN = (C::HX + C::B - 1) / C::B;
+    constexpr int PB = C::XI + (NBUN + C::U - 1) / C::U;
+    long long grid = (long long)per_sm * sms;
+    if (grid > (long long)nz * PB) grid = (long long)nz * PB;
+    // items in flight or being prefetched span 2*grid consecutive item numbers: lag the dependent kind beyond that
+    const int lag = (int)((2 * grid + PB - 1) / PB) + 1;
+    ProfScope prof_(INV ? "fft_plane_yx_inv" : "fft_plane_xy_fwd", st);
+    GSP_LAUNCH_COOP(kfn, dim3((unsigned)grid), dim3(PLANE_THREADS), C::SMEM, st, tmHy, in, out, H, twx, twy, nz, lag, cnt, epoch, scale, mu);
+    g_launches++;
+    return cudaGetLastError();
+  }
+}
+
+// (HN, NY) combinations compiled for the fused x+y kernels; everything else runs the separate passes
+inline bool plane_supported(int hn, int ny) { return (hn == 64 || hn == 128 || hn == 256) && (ny == 128 || ny == 256); }
+
+template <bool INV>
+cudaError_t launch_plane_dispatch(int hn, int ny, cudaStream_t st, int sms, const TensorMap& tmHy, const double* in, double* out, cplx* H,
+                                  const cplx* twx, const cplx* twy, int nz, int* cnt, int epoch, double scale, double mu) {
+#define GSP_PL(HN_, NY_) \
+  if (hn == HN_ && ny == NY_) return launch_plane<HN_, NY_, INV>(st, sms, tmHy, in, out, H, twx, twy, nz, cnt, epoch, scale, mu);
+  GSP_PL(64, 128) GSP_PL(64, 256) GSP_PL(128, 128) GSP_PL(128, 256) GSP_PL(256, 128) GSP_PL(256, 256)
+#undef GSP_PL
+  return cudaErrorInvalidValue;
 }
 
 #define GSP_P2_SWITCH(n, CALL)        \
@@ -492,8 +538,23 @@ cudaError_t run_strided(FftDev* d, gsp_fft_plan* p, int axis, cplx* H, int flags
   return cudaGetLastError();
 }
 
+cudaError_t run_plane_fwd(FftDev* d, gsp_fft_plan* p, const double* in) {
+  return launch_plane_dispatch<false>((int)p->dims[0] / 2, (int)p->dims[1], d->dc->stream, d->dc->sms, d->ax[1].tmH, in, nullptr,
+                                      d->H.as<cplx>(), d->ax[0].lp.tw, d->ax[1].lp.tw, (int)p->dims[2], d->cnt.as<int>(), ++d->epoch_fwd, 0.0, 0.0);
+}
+cudaError_t run_plane_inv(FftDev* d, gsp_fft_plan* p, double* out, double scale, double mu) {
+  return launch_plane_dispatch<true>((int)p->dims[0] / 2, (int)p->dims[1], d->dc->stream, d->dc->sms, d->ax[1].tmH, nullptr, out,
+                                     d->H.as<cplx>(), d->ax[0].lp.tw, d->ax[1].lp.tw, (int)p->dims[2], d->cnt.as<int>() + p->dims[2],
+                                     ++d->epoch_inv, scale, mu);
+}
+
 // forward transform of a real field into d->H (all axes)
 cudaError_t forward_all(FftDev* d, gsp_fft_plan* p, const double* in) {
+  if (d->fused_xy) {
+    cudaError_t e = run_plane_fwd(d, p, in);
+    if (e == cudaSuccess) e = run_strided(d, p, 2, d->H.as<cplx>(), PASS_FWD, nullptr, 0.0);
+    return e;
+  }
   cudaError_t e = run_xfwd(d, p, in, d->H.as<cplx>());
   for (int axis = 1; axis < p->ndim && e == cudaSuccess; ++axis) e = run_strided(d, p, axis, d->H.as<cplx>(), PASS_FWD, nullptr, 0.0);
   return e;
@@ -503,6 +564,13 @@ cudaError_t forward_all(FftDev* d, gsp_fft_plan* p, const double* in) {
 cudaError_t realization(FftDev* d, gsp_fft_plan* p, const double* w, double* out, double s, double scale_out, double mu) {
   cplx* H = d->H.as<cplx>();
   const double* Fh = d->Fh.as<double>();
+  if (d->fused_xy) {
+    // 3 kernels per realization: (x+y forward) -> (z forward, spectral multiply, z inverse) -> (y+x inverse)
+    cudaError_t e = run_plane_fwd(d, p, w);
+    if (e == cudaSuccess) e = run_strided(d, p, 2, H, PASS_FWD | PASS_MUL | PASS_INV, Fh, s);
+    if (e == cudaSuccess) e = run_plane_inv(d, p, out, scale_out, mu);
+    return e;
+  }
   cudaError_t e = run_xfwd(d, p, w, H);
   if (e != cudaSuccess) return e;
   const int last = p->ndim - 1;
@@ -541,6 +609,17 @@ int build_device(gsp_ctx* ctx, gsp_fft_plan* p, FftDev* d, const CovDev& cov, co
     int r1 = make_tensor_map_f64(&a.tmH, d->H.p, dH, 16ull * p->hx, 16ull * p->hx * p->dims[1], boxH);
     int r2 = make_tensor_map_f64(&a.tmF, d->Fh.p, dF, 8ull * p->hxF, 8ull * p->hxF * p->dims[1], boxF);
     if (r1 != 0 || r2 != 0) return set_err(ctx, GSP_E_CUDA, "cuTensorMapEncodeTiled failed for an FFT pass (code " + std::to_string(r1 ? r1 : r2) + ")");
+  }
+  {
+    // Opt-in (GSP_FFT_FUSE=1): measured on B200 at 256^3 the fused x+y kernels halve the HBM traffic of those passes but
+    // run at 146 us + 121 us against 126 us + 105 us for the four separate passes - with 8 warps per SM the items'
+    // shared-memory / FP64 / wait phases do not overlap enough (profiles/r01_fused_plane_notes.md).
+    const char* env = getenv("GSP_FFT_FUSE");
+    const bool allow = env && env[0] == '1';
+    d->fused_xy = allow && p->ndim == 3 && d->ax[0].fast && d->ax[1].fast && d->ax[2].fast &&
+                  plane_supported((int)p->dims[0] / 2, (int)p->dims[1]);
+    GSP_CUDA_OK(ctx, d->cnt.alloc(d->dc->dev, (size_t)(2 * p->dims[2] + 2) * sizeof(int)));
+    GSP_CUDA_OK(ctx, cudaMemsetAsync(d->cnt.p, 0, (size_t)(2 * p->dims[2] + 2) * sizeof(int), d->dc->stream));
   }
   DevBuf C, partial, total;
   GSP_CUDA_OK(ctx, C.alloc(d->dc->dev, (size_t)p->N * sizeof(double)));

@@ -7,7 +7,7 @@
 
 #ifdef GSP_EMU
 #include "gsp_emu.h"
-#define GSP_DYN_SMEM(name) unsigned char* name = ::emu::g->dyn_smem
+#define GSP_DYN_SMEM(name) unsigned char* name = ::emu::dyn_smem()
 #define GSP_HD
 #else
 #include <cuda_runtime.h>
@@ -15,6 +15,7 @@
   extern __shared__ __align__(128) unsigned char name##_raw_[]; \
   unsigned char* name = name##_raw_
 #define GSP_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#define GSP_LAUNCH_COOP(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #define GSP_HD __host__ __device__
 #endif
 
@@ -166,6 +167,31 @@ GSP_DEV void tma_load_3d(void* dst, const TensorMap* tm, int c0, int c1, int c2,
 // host: FP64 tensor `base` with extents dims[3] (elements), byte strides of dims 1 and 2, tile box[3].  Returns 0 on success.
 int make_tensor_map_f64(TensorMap* out, const void* base, const unsigned long long dims[3], unsigned long long stride1_bytes,
                         unsigned long long stride2_bytes, const unsigned box[3]);
+
+// inter-CTA flags in global memory (persistent kernels): release after the CTA's stores, acquire before dependent loads
+GSP_DEV void spin_pause() {
+#ifdef GSP_EMU
+  emu::spin_yield();
+#else
+  __nanosleep(64);
+#endif
+}
+GSP_DEV int ld_acquire_gpu(const int* p) {
+#ifdef GSP_EMU
+  return *p;
+#else
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+#endif
+}
+GSP_DEV void red_release_gpu_add(int* p, int v) {
+#ifdef GSP_EMU
+  *p += v;
+#else
+  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+#endif
+}
 
 // streaming (read-once / write-once) 16-byte global accesses
 GSP_DEV double2 ld_stream2(const double* p) {

@@ -76,6 +76,7 @@ static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t = 0) { retur
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return cudaSuccess; }
 template <class F> static inline cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess; }
+template <class F> static inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int* n, F, int, size_t) { *n = 2; return cudaSuccess; }
 struct cudaDeviceProp { int multiProcessorCount; size_t sharedMemPerBlockOptin; char name[64]; int major, minor; };
 static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) {
   p->multiProcessorCount = 4; p->sharedMemPerBlockOptin = 227 * 1024; std::strcpy(p->name, "gsp-emu"); p->major = 10; p->minor = 0;
@@ -97,7 +98,17 @@ struct Fiber {
   // wait state
   int wait_kind = 0;   // 0 runnable, 1 block barrier, 2 named barrier, 3 warp rendezvous, 4 spin (always runnable)
   int wait_id = 0;
+  int block = 0;  // index into State::blocks
   uint3 tid;
+};
+
+struct BlockState {
+  uint3 bid;
+  unsigned char* dyn_smem = nullptr;
+  int live = 0;
+  int bar_waiting = 0;
+  int named_count[16] = {0};
+  int named_gen[16] = {0};
 };
 
 struct State {
@@ -105,14 +116,10 @@ struct State {
   ucontext_t sched;
   int cur = -1;
   int nthreads = 0;
+  int tpb = 0;     // threads per block
   int live = 0;
   std::function<void()> body;
-  unsigned char* dyn_smem = nullptr;
-  // block barrier
-  int bar_waiting = 0;
-  // named barriers
-  int named_count[16] = {0};
-  int named_gen[16] = {0};
+  std::vector<BlockState> blocks;
   // warp rendezvous
   std::vector<int> warp_arrived, warp_gen;
   std::vector<uint64_t> warp_buf;   // 32 slots per warp
@@ -123,6 +130,8 @@ extern uint3 g_threadIdx, g_blockIdx;
 extern dim3 g_blockDim, g_gridDim;
 
 void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body);
+void launch_coop(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body);  // all blocks co-resident
+inline unsigned char* dyn_smem() { return g->blocks[g->fibers[g->cur].block].dyn_smem; }
 void yield_to_sched();
 void syncthreads();
 void named_bar_sync(int id, int count);
@@ -203,4 +212,10 @@ inline void launch_k(dim3 grid, dim3 block, size_t smem, K kernel, Args... args)
   launch(grid, block, smem, [=]() { kernel(args...); });
 }
 }  // namespace emu
+template <class K, class... Args>
+inline void emu_launch_coop_k(dim3 grid, dim3 block, size_t smem, K kernel, Args... args) {
+  ::emu::launch_coop(grid, block, smem, [=]() { kernel(args...); });
+}
 #define GSP_LAUNCH(kernel, grid, block, smem, stream, ...) ::emu::launch_k((grid), (block), (smem), (kernel), __VA_ARGS__)
+// persistent kernels whose CTAs wait on each other: the whole grid must be co-resident
+#define GSP_LAUNCH_COOP(kernel, grid, block, smem, stream, ...) ::emu_launch_coop_k((grid), (block), (smem), (kernel), __VA_ARGS__)

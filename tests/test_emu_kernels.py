@@ -167,3 +167,67 @@ def test_philox_matches_restatement(emu_lib):
         w[2 * pair + 1] = (b >> 11) / 2.0 ** 53
     assert np.array_equal(plan.sample(1, None, seed=seed, first_real=real), plan.sample(1, w[None, :]))
     plan.close()
+
+
+def test_fftsim_pow2_fast_path(emu_lib):
+    """register-resident power-of-two passes (fft_pow2.cuh): 2- and 3-stage plans, TMA tiles, persistent pipelining."""
+    rng = np.random.default_rng(11)
+    for dims in ((64, 32), (32, 16, 16), (256, 16), (1024, 16), (32, 512), (32, 1024), (64, 16, 32)):
+        nd = len(dims)
+        st = iso(O.SPHERICAL, 1.7, 4.0, nd)
+        plan = gsp.FFTPlan(emu_lib, st, dims, [0.0] * nd, [1.0] * nd)
+        Fo = O.fftsim_preprocess(ostructs(st), dims, [0.0] * nd, [1.0] * nd)
+        w = rng.random((2, int(np.prod(dims))))
+        Z = plan.sample(2, w, sill=1.7, mu=0.3)
+        Zo = np.stack([O.fftsim_sample(Fo, w[r], 1.7, 0.3) for r in range(2)])
+        assert relerr(Z, Zo) < TOL, dims
+        plan.close()
+
+
+def test_fftsim_fused_plane_kernels(emu_lib, monkeypatch):
+    """opt-in fused x+y kernels (fft_plane.cuh): inter-CTA plane dependencies, counters reused across realizations."""
+    monkeypatch.setenv("GSP_FFT_FUSE", "1")
+    rng = np.random.default_rng(12)
+    for dims in ((128, 128, 6), (256, 128, 3)):
+        st = iso(O.EXPONENTIAL, 1.0, 6.0, 3)
+        plan = gsp.FFTPlan(emu_lib, st, dims, [0.0] * 3, [1.0] * 3)
+        Fo = O.fftsim_preprocess(ostructs(st), dims, [0.0] * 3, [1.0] * 3)
+        assert relerr(plan.spectrum(), Fo) < 1e-12
+        w = rng.random((3, int(np.prod(dims))))
+        Z = plan.sample(3, w, sill=1.0, mu=0.0)
+        for r in range(3):
+            assert relerr(Z[r], O.fftsim_sample(Fo, w[r], 1.0, 0.0)) < TOL
+        plan.close()
+
+
+def test_plan_times_and_profile(emu_lib):
+    st = iso(O.SPHERICAL, 1.0, 4.0, 2)
+    emu_lib.profile_enable(True)
+    plan = gsp.LUPlan(emu_lib, st, (gsp._lib.make_grid_domain((9, 7), (0, 0), (1, 1)), None), None, None, 0.0)
+    assert len(plan.times()) == 3
+    plan.sample(2, None, seed=1)
+    prof = emu_lib.profile_read()
+    emu_lib.profile_enable(False)
+    assert {"assemble", "potrf_diag", "gemm_dmma_sample"} <= set(prof)
+    assert all(v["launches"] >= 1 for v in prof.values())
+    plan.close()
+
+
+def test_cholesky_big_tile_path(emu_lib):
+    """GSP_GEMM_SMALL_TILES is read once per process, so the 128x128 TRSM/SYRK variants are covered in a subprocess."""
+    import os, subprocess, sys, textwrap
+    code = textwrap.dedent("""
+        import sys, numpy as np, scipy.linalg
+        sys.path.insert(0, %r); sys.path.insert(0, %r)
+        import gsp_b200 as gsp
+        lib = gsp.Library(%r)
+        rng = np.random.default_rng(0)
+        M = rng.standard_normal((300, 300)); S = M @ M.T + 300 * np.eye(300)
+        L = lib.potrf(S)
+        err = np.abs(L - scipy.linalg.cholesky(S, lower=True)).max()
+        assert err < 1e-11, err
+        print("OK")
+    """) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)), emu_lib.path)
+    env = dict(os.environ, GSP_GEMM_SMALL_TILES="0", GSP_CHOL_LOOKAHEAD="1")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0 and "OK" in out.stdout, out.stderr[-1500:]

@@ -14,7 +14,8 @@ from typing import Optional, Sequence
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-DEFAULT_LIB = os.path.join(_HERE, "libgspb200.so")
+# GSP_B200_LIB selects another BUILD of the same CUDA library (A/B experiments); there is still no non-CUDA alternative
+DEFAULT_LIB = os.environ.get("GSP_B200_LIB") or os.path.join(_HERE, "libgspb200.so")
 
 GSP_E_CUDA, GSP_E_UNSUPPORTED, GSP_E_NOMEM, GSP_E_STATE = -1001, -1002, -1003, -1004
 MAX_STRUCTS = 8

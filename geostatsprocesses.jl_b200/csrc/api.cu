@@ -173,6 +173,17 @@ extern "C" int gsp_ctx_create(int32_t ndev, const int32_t* devs, gsp_ctx** out) 
     dc.sms = prop.multiProcessorCount;
     dc.smem_optin = prop.sharedMemPerBlockOptin;
   }
+  // peer access between all device pairs (panel broadcasts of the multi-GPU factorization, copies of L / d2)
+  for (auto& a : ctx->devs)
+    for (auto& b : ctx->devs) {
+      if (a.dev == b.dev) continue;
+      int can = 0;
+      if (cudaDeviceCanAccessPeer(&can, a.dev, b.dev) == cudaSuccess && can) {
+        cudaSetDevice(a.dev);
+        cudaDeviceEnablePeerAccess(b.dev, 0);
+        cudaGetLastError();  // "already enabled" is fine
+      }
+    }
   *out = ctx;
   return GSP_OK;
 }

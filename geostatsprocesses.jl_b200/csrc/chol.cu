@@ -17,31 +17,45 @@ constexpr int DLD = 129;  // padded smem leading dimension (row-major S[r][c])
 constexpr int DPW = 16;   // inner panel width
 constexpr int DIAG_SMEM = (DB * DLD + DPW * (DPW + 1) + DPW) * 8;
 
-// columns J.. of one 128x16 panel, one matrix row per thread (x = that row's 16 panel entries, in registers).
-// Left-looking: the pivot thread finalises its diagonal entry and publishes its row, everyone below
-// finishes its entry of column J.  One barrier per column.
+// 16x16 diagonal block of a panel, factorised by ONE warp in registers (lane l < 16 owns row l), right-looking,
+// no block barriers: per column one shuffle broadcasts the pivot, rsqrt gives 1/L_jj, the remaining columns are
+// updated with shuffled L_kj.  Fully unrolled through the template recursion (static register indexing).
 template <int J>
-GSP_DEV void diag_panel_cols(double (&x)[DPW], int i, int c0, bool active, double* P, double* rinv, int* info, int gbase) {
+GSP_DEV void diag16_cols(double (&row)[DPW], int l, double* rdiag, int* info, int gpos) {
   if constexpr (J < DPW) {
-    if (active && i == c0 + J) {
-      double d = x[J];
-#pragma unroll
-      for (int k = 0; k < J; ++k) d -= x[k] * x[k];
-      if (!(d > 0.0)) atomicCAS(info, 0, gbase + c0 + J + 1);
-      const double s = sqrt(d);
-      x[J] = s;
-#pragma unroll
-      for (int k = 0; k <= J; ++k) P[J * (DPW + 1) + k] = x[k];
-      rinv[J] = 1.0 / s;
+    const double piv = __shfl_sync(0xffffffffu, row[J], J);
+    if (!(piv > 0.0) && l == 0) atomicCAS(info, 0, gpos + J + 1);
+    const double rinv = rsqrt(piv);
+    if (l == J) {
+      row[J] = piv * rinv;
+      rdiag[J] = rinv;
+    } else if (l > J) {
+      row[J] *= rinv;
     }
-    __syncthreads();
-    if (active && i > c0 + J) {
-      double v = x[J];
 #pragma unroll
-      for (int k = 0; k < J; ++k) v -= x[k] * P[J * (DPW + 1) + k];
-      x[J] = v * rinv[J];
+    for (int k = J + 1; k < DPW; ++k) {
+      const double lkj = __shfl_sync(0xffffffffu, row[J], k);
+      if (l >= k) row[k] -= row[J] * lkj;
     }
-    diag_panel_cols<J + 1>(x, i, c0, active, P, rinv, info, gbase);
+    diag16_cols<J + 1>(row, l, rdiag, info, gpos);
+  }
+}
+
+// rows below the diagonal block: x * D^T = b, one row per thread, D (16x16 lower) broadcast from shared memory
+template <int C_>
+GSP_DEV void diag_row_solve(double (&x)[DPW], const double* D16, const double* rdiag) {
+  if constexpr (C_ < DPW) {
+    double t0 = x[C_], t1 = 0.0, t2 = 0.0, t3 = 0.0;
+#pragma unroll
+    for (int k = 0; k < C_; ++k) {
+      const double pr = x[k] * D16[C_ * (DPW + 1) + k];
+      if ((k & 3) == 0) t0 -= pr;
+      else if ((k & 3) == 1) t1 -= pr;
+      else if ((k & 3) == 2) t2 -= pr;
+      else t3 -= pr;
+    }
+    x[C_] = ((t0 + t1) + (t2 + t3)) * rdiag[C_];
+    diag_row_solve<C_ + 1>(x, D16, rdiag);
   }
 }
 
@@ -108,18 +122,31 @@ __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(double* __restrict__
 
   for (int p = 0; p < DB / DPW; ++p) {
     const int c0 = p * DPW;
-    // (a) panel factorisation, one row per thread
-    {
-      const int i = tid;
-      const bool active = tid < DB && i >= c0;
-      double x[DPW];
+    // (a) 16x16 diagonal block in the registers of warp 0, then the rows below it, one per thread
+    if (tid < 32) {
+      const int l = tid;
+      double row[DPW];
 #pragma unroll
-      for (int k = 0; k < DPW; ++k) x[k] = active ? S[i * DLD + c0 + k] : 0.0;
-      diag_panel_cols<0>(x, i, c0, active, P, rinv, info, (int)(blk * DB));
-      if (active) {
+      for (int k = 0; k < DPW; ++k) row[k] = (l < DPW) ? S[(c0 + l) * DLD + c0 + k] : 0.0;
+      diag16_cols<0>(row, l, rinv, info, (int)(blk * DB) + c0);
+      if (l < DPW) {
 #pragma unroll
-        for (int k = 0; k < DPW; ++k) S[i * DLD + c0 + k] = (c0 + k <= i) ? x[k] : 0.0;
+        for (int k = 0; k < DPW; ++k) {
+          const double v = (k <= l) ? row[k] : 0.0;
+          S[(c0 + l) * DLD + c0 + k] = v;
+          P[l * (DPW + 1) + k] = v;
+        }
       }
+    }
+    __syncthreads();
+    if (tid < DB && tid >= c0 + DPW) {
+      double x[DPW];
+      double* srow = S + tid * DLD + c0;
+#pragma unroll
+      for (int k = 0; k < DPW; ++k) x[k] = srow[k];
+      diag_row_solve<0>(x, P, rinv);
+#pragma unroll
+      for (int k = 0; k < DPW; ++k) srow[k] = x[k];
     }
     __syncthreads();
     // (b) trailing update of the lower triangle right of the panel (rank-16)
@@ -130,17 +157,26 @@ __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(double* __restrict__
         double ra[DPW];
 #pragma unroll
         for (int c = 0; c < DPW; ++c) ra[c] = S[i * DLD + c0 + c];
-        for (int b = p + 1; b <= a; ++b) {
-          const int k = tk + DPW * b;
-          if (i < k) continue;
-          const double* sk = S + k * DLD + c0;
-          double acc0 = 0.0, acc1 = 0.0;
+        // two output columns per iteration, four independent partial sums each: short dependent FMA chains
+        for (int b = p + 1; b <= a; b += 2) {
+          const int k0 = tk + DPW * b, k1 = k0 + DPW;
+          const bool do0 = i >= k0, do1 = (b + 1 <= a) && i >= k1;
+          const double* s0 = S + k0 * DLD + c0;
+          const double* s1 = S + (do1 ? k1 : k0) * DLD + c0;
+          double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
 #pragma unroll
-          for (int c = 0; c < DPW; c += 2) {
-            acc0 += ra[c] * sk[c];
-            acc1 += ra[c + 1] * sk[c + 1];
+          for (int c = 0; c < DPW; c += 4) {
+            a0 += ra[c] * s0[c];
+            a1 += ra[c + 1] * s0[c + 1];
+            a2 += ra[c + 2] * s0[c + 2];
+            a3 += ra[c + 3] * s0[c + 3];
+            b0 += ra[c] * s1[c];
+            b1 += ra[c + 1] * s1[c + 1];
+            b2 += ra[c + 2] * s1[c + 2];
+            b3 += ra[c + 3] * s1[c + 3];
           }
-          S[i * DLD + k] -= acc0 + acc1;
+          if (do0) S[i * DLD + k0] -= (a0 + a1) + (a2 + a3);
+          if (do1) S[i * DLD + k1] -= (b0 + b1) + (b2 + b3);
         }
       }
     }
@@ -352,6 +388,110 @@ cudaError_t chol_factor(cudaStream_t st, cudaStream_t* side, int nside, double* 
   // every side stream was joined into `st` by the events waited on above, except possibly none: nothing left pending
   for (cudaEvent_t ev : c.events) cudaEventDestroy(ev);
   return c.err;
+}
+
+// ------------------------------------------------------------------ multi-GPU factorization
+// 1-D block-cyclic panels of PB 128-blocks over the G devices of a context, every device holding the full
+// matrix buffer.  Step q: owner(q) = q mod G factors panel q (diagonal potrf + TRSM of the rows below), the
+// panel is pushed device-to-device (cudaMemcpy2DAsync over NVLink peer access) INTO THE SAME POSITION of every
+// other device's matrix, and every device applies it to the panels it owns.  Look-ahead: the owner of
+// panel q+1 updates that panel first on its main stream, factors it and starts the next broadcast while the
+// bulk updates of step q still run on the update streams.  Because panels land in place, every device ends
+// with the complete factor L: the all-gather needed for the realization-sharded sampling is free.
+cudaError_t chol_factor_mg(const std::vector<MgDev>& devs, long long ld, int nblocks, int PB) {
+  const int G = (int)devs.size();
+  const int Q = (nblocks + PB - 1) / PB;
+  cudaError_t err = cudaSuccess;
+  auto check = [&](cudaError_t e) {
+    if (err == cudaSuccess && e != cudaSuccess) err = e;
+  };
+  std::vector<Chol> ch;
+  ch.reserve(G);
+  for (int g = 0; g < G; ++g) {
+    check(cudaSetDevice(devs[g].dev));
+    ch.push_back(Chol{devs[g].main, nullptr, 0, devs[g].A, ld, devs[g].invD, devs[g].info});
+    check(cudaMemsetAsync(devs[g].info, 0, sizeof(int), devs[g].main));
+  }
+  std::vector<cudaEvent_t> evs;
+  auto record = [&](int g, cudaStream_t s) {
+    cudaEvent_t ev;
+    check(cudaSetDevice(devs[g].dev));
+    check(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    check(cudaEventRecord(ev, s));
+    evs.push_back(ev);
+    return ev;
+  };
+  std::vector<cudaEvent_t> upd_done(G, nullptr);   // last event of device g's update stream
+  std::vector<cudaEvent_t> have(G, nullptr);       // panel q is present on device g (factored there or received)
+  const size_t esz = sizeof(double);
+  for (int q = 0; q < Q && err == cudaSuccess; ++q) {
+    const int o = q % G;
+    const int r0 = q * PB;
+    const int nq = (nblocks - r0 < PB) ? nblocks - r0 : PB;
+    const int below = nblocks - r0 - nq;
+    // ---- factor panel q on its owner.  No extra wait: the panel's last update (by panel q-1) ran on this main stream as
+    // the look-ahead update of step q-1, and that update already waited for the update stream's earlier work on the panel;
+    // the bulk updates of step q-1 touch other panels and keep running underneath.
+    check(cudaSetDevice(devs[o].dev));
+    ch[o].potrf(r0, nq, nullptr, 0);
+    ch[o].trsm(r0 + nq, below, r0, nq);
+    check(ch[o].err);
+    cudaEvent_t ready = record(o, devs[o].main);
+    // ---- broadcast: rows >= r0*128 of the panel's columns, plus the inverses of its diagonal blocks
+    for (int g = 0; g < G; ++g) {
+      if (g == o) {
+        have[g] = ready;
+        continue;
+      }
+      check(cudaSetDevice(devs[g].dev));
+      check(cudaStreamWaitEvent(devs[g].copy, ready, 0));
+      const size_t off = (size_t)r0 * DB * (size_t)(ld + 1);
+      check(cudaMemcpy2DAsync(devs[g].A + off, (size_t)ld * esz, devs[o].A + off, (size_t)ld * esz, (size_t)(nblocks - r0) * DB * esz,
+                              (size_t)nq * DB, cudaMemcpyDefault, devs[g].copy));
+      check(cudaMemcpyAsync(devs[g].invD + (size_t)r0 * DB * DB, devs[o].invD + (size_t)r0 * DB * DB, (size_t)nq * DB * DB * esz,
+                            cudaMemcpyDefault, devs[g].copy));
+      have[g] = record(g, devs[g].copy);
+    }
+    if (below <= 0) break;
+    // ---- trailing updates with panel q on every device, for the panels it owns
+    for (int g = 0; g < G; ++g) {
+      check(cudaSetDevice(devs[g].dev));
+      bool any_upd = false;
+      for (int q2 = q + 1; q2 < Q; ++q2) {
+        if (q2 % G != g) continue;
+        const int c0 = q2 * PB;
+        const int n2 = (nblocks - c0 < PB) ? nblocks - c0 : PB;
+        const bool lookahead = (q2 == q + 1);
+        cudaStream_t s = lookahead ? devs[g].main : devs[g].upd;
+        if (lookahead) {
+          check(cudaStreamWaitEvent(s, have[g], 0));
+          if (upd_done[g]) check(cudaStreamWaitEvent(s, upd_done[g], 0));
+        } else if (!any_upd) {
+          check(cudaStreamWaitEvent(s, have[g], 0));
+          any_upd = true;
+        }
+        ch[g].st = s;  // Chol::update launches on the stream it is given; keep st consistent for error paths
+        ch[g].update(s, false, c0, c0, nblocks - c0, n2, c0, r0, c0, r0, nq, false);
+        ch[g].st = devs[g].main;
+        check(ch[g].err);
+      }
+      if (any_upd) upd_done[g] = record(g, devs[g].upd);
+    }
+  }
+  // join: every stream of every device has finished before the caller continues on the main streams
+  for (int g = 0; g < G; ++g) {
+    check(cudaSetDevice(devs[g].dev));
+    if (upd_done[g]) check(cudaStreamWaitEvent(devs[g].main, upd_done[g], 0));
+    if (have[g]) check(cudaStreamWaitEvent(devs[g].main, have[g], 0));
+  }
+  for (int g = 0; g < G; ++g) {
+    check(cudaSetDevice(devs[g].dev));
+    check(cudaStreamSynchronize(devs[g].main));
+    check(cudaStreamSynchronize(devs[g].copy));
+    check(cudaStreamSynchronize(devs[g].upd));
+  }
+  for (cudaEvent_t ev : evs) cudaEventDestroy(ev);
+  return err;
 }
 
 cudaError_t chol_forward_solve(cudaStream_t st, const double* L, long long ld, const double* invD, int nblocks, double* z) {

@@ -1,5 +1,7 @@
 // Device Cholesky / triangular helpers (chol.cu) and assembly launchers (assemble.cu).
 #pragma once
+#include <vector>
+
 #include "cov.cuh"
 
 namespace gsp {
@@ -10,6 +12,16 @@ namespace gsp {
 // `side[nside]`: low-priority streams used for look-ahead (the bulk of every trailing update runs there while
 // the next diagonal block / panel proceeds on `st`); everything is joined back into `st` before returning.
 cudaError_t chol_factor(cudaStream_t st, cudaStream_t* side, int nside, double* A, long long ld, int nblocks, double* invD, int* info);
+// multi-GPU variant: every device holds a full (nblocks*128)^2 buffer `A` with the matrix assembled; panels of PB blocks are
+// owned cyclically, factored by their owner and pushed peer-to-peer into the same place on all devices (chol.cu).
+struct MgDev {
+  int dev;
+  cudaStream_t main, upd, copy;
+  double* A;
+  double* invD;
+  int* info;
+};
+cudaError_t chol_factor_mg(const std::vector<MgDev>& devs, long long ld, int nblocks, int PB);
 // z[0 : nblocks*128] <- L^{-1} z  for the leading nblocks diagonal blocks
 cudaError_t chol_forward_solve(cudaStream_t st, const double* L, long long ld, const double* invD, int nblocks, double* z);
 // out[i] = sum_{k<kn} L[row0+i][k] y[k]

@@ -11,6 +11,7 @@
 // starts on a tile boundary, and the simulation block padded likewise at the end.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <memory>
 
 #include "chol.h"
@@ -206,56 +207,104 @@ extern "C" int gsp_lu_plan_create(gsp_ctx* ctx, const gsp_cov_model* cov, const 
     }
   }
 
-  // device 0 builds the factor
-  std::unique_ptr<LuDev> d(new LuDev);
-  d->dc = &ctx->devs[0];
-  DevCtx& dc = *d->dc;
+  // ---- which devices build: one (factor there, copy L to the others) or all (multi-GPU block-cyclic factorization)
+  const int ndev = (int)ctx->devs.size();
+  static int mg_min_blocks = -1, mg_pb_env = 0;
+  if (mg_min_blocks < 0) {
+    const char* e1 = getenv("GSP_CHOL_MG_MIN_BLOCKS");
+    const char* e2 = getenv("GSP_CHOL_MG_PB");
+    mg_min_blocks = e1 ? atoi(e1) : 64;  // below ~8k nodes the panel chain dominates: replicate instead
+    if (e2 && atoi(e2) > 0) mg_pb_env = atoi(e2);
+  }
+  const int nb = (int)(p->Np / 128);
+  // panel width in 128-blocks (measured on 2 B200: N = 33k: PB 4 -> 298 ms, PB 8 -> 251 ms; N = 16.5k: 49 ms vs 51 ms)
+  const int mg_pb = mg_pb_env > 0 ? mg_pb_env : (nb >= 192 ? 8 : 4);
+  const bool mg = ndev > 1 && nb >= mg_min_blocks;
+  const int nbuild = mg ? ndev : 1;
+
+  auto build_one = [&](LuDev* d, bool with_matrix) -> int {
+    DevCtx& dc = *d->dc;
+    cudaSetDevice(dc.dev);
+    cudaStream_t st = dc.stream;
+    GSP_CUDA_OK(ctx, d->d2.alloc(dc.dev, (size_t)p->Nsp * sizeof(double)));
+    GSP_CUDA_OK(ctx, d->sinds.alloc(dc.dev, (size_t)p->Ns * sizeof(long long)));
+    GSP_CUDA_OK(ctx, d->dinds.alloc(dc.dev, (size_t)std::max<long long>(nd, 1) * sizeof(long long)));
+    GSP_CUDA_OK(ctx, d->z1.alloc(dc.dev, (size_t)std::max<long long>(nd, 1) * sizeof(double)));
+    GSP_CUDA_OK(ctx, d->info.alloc(dc.dev, sizeof(int)));
+    GSP_CUDA_OK(ctx, cudaEventCreate(&d->ev0));
+    GSP_CUDA_OK(ctx, cudaEventCreate(&d->ev1));
+    GSP_CUDA_OK(ctx, cudaMemcpyAsync(d->sinds.p, sinds.data(), sinds.size() * sizeof(long long), cudaMemcpyHostToDevice, st));
+    if (nd > 0) {
+      GSP_CUDA_OK(ctx, cudaMemcpyAsync(d->dinds.p, dind0.data(), dind0.size() * sizeof(long long), cudaMemcpyHostToDevice, st));
+      GSP_CUDA_OK(ctx, cudaMemcpyAsync(d->z1.p, z1, (size_t)nd * sizeof(double), cudaMemcpyHostToDevice, st));
+    }
+    GSP_CUDA_OK(ctx, d->A.alloc(dc.dev, (size_t)p->Np * p->Np * sizeof(double)));
+    if (!with_matrix) return GSP_OK;
+    GSP_CUDA_OK(ctx, d->invD.alloc(dc.dev, (size_t)nb * 128 * 128 * sizeof(double)));
+    DevBuf dperm, dcoords;
+    GSP_CUDA_OK(ctx, dperm.alloc(dc.dev, (size_t)p->Np * sizeof(long long)));
+    GSP_CUDA_OK(ctx, cudaMemcpyAsync(dperm.p, perm.data(), perm.size() * sizeof(long long), cudaMemcpyHostToDevice, st));
+    DomDev ddl = dd;
+    if (dd.kind == 0) {
+      GSP_CUDA_OK(ctx, dcoords.alloc(dc.dev, (size_t)N * dd.dim * sizeof(double)));
+      GSP_CUDA_OK(ctx, cudaMemcpyAsync(dcoords.p, dom->coords, (size_t)N * dd.dim * sizeof(double), cudaMemcpyHostToDevice, st));
+      ddl.coords = dcoords.as<double>();
+    }
+    // a1: joint covariance, lower tiles only (lusim.jl:88,95,96)
+    launch_assemble(st, cd, ddl, ddl, dperm.as<long long>(), dperm.as<long long>(), p->Np, p->Np, d->A.as<double>(), p->Np, true);
+    GSP_CUDA_OK(ctx, cudaGetLastError());
+    GSP_CUDA_OK(ctx, cudaStreamSynchronize(st));  // dperm / dcoords go out of scope
+    return GSP_OK;
+  };
+
+  cudaEvent_t tev[4];
+  {
+    cudaSetDevice(ctx->devs[0].dev);
+    for (auto& e : tev) GSP_CUDA_OK(ctx, cudaEventCreate(&e));
+    GSP_CUDA_OK(ctx, cudaEventRecord(tev[0], ctx->devs[0].stream));
+  }
+  for (int i = 0; i < ndev; ++i) {
+    std::unique_ptr<LuDev> d(new LuDev);
+    d->dc = &ctx->devs[i];
+    GSP_TRY(build_one(d.get(), i < nbuild));
+    p->dev.push_back(std::move(d));
+  }
+  LuDev* d0 = p->dev[0].get();
+  DevCtx& dc = *d0->dc;
   cudaSetDevice(dc.dev);
   cudaStream_t st = dc.stream;
-  DevBuf dperm, dcoords, y;
-  GSP_CUDA_OK(ctx, d->A.alloc(dc.dev, (size_t)p->Np * p->Np * sizeof(double)));
-  GSP_CUDA_OK(ctx, d->invD.alloc(dc.dev, (size_t)(p->Np / 128) * 128 * 128 * sizeof(double)));
-  GSP_CUDA_OK(ctx, d->d2.alloc(dc.dev, (size_t)p->Nsp * sizeof(double)));
-  GSP_CUDA_OK(ctx, d->sinds.alloc(dc.dev, (size_t)p->Ns * sizeof(long long)));
-  GSP_CUDA_OK(ctx, d->dinds.alloc(dc.dev, (size_t)std::max<long long>(nd, 1) * sizeof(long long)));
-  GSP_CUDA_OK(ctx, d->z1.alloc(dc.dev, (size_t)std::max<long long>(nd, 1) * sizeof(double)));
-  GSP_CUDA_OK(ctx, d->info.alloc(dc.dev, sizeof(int)));
-  GSP_CUDA_OK(ctx, dperm.alloc(dc.dev, (size_t)p->Np * sizeof(long long)));
-  GSP_CUDA_OK(ctx, cudaEventCreate(&d->ev0));
-  GSP_CUDA_OK(ctx, cudaEventCreate(&d->ev1));
-  GSP_CUDA_OK(ctx, cudaMemcpyAsync(dperm.p, perm.data(), perm.size() * sizeof(long long), cudaMemcpyHostToDevice, st));
-  GSP_CUDA_OK(ctx, cudaMemcpyAsync(d->sinds.p, sinds.data(), sinds.size() * sizeof(long long), cudaMemcpyHostToDevice, st));
-  if (nd > 0) {
-    GSP_CUDA_OK(ctx, cudaMemcpyAsync(d->dinds.p, dind0.data(), dind0.size() * sizeof(long long), cudaMemcpyHostToDevice, st));
-    GSP_CUDA_OK(ctx, cudaMemcpyAsync(d->z1.p, z1, (size_t)nd * sizeof(double), cudaMemcpyHostToDevice, st));
-  }
-  if (dd.kind == 0) {
-    GSP_CUDA_OK(ctx, dcoords.alloc(dc.dev, (size_t)N * dd.dim * sizeof(double)));
-    GSP_CUDA_OK(ctx, cudaMemcpyAsync(dcoords.p, dom->coords, (size_t)N * dd.dim * sizeof(double), cudaMemcpyHostToDevice, st));
-    dd.coords = dcoords.as<double>();
-  }
-  cudaEvent_t tev[4];
-  for (auto& e : tev) GSP_CUDA_OK(ctx, cudaEventCreate(&e));
-  GSP_CUDA_OK(ctx, cudaEventRecord(tev[0], st));
-  // a1: joint covariance, lower tiles only (lusim.jl:88,95,96)
-  launch_assemble(st, cd, dd, dd, dperm.as<long long>(), dperm.as<long long>(), p->Np, p->Np, d->A.as<double>(), p->Np, true);
-  GSP_CUDA_OK(ctx, cudaGetLastError());
   GSP_CUDA_OK(ctx, cudaEventRecord(tev[1], st));
   // a2/a3: one joint Cholesky (lusim.jl:92 or 98-103)
-  GSP_CUDA_OK(ctx, chol_factor(st, dc.side, DevCtx::kSide, d->A.as<double>(), p->Np, (int)(p->Np / 128), d->invD.as<double>(), d->info.as<int>()));
+  if (mg) {
+    std::vector<MgDev> mds;
+    for (auto& d : p->dev)
+      mds.push_back(MgDev{d->dc->dev, d->dc->stream, d->dc->side[0], d->dc->h2d, d->A.as<double>(), d->invD.as<double>(), d->info.as<int>()});
+    GSP_CUDA_OK(ctx, chol_factor_mg(mds, p->Np, nb, mg_pb));
+    cudaSetDevice(dc.dev);
+  } else {
+    GSP_CUDA_OK(ctx, chol_factor(st, dc.side, DevCtx::kSide, d0->A.as<double>(), p->Np, nb, d0->invD.as<double>(), d0->info.as<int>()));
+  }
   GSP_CUDA_OK(ctx, cudaEventRecord(tev[2], st));
   // d2 = A21 * (L11 \ z1)   (lusim.jl:102); zero when unconditional (lusim.jl:91)
-  GSP_CUDA_OK(ctx, cudaMemsetAsync(d->d2.p, 0, (size_t)p->Nsp * sizeof(double), st));
+  DevBuf y;
+  GSP_CUDA_OK(ctx, cudaMemsetAsync(d0->d2.p, 0, (size_t)p->Nsp * sizeof(double), st));
   if (nd > 0) {
     GSP_CUDA_OK(ctx, y.alloc(dc.dev, (size_t)p->Ndp * sizeof(double)));
     GSP_CUDA_OK(ctx, cudaMemsetAsync(y.p, 0, (size_t)p->Ndp * sizeof(double), st));
     GSP_CUDA_OK(ctx, cudaMemcpyAsync(y.p, z1, (size_t)nd * sizeof(double), cudaMemcpyHostToDevice, st));
-    GSP_CUDA_OK(ctx, chol_forward_solve(st, d->A.as<double>(), p->Np, d->invD.as<double>(), (int)(p->Ndp / 128), y.as<double>()));
-    GSP_CUDA_OK(ctx, chol_gemv_rows(st, d->A.as<double>(), p->Np, p->Ndp, p->Nsp, (int)p->Ndp, y.as<double>(), d->d2.as<double>()));
+    GSP_CUDA_OK(ctx, chol_forward_solve(st, d0->A.as<double>(), p->Np, d0->invD.as<double>(), (int)(p->Ndp / 128), y.as<double>()));
+    GSP_CUDA_OK(ctx, chol_gemv_rows(st, d0->A.as<double>(), p->Np, p->Ndp, p->Nsp, (int)p->Ndp, y.as<double>(), d0->d2.as<double>()));
   }
   GSP_CUDA_OK(ctx, cudaEventRecord(tev[3], st));
   int info = 0;
-  GSP_CUDA_OK(ctx, cudaMemcpyAsync(&info, d->info.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  for (int i = 0; i < nbuild; ++i) {  // the first non-positive pivot may have been met on any panel owner
+    int inf_i = 0;
+    cudaSetDevice(p->dev[i]->dc->dev);
+    GSP_CUDA_OK(ctx, cudaMemcpyAsync(&inf_i, p->dev[i]->info.p, sizeof(int), cudaMemcpyDeviceToHost, p->dev[i]->dc->stream));
+    GSP_CUDA_OK(ctx, cudaStreamSynchronize(p->dev[i]->dc->stream));
+    if (inf_i > 0 && (info == 0 || inf_i < info)) info = inf_i;
+  }
+  cudaSetDevice(dc.dev);
   GSP_CUDA_OK(ctx, cudaStreamSynchronize(st));
   {
     float ms = 0.f;
@@ -271,28 +320,13 @@ extern "C" int gsp_lu_plan_create(gsp_ctx* ctx, const gsp_cov_model* cov, const 
     set_err(ctx, (int)ref, "matrix is not positive definite (PosDefException)");
     return (int)ref;
   }
-  p->dev.push_back(std::move(d));
-
-  // other devices receive L, d2 and the index maps (realizations are sharded, the factor is not)
-  for (size_t i = 1; i < ctx->devs.size(); ++i) {
-    std::unique_ptr<LuDev> e(new LuDev);
-    e->dc = &ctx->devs[i];
-    LuDev* s0 = p->dev[0].get();
+  // the other devices receive d2 (and L, unless the multi-GPU factorization already left it everywhere)
+  for (int i = 1; i < ndev; ++i) {
+    LuDev* e = p->dev[i].get();
     cudaSetDevice(e->dc->dev);
-    GSP_CUDA_OK(ctx, e->A.alloc(e->dc->dev, s0->A.bytes));
-    GSP_CUDA_OK(ctx, e->d2.alloc(e->dc->dev, s0->d2.bytes));
-    GSP_CUDA_OK(ctx, e->sinds.alloc(e->dc->dev, s0->sinds.bytes));
-    GSP_CUDA_OK(ctx, e->dinds.alloc(e->dc->dev, s0->dinds.bytes));
-    GSP_CUDA_OK(ctx, e->z1.alloc(e->dc->dev, s0->z1.bytes));
-    GSP_CUDA_OK(ctx, cudaEventCreate(&e->ev0));
-    GSP_CUDA_OK(ctx, cudaEventCreate(&e->ev1));
-    GSP_CUDA_OK(ctx, cudaMemcpyPeerAsync(e->A.p, e->dc->dev, s0->A.p, s0->dc->dev, s0->A.bytes, e->dc->stream));
-    GSP_CUDA_OK(ctx, cudaMemcpyPeerAsync(e->d2.p, e->dc->dev, s0->d2.p, s0->dc->dev, s0->d2.bytes, e->dc->stream));
-    GSP_CUDA_OK(ctx, cudaMemcpyPeerAsync(e->sinds.p, e->dc->dev, s0->sinds.p, s0->dc->dev, s0->sinds.bytes, e->dc->stream));
-    GSP_CUDA_OK(ctx, cudaMemcpyPeerAsync(e->dinds.p, e->dc->dev, s0->dinds.p, s0->dc->dev, s0->dinds.bytes, e->dc->stream));
-    GSP_CUDA_OK(ctx, cudaMemcpyPeerAsync(e->z1.p, e->dc->dev, s0->z1.p, s0->dc->dev, s0->z1.bytes, e->dc->stream));
+    if (!mg) GSP_CUDA_OK(ctx, cudaMemcpyPeerAsync(e->A.p, e->dc->dev, d0->A.p, d0->dc->dev, d0->A.bytes, e->dc->stream));
+    GSP_CUDA_OK(ctx, cudaMemcpyPeerAsync(e->d2.p, e->dc->dev, d0->d2.p, d0->dc->dev, d0->d2.bytes, e->dc->stream));
     GSP_CUDA_OK(ctx, cudaStreamSynchronize(e->dc->stream));
-    p->dev.push_back(std::move(e));
   }
   *out = p.release();
   return GSP_OK;
@@ -401,7 +435,8 @@ extern "C" int gsp_lu_sample(gsp_lu_plan* p, int64_t R, const double* W, uint64_
     cudaEventRecord(d0->ev0, d0->dc->stream);
   }
   int rc = GSP_OK;
-  // chunks are issued round-robin over the devices; each device runs H2D -> compute -> D2H in stream order
+  // chunks are issued round-robin over the devices; each device runs H2D -> compute -> D2H in stream order.  The D2H copies
+  // are issued in a second sweep so that a (host-blocking) copy into pageable memory overlaps the other devices' compute.
   for (long long c0 = 0; c0 < maxshard && rc == GSP_OK; c0 += chunk) {
     for (int i = 0; i < ndev && rc == GSP_OK; ++i) {
       const long long nloc = r0[i + 1] - r0[i];
@@ -424,8 +459,15 @@ extern "C" int gsp_lu_sample(gsp_lu_plan* p, int64_t R, const double* W, uint64_
       }
       if (e != cudaSuccess) { rc = set_err(ctx, GSP_E_CUDA, cudaGetErrorString(e)); break; }
       rc = sample_core(ctx, p, d, cols, Wd, p->Ns, seed, stream, first_real + ra, rho, W1d, d->Zc.as<double>(), p->N);
-      if (rc != GSP_OK) break;
-      e = cudaMemcpyAsync(Z + ra * p->N, d->Zc.p, (size_t)p->N * cols * sizeof(double), cudaMemcpyDeviceToHost, st);
+    }
+    for (int i = 0; i < ndev && rc == GSP_OK; ++i) {
+      const long long nloc = r0[i + 1] - r0[i];
+      if (c0 >= nloc) continue;
+      LuDev* d = p->dev[i].get();
+      cudaSetDevice(d->dc->dev);
+      const long long cols = std::min(chunk, nloc - c0);
+      const long long ra = r0[i] + c0;
+      cudaError_t e = cudaMemcpyAsync(Z + ra * p->N, d->Zc.p, (size_t)p->N * cols * sizeof(double), cudaMemcpyDeviceToHost, d->dc->stream);
       if (e != cudaSuccess) { rc = set_err(ctx, GSP_E_CUDA, cudaGetErrorString(e)); break; }
     }
   }

@@ -231,3 +231,35 @@ def test_cholesky_big_tile_path(emu_lib):
     env = dict(os.environ, GSP_GEMM_SMALL_TILES="0", GSP_CHOL_LOOKAHEAD="1")
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
     assert out.returncode == 0 and "OK" in out.stdout, out.stderr[-1500:]
+
+
+def test_multi_device_block_cyclic_cholesky(emu_lib):
+    """multi-GPU factorization (chol_factor_mg): panels owned cyclically, pushed in place to every device; exercised with the
+    emulated device listed 3 times (separate buffers per listed device), PB = 1 block, in a subprocess (env is cached)."""
+    import os, subprocess, sys, textwrap
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = textwrap.dedent("""
+        import sys, numpy as np
+        sys.path.insert(0, %r); sys.path.insert(0, %r); sys.path.insert(0, %r)
+        import gsp_b200 as gsp, gsp_oracle as O
+        from helpers import iso, ostructs, relerr
+        for devs in ([0, 0, 0],):
+            lib = gsp.Library(%r, devices=devs)
+            rng = np.random.default_rng(0)
+            dims = (24, 20); st = iso(O.EXPONENTIAL, 1.0, 6.0, 2)
+            coords = O.grid_centroids(dims, [0, 0], [1, 1])
+            dinds = np.sort(rng.choice(480, 140, replace=False)); z1 = rng.standard_normal(140)
+            plan = gsp.LUPlan(lib, st, (gsp._lib.make_grid_domain(dims, [0, 0], [1, 1]), None), dinds + 1, z1, 0.0)
+            pre = O.lusim_preprocess(ostructs(st), coords, dinds, z1, 0.0)
+            d2, L22 = plan.get()
+            assert relerr(L22, pre.L22) < 1e-12 and np.abs(d2 - pre.d2).max() < 1e-12
+            W = rng.standard_normal((plan.Ns, 7))
+            Z = plan.sample(7, W)
+            assert relerr(Z, O.lusim_sample(pre, W)) < 1e-9
+            assert np.array_equal(Z[dinds], np.repeat(z1[:, None], 7, 1))
+            plan.close(); lib.close()
+        print("OK")
+    """) % (root, os.path.join(root, "oracle"), os.path.join(root, "tests"), emu_lib.path)
+    env = dict(os.environ, GSP_CHOL_MG_MIN_BLOCKS="2", GSP_CHOL_MG_PB="1")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=900)
+    assert out.returncode == 0 and "OK" in out.stdout, out.stderr[-1500:]

@@ -15,6 +15,11 @@ dom = (gsp._lib.make_grid_domain((128, 128), [0.0, 0.0], [1.0, 1.0]), None)
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 for _ in range(reps):
     t = time.time(); plan = gsp.LUPlan(lib, st, dom, dinds + 1, z1, 0.0); print("plan s", time.time() - t, "stage ms (assemble, factor, solve)", plan.times(), flush=True)
+lib.profile_enable(True)
+p2 = gsp.LUPlan(lib, st, dom, dinds + 1, z1, 0.0)
+print("kernel ms:", {k: (round(v["ms"], 2), v["launches"]) for k, v in lib.profile_read().items()}, "factor ms", p2.times()[1], flush=True)
+lib.profile_enable(False)
+p2.close()
 R = 1000
 dev = torch.device("cuda:0")
 W = torch.randn((R, plan.Ns), dtype=torch.float64, device=dev); Z = torch.empty((R, N), dtype=torch.float64, device=dev)

@@ -182,6 +182,17 @@ def run_gpu(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE JSON line: anything libraries print while we run (e.g. NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(obj), flush=True)
+        os.dup2(2, 1)
+
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -322,7 +333,7 @@ def run_gpu(args):
                                               f"(scipy.fft workers={os.cpu_count()}); Julia is absent so the restatement stands in for the reference CPU path"}
         if lus is not None:
             line["lusim"] = lus
-        print(json.dumps(line))
+        emit(line)
     plan.close()
     if world > 1:
         dist.destroy_process_group()

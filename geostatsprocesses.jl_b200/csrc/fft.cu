@@ -242,6 +242,21 @@ bool choose_radices(int n, LinePlan* lp) {
   return m == 1;
 }
 
+// per-stage tables of fft_pow2.cuh: stage s >= 1 of the length-n transform, w[r][k] = exp(-2*pi*i*r*k/(Ns*R)), k fastest
+std::vector<cplx> make_stage_twiddles(int n, bool inv) {
+  std::vector<cplx> t((size_t)p2_stw_size(n, inv) + 1);
+  const long double two_pi = 6.283185307179586476925286766559005768L;
+  for (int s = 1; s < p2_stages(n); ++s) {
+    const int R = p2_radix(n, inv, s), Ns = p2_ns(n, inv, s), off = p2_stw_offset(n, inv, s);
+    for (int r = 0; r < R; ++r)
+      for (int k = 0; k < Ns; ++k) {
+        const long double a = two_pi * (long double)(r * k) / (long double)(Ns * R);
+        t[(size_t)off + (size_t)r * Ns + k] = cplx{(double)cosl(a), (double)-sinl(a)};
+      }
+  }
+  return t;
+}
+
 std::vector<cplx> make_twiddles(int n) {
   std::vector<cplx> t((size_t)n);
   const long double two_pi = 6.283185307179586476925286766559005768L;
@@ -266,6 +281,8 @@ struct AxisPlan {
 struct FftDev {
   DevCtx* dc = nullptr;
   DevBuf tw[3];
+  DevBuf stw_fwd, stw_inv;  // x axis: per-stage twiddle tables of the length-nx/2 transform (forward / inverse radix order)
+  DevBuf stw_ax_fwd[3], stw_ax_inv[3];  // strided axes: the same for the full-length transforms
   DevBuf Fh;       // real half spectrum
   DevBuf H;        // complex half-spectrum work buffer
   DevBuf win[2], zout[2];  // staging for host-pointer sampling
@@ -316,33 +333,34 @@ inline unsigned persistent_grid(K kfn, int threads, int sms, size_t smem, long l
 }
 
 template <int HN>
-cudaError_t launch_p2_xfwd(cudaStream_t st, int sms, const double* in, cplx* H, const cplx* tw, long long nrows) {
+cudaError_t launch_p2_xfwd(cudaStream_t st, int sms, const double* in, cplx* H, const cplx* tw, const cplx* stw, long long nrows) {
   using C = XCfg<HN, false>;
   auto kfn = p2_xfwd_kernel<HN>;
   cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
   if (e != cudaSuccess) return e;
   const long long ngroups = (nrows + C::ROWS - 1) / C::ROWS;
   ProfScope prof_("fft_xpass_fwd", st);
-  GSP_LAUNCH(kfn, dim3(persistent_grid(kfn, C::THREADS, sms, C::SMEM, ngroups)), dim3(C::THREADS), C::SMEM, st, in, H, tw, nrows);
+  GSP_LAUNCH(kfn, dim3(persistent_grid(kfn, C::THREADS, sms, C::SMEM, ngroups)), dim3(C::THREADS), C::SMEM, st, in, H, tw, stw, nrows);
   g_launches++;
   return cudaGetLastError();
 }
 
 template <int HN>
-cudaError_t launch_p2_xinv(cudaStream_t st, int sms, const cplx* H, double* out, const cplx* tw, long long nrows, double scale, double mu) {
+cudaError_t launch_p2_xinv(cudaStream_t st, int sms, const cplx* H, double* out, const cplx* tw, const cplx* stw, long long nrows, double scale,
+                           double mu) {
   using C = XCfg<HN, true>;
   auto kfn = p2_xinv_kernel<HN>;
   cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
   if (e != cudaSuccess) return e;
   const long long ngroups = (nrows + C::ROWS - 1) / C::ROWS;
   ProfScope prof_("fft_xpass_inv", st);
-  GSP_LAUNCH(kfn, dim3(persistent_grid(kfn, C::THREADS, sms, C::SMEM, ngroups)), dim3(C::THREADS), C::SMEM, st, H, out, tw, nrows, scale, mu);
+  GSP_LAUNCH(kfn, dim3(persistent_grid(kfn, C::THREADS, sms, C::SMEM, ngroups)), dim3(C::THREADS), C::SMEM, st, H, out, tw, stw, nrows, scale, mu);
   g_launches++;
   return cudaGetLastError();
 }
 
 template <int N, int FLAGS>
-cudaError_t launch_p2_strided_f(cudaStream_t st, int sms, const TensorMap& tmH, int axis, cplx* H, const cplx* tw, long long es, int hx,
+cudaError_t launch_p2_strided_f(cudaStream_t st, int sms, const TensorMap& tmH, int axis, cplx* H, const cplx* tw, const cplx* twi, long long es, int hx,
                                 long long nother, long long other_stride, const double* Fh, long long esF, long long other_strideF, double s) {
   constexpr int B = p2_bundle(N);
   constexpr int STAGES = GSP_STRIDED_STAGES;
@@ -353,19 +371,19 @@ cudaError_t launch_p2_strided_f(cudaStream_t st, int sms, const TensorMap& tmH, 
   const int nbundles = (hx + B - 1) / B;
   const long long nunits = (long long)nbundles * nother;
   ProfScope prof_((FLAGS & P2_MUL) ? "fft_strided_fwd_mul_inv" : ((FLAGS & P2_FWD) ? "fft_strided_fwd" : "fft_strided_inv"), st);
-  GSP_LAUNCH(kfn, dim3(persistent_grid(kfn, C::THREADS, sms, C::SMEM, nunits)), dim3(C::THREADS), C::SMEM, st, tmH, axis, H, tw, es, hx, nbundles, nunits,
+  GSP_LAUNCH(kfn, dim3(persistent_grid(kfn, C::THREADS, sms, C::SMEM, nunits)), dim3(C::THREADS), C::SMEM, st, tmH, axis, H, tw, twi, es, hx, nbundles, nunits,
              other_stride, Fh, esF, other_strideF, s);
   g_launches++;
   return cudaGetLastError();
 }
 
 template <int N>
-cudaError_t launch_p2_strided(cudaStream_t st, int sms, int flags, const TensorMap& tmH, int axis, cplx* H, const cplx* tw, long long es,
+cudaError_t launch_p2_strided(cudaStream_t st, int sms, int flags, const TensorMap& tmH, int axis, cplx* H, const cplx* tw, const cplx* twi, long long es,
                               int hx, long long nother, long long other_stride, const double* Fh, long long esF, long long other_strideF,
                               double s) {
-  if (flags == P2_FWD) return launch_p2_strided_f<N, P2_FWD>(st, sms, tmH, axis, H, tw, es, hx, nother, other_stride, Fh, esF, other_strideF, s);
-  if (flags == P2_INV) return launch_p2_strided_f<N, P2_INV>(st, sms, tmH, axis, H, tw, es, hx, nother, other_stride, Fh, esF, other_strideF, s);
-  return launch_p2_strided_f<N, P2_FWD | P2_MUL | P2_INV>(st, sms, tmH, axis, H, tw, es, hx, nother, other_stride, Fh, esF, other_strideF, s);
+  if (flags == P2_FWD) return launch_p2_strided_f<N, P2_FWD>(st, sms, tmH, axis, H, tw, twi, es, hx, nother, other_stride, Fh, esF, other_strideF, s);
+  if (flags == P2_INV) return launch_p2_strided_f<N, P2_INV>(st, sms, tmH, axis, H, tw, twi, es, hx, nother, other_stride, Fh, esF, other_strideF, s);
+  return launch_p2_strided_f<N, P2_FWD | P2_MUL | P2_INV>(st, sms, tmH, axis, H, tw, twi, es, hx, nother, other_stride, Fh, esF, other_strideF, s);
 }
 
 template <int HN, int NY, bool INV>
@@ -450,6 +468,15 @@ int setup_axes(gsp_ctx* ctx, gsp_fft_plan* p, FftDev* d) {
     a.B = B;
     a.smem = 2 * L * B * sizeof(cplx);
     a.fast = a.packed && p2_supported(nx / 2) && !g_force_generic;
+    if (a.fast) {
+      for (int inv = 0; inv < 2; ++inv) {
+        std::vector<cplx> stw = make_stage_twiddles(nx / 2, inv != 0);
+        DevBuf& b = inv ? d->stw_inv : d->stw_fwd;
+        GSP_CUDA_OK(ctx, b.alloc(d->dc->dev, stw.size() * sizeof(cplx)));
+        GSP_CUDA_OK(ctx, cudaMemcpyAsync(b.p, stw.data(), stw.size() * sizeof(cplx), cudaMemcpyHostToDevice, d->dc->stream));
+        GSP_CUDA_OK(ctx, cudaStreamSynchronize(d->dc->stream));
+      }
+    }
     if (!a.fast && a.smem > kMaxSmem) return set_err(ctx, GSP_E_UNSUPPORTED, "x extent too large for one shared-memory line");
   }
   for (int axis = 1; axis < p->ndim; ++axis) {
@@ -469,6 +496,15 @@ int setup_axes(gsp_ctx* ctx, gsp_fft_plan* p, FftDev* d) {
     a.B = B;
     a.smem = 2 * (size_t)n * B * sizeof(cplx);
     a.fast = p2_supported(n) && !g_force_generic;
+    if (a.fast) {
+      for (int inv = 0; inv < 2; ++inv) {
+        std::vector<cplx> stw = make_stage_twiddles(n, inv != 0);
+        DevBuf& b = inv ? d->stw_ax_inv[axis] : d->stw_ax_fwd[axis];
+        GSP_CUDA_OK(ctx, b.alloc(d->dc->dev, stw.size() * sizeof(cplx)));
+        GSP_CUDA_OK(ctx, cudaMemcpyAsync(b.p, stw.data(), stw.size() * sizeof(cplx), cudaMemcpyHostToDevice, d->dc->stream));
+        GSP_CUDA_OK(ctx, cudaStreamSynchronize(d->dc->stream));
+      }
+    }
     if (!a.fast && a.smem > kMaxSmem) return set_err(ctx, GSP_E_UNSUPPORTED, "grid extent too large for one shared-memory line");
   }
   return GSP_OK;
@@ -478,7 +514,7 @@ cudaError_t run_xfwd(FftDev* d, gsp_fft_plan* p, const double* in, cplx* H) {
   const AxisPlan& a = d->ax[0];
   const long long nrows = p->dims[1] * p->dims[2];
   if (a.fast) {
-#define GSP_CALL(HN) launch_p2_xfwd<HN>(d->dc->stream, d->dc->sms, in, H, a.lp.tw, nrows)
+#define GSP_CALL(HN) launch_p2_xfwd<HN>(d->dc->stream, d->dc->sms, in, H, a.lp.tw, d->stw_fwd.as<cplx>(), nrows)
     GSP_P2_SWITCH((int)p->dims[0] / 2, GSP_CALL)
 #undef GSP_CALL
   }
@@ -496,7 +532,7 @@ cudaError_t run_xinv(FftDev* d, gsp_fft_plan* p, const cplx* H, double* out, dou
   const AxisPlan& a = d->ax[0];
   const long long nrows = p->dims[1] * p->dims[2];
   if (a.fast) {
-#define GSP_CALL(HN) launch_p2_xinv<HN>(d->dc->stream, d->dc->sms, H, out, a.lp.tw, nrows, scale, mu)
+#define GSP_CALL(HN) launch_p2_xinv<HN>(d->dc->stream, d->dc->sms, H, out, a.lp.tw, d->stw_inv.as<cplx>(), nrows, scale, mu)
     GSP_P2_SWITCH((int)p->dims[0] / 2, GSP_CALL)
 #undef GSP_CALL
   }
@@ -530,7 +566,8 @@ cudaError_t run_strided(FftDev* d, gsp_fft_plan* p, int axis, cplx* H, int flags
   }
   if (a.fast) {
 #define GSP_CALL(NN) \
-  launch_p2_strided<NN>(d->dc->stream, d->dc->sms, flags, a.tmH, axis, H, a.lp.tw, es, (int)hx, nother, other_stride, Fh, esF, other_strideF, s)
+  launch_p2_strided<NN>(d->dc->stream, d->dc->sms, flags, a.tmH, axis, H, d->stw_ax_fwd[axis].as<cplx>(), d->stw_ax_inv[axis].as<cplx>(), es, (int)hx, \
+                        nother, other_stride, Fh, esF, other_strideF, s)
     GSP_P2_SWITCH(a.len, GSP_CALL)
 #undef GSP_CALL
   }

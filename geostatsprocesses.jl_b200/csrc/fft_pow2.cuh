@@ -64,7 +64,17 @@ GSP_DEV int p2_out_pos(int t, int q, int r) {
   return (jb - k) * R + k + r * Ns;
 }
 
-// twiddle + butterflies of stage s on the register slots.  tw[i * TWS] = exp(-2*pi*i*i/N) (shared memory)
+// Per-stage twiddle tables (x passes): stage s >= 1 stores w[r][k] = exp(-2*pi*i*r*k/(Ns*R)), k fastest, so that lanes with
+// consecutive k read consecutive 16-byte entries (the strided table tw[(r*k)*step] costs up to 8-way bank conflicts there).
+GSP_HD constexpr int p2_stw_offset(int N, bool inv, int s) {
+  int off = 0;
+  for (int i = 1; i < s; ++i) off += p2_radix(N, inv, i) * p2_ns(N, inv, i);
+  return off;
+}
+GSP_HD constexpr int p2_stw_size(int N, bool inv) { return p2_stw_offset(N, inv, p2_stages(N)); }
+
+// twiddle + butterflies of stage s on the register slots.  TWS > 0: tw[i * TWS] = exp(-2*pi*i*i/N) (strided table);
+// TWS == 0: tw = per-stage tables (p2_stw_offset layout).  Both in shared memory.
 template <int N, bool INV, int S_, int TWS>
 GSP_DEV void p2_stage(cplx* v, int t, const cplx* tw) {
   constexpr int R = p2_radix(N, INV, S_);
@@ -78,7 +88,7 @@ GSP_DEV void p2_stage(cplx* v, int t, const cplx* tw) {
       const int k = (t + TPL * q) & (Ns - 1);
 #pragma unroll
       for (int r = 1; r < R; ++r) {
-        cplx w = tw[(r * k) * (N / (Ns * R)) * TWS];
+        cplx w = (TWS == 0) ? tw[p2_stw_offset(N, INV, S_) + r * Ns + k] : tw[(r * k) * (N / (Ns * R)) * (TWS == 0 ? 1 : TWS)];
         if (INV) w.im = -w.im;
         v[q * R + r] = cmul(v[q * R + r], w);
       }
@@ -155,14 +165,17 @@ struct StridedCfg {
   static constexpr bool MUL = (FLAGS & P2_MUL) != 0;
   static constexpr size_t IN_BYTES = (size_t)N * B * sizeof(cplx);
   static constexpr size_t F_BYTES = 0;  // F goes global -> registers (issued before the forward transform): keeps 3 CTAs per SM
-  static constexpr size_t SMEM = (size_t)N * sizeof(cplx) + STAGES * (IN_BYTES + F_BYTES) + 2 * sizeof(mbar_t) + 16;
+  static constexpr int STWF = p2_stw_size(N, false), STWI = p2_stw_size(N, true);  // per-stage twiddle tables
+  static constexpr size_t TW_BYTES = ((size_t)(STWF + STWI) * sizeof(cplx) + 127) / 128 * 128;
+  static constexpr size_t SMEM = TW_BYTES + STAGES * (IN_BYTES + F_BYTES) + 2 * sizeof(mbar_t) + 16;
   static constexpr int MINB = (STAGES == 1 && THREADS <= 128) ? 4 : 1;  // register cap for 4 CTAs per SM
 };
 
 template <int N, int B, int FLAGS, int STAGES>
 __global__ void __launch_bounds__(StridedCfg<N, B, FLAGS, STAGES>::THREADS, StridedCfg<N, B, FLAGS, STAGES>::MINB)
     p2_strided_kernel(const GSP_GRID_CONSTANT TensorMap tmH, int line_axis,
-                                                                                     cplx* __restrict__ H, const cplx* __restrict__ twg,
+                                                                                     cplx* __restrict__ H, const cplx* __restrict__ stwfg,
+                                                                                     const cplx* __restrict__ stwig,
                                                                                      long long es, int hx, int nbundles, long long nunits,
                                                                                      long long other_stride, const double* __restrict__ Fh,
                                                                                      long long esF, long long other_strideF, double s) {
@@ -170,8 +183,9 @@ __global__ void __launch_bounds__(StridedCfg<N, B, FLAGS, STAGES>::THREADS, Stri
   constexpr int SL = C::SL, TPU = C::THREADS;
   constexpr bool MUL = C::MUL;
   GSP_DYN_SMEM(smem);
-  cplx* tw = reinterpret_cast<cplx*>(smem);
-  unsigned char* stage0 = smem + (size_t)N * sizeof(cplx);
+  cplx* stwf = reinterpret_cast<cplx*>(smem);  // per-stage twiddles, forward radix order
+  cplx* stwi = stwf + C::STWF;                 // ... inverse radix order
+  unsigned char* stage0 = smem + C::TW_BYTES;
   mbar_t* full = reinterpret_cast<mbar_t*>(stage0 + STAGES * (C::IN_BYTES + C::F_BYTES));
   const int tid = threadIdx.x;
   const int b = tid % B, t = tid / B;
@@ -180,13 +194,19 @@ __global__ void __launch_bounds__(StridedCfg<N, B, FLAGS, STAGES>::THREADS, Stri
     mbar_init(&full[1], 1);
     fence_mbar_init();
   }
-  for (int i = tid; i < N; i += TPU) tw[i] = twg[i];
+  if ((FLAGS & P2_FWD) != 0)
+    for (int i = tid; i < C::STWF; i += TPU) stwf[i] = stwfg[i];
+  if ((FLAGS & P2_INV) != 0)
+    for (int i = tid; i < C::STWI; i += TPU) stwi[i] = stwig[i];
   __syncthreads();
 
   auto stage_in = [&](int sg) { return reinterpret_cast<cplx*>(stage0 + (size_t)sg * (C::IN_BYTES + C::F_BYTES)); };
   // one TMA tensor copy per item and operand: box = (B kx as 2B doubles) x (whole line), zero-filled past hx
   auto issue = [&](long long unit, int sg) {
     if (tid == 0) {
+      // the stage was last touched through the generic proxy (exchanges overlay it); the block barrier that ended that
+      // iteration ordered those accesses before this thread, the proxy fence orders them before the async-proxy fill
+      fence_proxy_async();
       const long long o = unit / nbundles;
       const int bx = (int)(unit - o * nbundles);
       const int c1 = line_axis == 1 ? 0 : (int)o, c2 = line_axis == 1 ? (int)o : 0;
@@ -232,7 +252,7 @@ __global__ void __launch_bounds__(StridedCfg<N, B, FLAGS, STAGES>::THREADS, Stri
     for (int q = 0; q < SL / R0; ++q)
 #pragma unroll
       for (int r = 0; r < R0; ++r) v[q * R0 + r] = buf[lay(p2_in_pos<N, FIRST_INV, 0>(t, q, r))];
-    if constexpr ((FLAGS & P2_FWD) != 0) p2_fft<N, false, 1>(v, t, buf, lay, tw);
+    if constexpr ((FLAGS & P2_FWD) != 0) p2_fft<N, false, 0>(v, t, buf, lay, stwf);
     if constexpr (MUL) {
       // slot (q, r) holds frequency f = p2_in_pos<N, true, 0>(t, q, r): P = s*F*W/|W|, angle(0) = 0 (fftsim.jl:125)
       constexpr int RI = p2_radix(N, true, 0);
@@ -251,7 +271,7 @@ __global__ void __launch_bounds__(StridedCfg<N, B, FLAGS, STAGES>::THREADS, Stri
           }
         }
     }
-    if constexpr ((FLAGS & P2_INV) != 0) p2_fft<N, true, 1>(v, t, buf, lay, tw);
+    if constexpr ((FLAGS & P2_INV) != 0) p2_fft<N, true, 0>(v, t, buf, lay, stwi);
     constexpr bool LAST_INV = (FLAGS & P2_INV) != 0;
     constexpr int RO = p2_radix(N, !LAST_INV, 0);
     if (valid) {
@@ -263,7 +283,6 @@ __global__ void __launch_bounds__(StridedCfg<N, B, FLAGS, STAGES>::THREADS, Stri
           st_stream2(reinterpret_cast<double*>(H + base + (long long)m * es), make_double2(v[q * RO + r].re, v[q * RO + r].im));
         }
     }
-    fence_proxy_async();  // generic-proxy traffic on this stage is ordered before the next bulk fill
     __syncthreads();
   }
 }
@@ -287,18 +306,22 @@ struct XCfg {
   static constexpr size_t EX_BYTES = (size_t)ROWS * ROWLEN * sizeof(cplx);
   // the exchange buffer overlays the (already consumed) input stage: 2 stages + twiddles = 74.5 KB at nx = 256 -> 3 CTAs per SM
   static constexpr size_t STAGE_BYTES = ((IN_BYTES > EX_BYTES ? IN_BYTES : EX_BYTES) + 127) / 128 * 128;
-  static constexpr size_t SMEM = (size_t)NX * sizeof(cplx) + STAGES * STAGE_BYTES + 2 * sizeof(mbar_t) + 16;
+  static constexpr int STW = p2_stw_size(HN, INV);  // per-stage twiddle entries (conflict-free layout)
+  static constexpr size_t TW_BYTES = ((size_t)(NX + STW) * sizeof(cplx) + 127) / 128 * 128;
+  static constexpr size_t SMEM = TW_BYTES + STAGES * STAGE_BYTES + 2 * sizeof(mbar_t) + 16;
   static constexpr int MINB = (STAGES == 1 && THREADS <= 128) ? 4 : 1;
 };
 
 template <int HN>
 __global__ void __launch_bounds__(XCfg<HN, false>::THREADS, XCfg<HN, false>::MINB) p2_xfwd_kernel(const double* __restrict__ in, cplx* __restrict__ H,
-                                                                          const cplx* __restrict__ twg, long long nrows) {
+                                                                          const cplx* __restrict__ twg, const cplx* __restrict__ stwg,
+                                                                          long long nrows) {
   using C = XCfg<HN, false>;
   constexpr int NX = C::NX, HX = C::HX, SL = C::SL, TPL = C::TPL;
   GSP_DYN_SMEM(smem);
-  cplx* tw = reinterpret_cast<cplx*>(smem);  // exp(-2*pi*i*t/NX), t < NX
-  unsigned char* stage0 = smem + (size_t)NX * sizeof(cplx);
+  cplx* tw = reinterpret_cast<cplx*>(smem);  // exp(-2*pi*i*t/NX), t < NX (untangling)
+  cplx* stw = tw + NX;                         // per-stage twiddles of the length-HN transform
+  unsigned char* stage0 = smem + C::TW_BYTES;
   mbar_t* full = reinterpret_cast<mbar_t*>(stage0 + C::STAGES * C::STAGE_BYTES);
   const int tid = threadIdx.x;
   if (tid == 0) {
@@ -307,10 +330,12 @@ __global__ void __launch_bounds__(XCfg<HN, false>::THREADS, XCfg<HN, false>::MIN
     fence_mbar_init();
   }
   for (int i = tid; i < NX; i += C::THREADS) tw[i] = twg[i];
+  for (int i = tid; i < C::STW; i += C::THREADS) stw[i] = stwg[i];
   __syncthreads();
   const long long ngroups = (nrows + C::ROWS - 1) / C::ROWS;
   auto issue = [&](long long g, int sg) {
     if (tid == 0) {
+      fence_proxy_async();  // see p2_strided_kernel: generic-proxy accesses of the stage precede the async-proxy fill
       const long long r0 = g * C::ROWS;
       const long long nv = (nrows - r0 < C::ROWS) ? nrows - r0 : C::ROWS;
       const uint32_t bytes = (uint32_t)(nv * NX * sizeof(double));
@@ -340,7 +365,7 @@ __global__ void __launch_bounds__(XCfg<HN, false>::THREADS, XCfg<HN, false>::MIN
     for (int q = 0; q < SL / R0; ++q)
 #pragma unroll
       for (int r = 0; r < R0; ++r) v[q * R0 + r] = src[p2_in_pos<HN, false, 0>(t, q, r)];
-    p2_fft<HN, false, 2>(v, t, ex, lay, tw);
+    p2_fft<HN, false, 0>(v, t, ex, lay, stw);
     // untangle: X[f] = E + w^f * O with E = (Z[f] + conj Z[h-f])/2, O = -i (Z[f] - conj Z[h-f])/2
     constexpr int RI = p2_radix(HN, true, 0);
     __syncthreads();
@@ -366,7 +391,6 @@ __global__ void __launch_bounds__(XCfg<HN, false>::THREADS, XCfg<HN, false>::MIN
           if (f == 0) st_stream2(reinterpret_cast<double*>(dst + HN), make_double2(zk.re - zk.im, 0.0));
         }
     }
-    fence_proxy_async();
     __syncthreads();
   }
 }
@@ -374,12 +398,14 @@ __global__ void __launch_bounds__(XCfg<HN, false>::THREADS, XCfg<HN, false>::MIN
 // x-axis inverse pass: half spectrum rows -> real rows; out = scale * (unnormalised inverse DFT) + mu
 template <int HN>
 __global__ void __launch_bounds__(XCfg<HN, true>::THREADS, XCfg<HN, true>::MINB) p2_xinv_kernel(const cplx* __restrict__ H, double* __restrict__ out,
-                                                                         const cplx* __restrict__ twg, long long nrows, double scale, double mu) {
+                                                                         const cplx* __restrict__ twg, const cplx* __restrict__ stwg,
+                                                                         long long nrows, double scale, double mu) {
   using C = XCfg<HN, true>;
   constexpr int NX = C::NX, HX = C::HX, SL = C::SL, TPL = C::TPL;
   GSP_DYN_SMEM(smem);
   cplx* tw = reinterpret_cast<cplx*>(smem);
-  unsigned char* stage0 = smem + (size_t)NX * sizeof(cplx);
+  cplx* stw = tw + NX;
+  unsigned char* stage0 = smem + C::TW_BYTES;
   mbar_t* full = reinterpret_cast<mbar_t*>(stage0 + C::STAGES * C::STAGE_BYTES);
   const int tid = threadIdx.x;
   if (tid == 0) {
@@ -388,10 +414,12 @@ __global__ void __launch_bounds__(XCfg<HN, true>::THREADS, XCfg<HN, true>::MINB)
     fence_mbar_init();
   }
   for (int i = tid; i < NX; i += C::THREADS) tw[i] = twg[i];
+  for (int i = tid; i < C::STW; i += C::THREADS) stw[i] = stwg[i];
   __syncthreads();
   const long long ngroups = (nrows + C::ROWS - 1) / C::ROWS;
   auto issue = [&](long long g, int sg) {
     if (tid == 0) {
+      fence_proxy_async();
       const long long r0 = g * C::ROWS;
       const long long nv = (nrows - r0 < C::ROWS) ? nrows - r0 : C::ROWS;
       const uint32_t bytes = (uint32_t)(nv * HX * sizeof(cplx));
@@ -429,7 +457,7 @@ __global__ void __launch_bounds__(XCfg<HN, true>::THREADS, XCfg<HN, true>::MINB)
         const cplx tt = cmul(cconj(tw[m]), d);
         v[q * R0 + r] = cplx{sm.re - tt.im, sm.im + tt.re};
       }
-    p2_fft<HN, true, 2>(v, t, ex, lay, tw);
+    p2_fft<HN, true, 0>(v, t, ex, lay, stw);
     constexpr int RO = p2_radix(HN, false, 0);
     if (valid) {
       double* dst = out + row * NX;
@@ -441,7 +469,6 @@ __global__ void __launch_bounds__(XCfg<HN, true>::THREADS, XCfg<HN, true>::MINB)
           st_stream2(dst + 2 * j, make_double2(v[q * RO + r].re * scale + mu, v[q * RO + r].im * scale + mu));
         }
     }
-    fence_proxy_async();
     __syncthreads();
   }
 }

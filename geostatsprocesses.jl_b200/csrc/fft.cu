@@ -164,11 +164,12 @@ __global__ void __launch_bounds__(256) strided_pass_kernel(LinePlan lp, cplx* __
 }
 
 // 1-D grids only: P = s * F * W/|W| elementwise on the half spectrum
+// (`total` = nh * batch elements; F repeats with period nh)
 __global__ void __launch_bounds__(256) spectral_mul_kernel(cplx* __restrict__ H, const double* __restrict__ Fh, long long nh,
-                                                           double s) {
+                                                           long long total, double s) {
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nh; i += stride) {
-    const double f = s * Fh[i];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const double f = s * Fh[i % nh];
     const cplx w = H[i];
     const double m2 = w.re * w.re + w.im * w.im;
     H[i] = (m2 > 0.0) ? cplx{f * rsqrt(m2) * w.re, f * rsqrt(m2) * w.im} : cplx{f, 0.0};
@@ -307,6 +308,7 @@ struct gsp_fft_plan {
   long long N = 1, nh = 1, nhF = 1;
   int hx = 1, hxF = 2;  // F rows are padded to an even length: 16-byte aligned rows for the bulk copies
   double sumF2 = 0.0;  // full-spectrum sum of F^2
+  long long rb = 1;    // realizations per launch (1-D / 2-D grids are batched so that small grids still fill the GPU)
   std::vector<std::unique_ptr<FftDev>> dev;
   std::mutex mu;
 };
@@ -360,7 +362,8 @@ cudaError_t launch_p2_xinv(cudaStream_t st, int sms, const cplx* H, double* out,
 }
 
 template <int N, int FLAGS>
-cudaError_t launch_p2_strided_f(cudaStream_t st, int sms, const TensorMap& tmH, int axis, cplx* H, const cplx* tw, const cplx* twi, long long es, int hx,
+cudaError_t launch_p2_strided_f(cudaStream_t st, int sms, const TensorMap& tmH, int axis, cplx* H, const cplx* twp, const cplx* tw, const cplx* twi,
+                                long long es, int hx,
                                 long long nother, long long other_stride, const double* Fh, long long esF, long long other_strideF, double s) {
   constexpr int B = p2_bundle(N);
   constexpr int STAGES = GSP_STRIDED_STAGES;
@@ -371,19 +374,20 @@ cudaError_t launch_p2_strided_f(cudaStream_t st, int sms, const TensorMap& tmH, 
   const int nbundles = (hx + B - 1) / B;
   const long long nunits = (long long)nbundles * nother;
   ProfScope prof_((FLAGS & P2_MUL) ? "fft_strided_fwd_mul_inv" : ((FLAGS & P2_FWD) ? "fft_strided_fwd" : "fft_strided_inv"), st);
-  GSP_LAUNCH(kfn, dim3(persistent_grid(kfn, C::THREADS, sms, C::SMEM, nunits)), dim3(C::THREADS), C::SMEM, st, tmH, axis, H, tw, twi, es, hx, nbundles, nunits,
+  GSP_LAUNCH(kfn, dim3(persistent_grid(kfn, C::THREADS, sms, C::SMEM, nunits)), dim3(C::THREADS), C::SMEM, st, tmH, axis, H, twp, tw, twi, es, hx, nbundles, nunits,
              other_stride, Fh, esF, other_strideF, s);
   g_launches++;
   return cudaGetLastError();
 }
 
 template <int N>
-cudaError_t launch_p2_strided(cudaStream_t st, int sms, int flags, const TensorMap& tmH, int axis, cplx* H, const cplx* tw, const cplx* twi, long long es,
+cudaError_t launch_p2_strided(cudaStream_t st, int sms, int flags, const TensorMap& tmH, int axis, cplx* H, const cplx* twp, const cplx* tw,
+                              const cplx* twi, long long es,
                               int hx, long long nother, long long other_stride, const double* Fh, long long esF, long long other_strideF,
                               double s) {
-  if (flags == P2_FWD) return launch_p2_strided_f<N, P2_FWD>(st, sms, tmH, axis, H, tw, twi, es, hx, nother, other_stride, Fh, esF, other_strideF, s);
-  if (flags == P2_INV) return launch_p2_strided_f<N, P2_INV>(st, sms, tmH, axis, H, tw, twi, es, hx, nother, other_stride, Fh, esF, other_strideF, s);
-  return launch_p2_strided_f<N, P2_FWD | P2_MUL | P2_INV>(st, sms, tmH, axis, H, tw, twi, es, hx, nother, other_stride, Fh, esF, other_strideF, s);
+  if (flags == P2_FWD) return launch_p2_strided_f<N, P2_FWD>(st, sms, tmH, axis, H, twp, tw, twi, es, hx, nother, other_stride, Fh, esF, other_strideF, s);
+  if (flags == P2_INV) return launch_p2_strided_f<N, P2_INV>(st, sms, tmH, axis, H, twp, tw, twi, es, hx, nother, other_stride, Fh, esF, other_strideF, s);
+  return launch_p2_strided_f<N, P2_FWD | P2_MUL | P2_INV>(st, sms, tmH, axis, H, twp, tw, twi, es, hx, nother, other_stride, Fh, esF, other_strideF, s);
 }
 
 template <int HN, int NY, bool INV>
@@ -510,9 +514,10 @@ int setup_axes(gsp_ctx* ctx, gsp_fft_plan* p, FftDev* d) {
   return GSP_OK;
 }
 
-cudaError_t run_xfwd(FftDev* d, gsp_fft_plan* p, const double* in, cplx* H) {
+// `batch` > 1 (1-D / 2-D grids only): that many realizations, stored back to back, go through ONE launch
+cudaError_t run_xfwd(FftDev* d, gsp_fft_plan* p, const double* in, cplx* H, long long batch = 1) {
   const AxisPlan& a = d->ax[0];
-  const long long nrows = p->dims[1] * p->dims[2];
+  const long long nrows = p->dims[1] * p->dims[2] * batch;
   if (a.fast) {
 #define GSP_CALL(HN) launch_p2_xfwd<HN>(d->dc->stream, d->dc->sms, in, H, a.lp.tw, d->stw_fwd.as<cplx>(), nrows)
     GSP_P2_SWITCH((int)p->dims[0] / 2, GSP_CALL)
@@ -528,9 +533,9 @@ cudaError_t run_xfwd(FftDev* d, gsp_fft_plan* p, const double* in, cplx* H) {
   return cudaGetLastError();
 }
 
-cudaError_t run_xinv(FftDev* d, gsp_fft_plan* p, const cplx* H, double* out, double scale, double mu) {
+cudaError_t run_xinv(FftDev* d, gsp_fft_plan* p, const cplx* H, double* out, double scale, double mu, long long batch = 1) {
   const AxisPlan& a = d->ax[0];
-  const long long nrows = p->dims[1] * p->dims[2];
+  const long long nrows = p->dims[1] * p->dims[2] * batch;
   if (a.fast) {
 #define GSP_CALL(HN) launch_p2_xinv<HN>(d->dc->stream, d->dc->sms, H, out, a.lp.tw, d->stw_inv.as<cplx>(), nrows, scale, mu)
     GSP_P2_SWITCH((int)p->dims[0] / 2, GSP_CALL)
@@ -546,7 +551,7 @@ cudaError_t run_xinv(FftDev* d, gsp_fft_plan* p, const cplx* H, double* out, dou
   return cudaGetLastError();
 }
 
-cudaError_t run_strided(FftDev* d, gsp_fft_plan* p, int axis, cplx* H, int flags, const double* Fh, double s) {
+cudaError_t run_strided(FftDev* d, gsp_fft_plan* p, int axis, cplx* H, int flags, const double* Fh, double s, long long batch = 1) {
   const AxisPlan& a = d->ax[axis];
   const long long hx = p->hx;
   long long es, other_stride, nother, esF, other_strideF;
@@ -557,6 +562,10 @@ cudaError_t run_strided(FftDev* d, gsp_fft_plan* p, int axis, cplx* H, int flags
     nother = p->dims[2];
     esF = hxF;
     other_strideF = hxF * p->dims[1];
+    if (p->ndim == 2) {  // the "other" index runs over the realizations of a batch; every realization sees the same F
+      nother = batch;
+      other_strideF = 0;
+    }
   } else {
     es = hx * p->dims[1];
     other_stride = hx;
@@ -566,7 +575,8 @@ cudaError_t run_strided(FftDev* d, gsp_fft_plan* p, int axis, cplx* H, int flags
   }
   if (a.fast) {
 #define GSP_CALL(NN) \
-  launch_p2_strided<NN>(d->dc->stream, d->dc->sms, flags, a.tmH, axis, H, d->stw_ax_fwd[axis].as<cplx>(), d->stw_ax_inv[axis].as<cplx>(), es, (int)hx, \
+  launch_p2_strided<NN>(d->dc->stream, d->dc->sms, flags, a.tmH, axis, H, a.lp.tw, d->stw_ax_fwd[axis].as<cplx>(), d->stw_ax_inv[axis].as<cplx>(), es, \
+                        (int)hx, \
                         nother, other_stride, Fh, esF, other_strideF, s)
     GSP_P2_SWITCH(a.len, GSP_CALL)
 #undef GSP_CALL
@@ -621,7 +631,7 @@ cudaError_t realization(FftDev* d, gsp_fft_plan* p, const double* w, double* out
   if (last == 0) {
     long long blocks = (p->nh + 255) / 256;
     if (blocks > (long long)d->dc->sms * 8) blocks = (long long)d->dc->sms * 8;
-    GSP_LAUNCH(spectral_mul_kernel, dim3((unsigned)blocks), dim3(256), 0, d->dc->stream, H, Fh, p->nh, s);
+    GSP_LAUNCH(spectral_mul_kernel, dim3((unsigned)blocks), dim3(256), 0, d->dc->stream, H, Fh, p->nh, p->nh, s);
     g_launches++;
     e = cudaGetLastError();
   } else {
@@ -633,19 +643,45 @@ cudaError_t realization(FftDev* d, gsp_fft_plan* p, const double* w, double* out
   return run_xinv(d, p, H, out, scale_out, mu);
 }
 
+// `nb` realizations at once (1-D / 2-D grids: one launch per pass for the whole batch; 3-D: one realization at a time)
+cudaError_t realization_batch(FftDev* d, gsp_fft_plan* p, const double* w, double* out, long long nb, double s, double scale_out, double mu) {
+  if (p->ndim == 3 || nb == 1) {
+    cudaError_t e = cudaSuccess;
+    for (long long r = 0; r < nb && e == cudaSuccess; ++r) e = realization(d, p, w + r * p->N, out + r * p->N, s, scale_out, mu);
+    return e;
+  }
+  cplx* H = d->H.as<cplx>();
+  const double* Fh = d->Fh.as<double>();
+  cudaError_t e = run_xfwd(d, p, w, H, nb);
+  if (e != cudaSuccess) return e;
+  if (p->ndim == 1) {
+    const long long total = p->nh * nb;
+    long long blocks = (total + 255) / 256;
+    if (blocks > (long long)d->dc->sms * 8) blocks = (long long)d->dc->sms * 8;
+    GSP_LAUNCH(spectral_mul_kernel, dim3((unsigned)blocks), dim3(256), 0, d->dc->stream, H, Fh, p->nh, total, s);
+    g_launches++;
+    e = cudaGetLastError();
+  } else {
+    e = run_strided(d, p, 1, H, PASS_FWD | PASS_MUL | PASS_INV, Fh, s, nb);
+  }
+  if (e != cudaSuccess) return e;
+  return run_xinv(d, p, H, out, scale_out, mu, nb);
+}
+
 int build_device(gsp_ctx* ctx, gsp_fft_plan* p, FftDev* d, const CovDev& cov, const DomDev& dom, long long eref) {
   cudaSetDevice(d->dc->dev);
   GSP_TRY(setup_axes(ctx, p, d));
   GSP_CUDA_OK(ctx, d->Fh.alloc(d->dc->dev, (size_t)p->nhF * sizeof(double)));
   GSP_CUDA_OK(ctx, cudaMemsetAsync(d->Fh.p, 0, (size_t)p->nhF * sizeof(double), d->dc->stream));
-  GSP_CUDA_OK(ctx, d->H.alloc(d->dc->dev, (size_t)p->nh * sizeof(cplx)));
+  GSP_CUDA_OK(ctx, d->H.alloc(d->dc->dev, (size_t)p->nh * p->rb * sizeof(cplx)));
   GSP_CUDA_OK(ctx, cudaEventCreate(&d->ev0));
   GSP_CUDA_OK(ctx, cudaEventCreate(&d->ev1));
   for (int axis = 1; axis < p->ndim; ++axis) {
     AxisPlan& a = d->ax[axis];
     if (!a.fast) continue;
     const unsigned B = (unsigned)p2_bundle(a.len);
-    const unsigned long long dH[3] = {2ull * p->hx, (unsigned long long)p->dims[1], (unsigned long long)p->dims[2]};
+    const unsigned long long dH[3] = {2ull * p->hx, (unsigned long long)p->dims[1],
+                                      (unsigned long long)(p->ndim == 2 ? p->rb : p->dims[2])};  // 2-D: 3rd extent = batch
     const unsigned long long dF[3] = {(unsigned long long)p->hxF, (unsigned long long)p->dims[1], (unsigned long long)p->dims[2]};
     const unsigned lbox = a.len < 256 ? (unsigned)a.len : 256u;
     const unsigned boxH[3] = {2 * B, axis == 1 ? lbox : 1u, axis == 2 ? lbox : 1u};
@@ -730,6 +766,17 @@ extern "C" int gsp_fft_plan_create(gsp_ctx* ctx, const gsp_cov_model* cov, const
   p->hxF = (p->hx + 1) & ~1;
   p->nh = (long long)p->hx * p->dims[1] * p->dims[2];
   p->nhF = (long long)p->hxF * p->dims[1] * p->dims[2];
+  if (p->ndim < 3) {
+    static long long batch_mb = -1;  // GSP_FFT_BATCH_MB: cap of a batch's work spectrum
+    if (batch_mb < 0) {
+      const char* env = getenv("GSP_FFT_BATCH_MB");
+      batch_mb = env ? atoll(env) : 1024;  // measured on B200 (1024^2 x 64): 24 MB 1.65 ms, 256 MB 1.09 ms, 1 GB 1.02 ms
+      if (batch_mb < 1) batch_mb = 1;
+    }
+    p->rb = (batch_mb << 20) / (p->nh * (long long)sizeof(cplx));
+    if (p->rb > 64) p->rb = 64;
+    if (p->rb < 1) p->rb = 1;
+  }
   for (auto& dc : ctx->devs) {
     std::unique_ptr<FftDev> d(new FftDev);
     d->dc = &dc;
@@ -785,27 +832,29 @@ int sample_on_device(gsp_fft_plan* p, FftDev* d, long long R, const double* w, u
                      DevBuf* scratch_z) {
   gsp_ctx* ctx = p->ctx;
   const double s = fold_scale(p, sill);
-  for (long long r = 0; r < R; ++r) {
+  const long long rb = p->rb;  // realizations per batch (1 for 3-D grids)
+  for (long long r = 0; r < R; r += rb) {
+    const long long nb = (R - r < rb) ? R - r : rb;
     const double* wr;
     if (w) {
       wr = w + r * p->N;
     } else {
-      if (!scratch_w->p) GSP_CUDA_OK(ctx, scratch_w->alloc(d->dc->dev, (size_t)p->N * sizeof(double)));
-      GSP_CUDA_OK(ctx, launch_rng_fill(d->dc->stream, d->dc->sms, scratch_w->as<double>(), p->N, p->N, 1, seed, 0,
+      if (!scratch_w->p) GSP_CUDA_OK(ctx, scratch_w->alloc(d->dc->dev, (size_t)p->N * rb * sizeof(double)));
+      GSP_CUDA_OK(ctx, launch_rng_fill(d->dc->stream, d->dc->sms, scratch_w->as<double>(), p->N, p->N, nb, seed, 0,
                                        (unsigned long long)(first_real + r), false));
       wr = scratch_w->as<double>();
     }
     if (n_inds > 0) {
-      if (!scratch_z->p) GSP_CUDA_OK(ctx, scratch_z->alloc(d->dc->dev, (size_t)p->N * sizeof(double)));
-      GSP_CUDA_OK(ctx, realization(d, p, wr, scratch_z->as<double>(), s, 1.0, mu));
-      long long blocks = (n_inds + 255) / 256;
+      if (!scratch_z->p) GSP_CUDA_OK(ctx, scratch_z->alloc(d->dc->dev, (size_t)p->N * rb * sizeof(double)));
+      GSP_CUDA_OK(ctx, realization_batch(d, p, wr, scratch_z->as<double>(), nb, s, 1.0, mu));
+      long long blocks = (n_inds * nb + 255) / 256;
       if (blocks > (long long)d->dc->sms * 8) blocks = (long long)d->dc->sms * 8;
       GSP_LAUNCH(gather_kernel, dim3((unsigned)blocks), dim3(256), 0, d->dc->stream, scratch_z->as<double>(), p->N, inds_dev, n_inds,
-                 1LL, out + r * n_inds);
+                 nb, out + r * n_inds);
       g_launches++;
       GSP_CUDA_OK(ctx, cudaGetLastError());
     } else {
-      GSP_CUDA_OK(ctx, realization(d, p, wr, out + r * p->N, s, 1.0, mu));
+      GSP_CUDA_OK(ctx, realization_batch(d, p, wr, out + r * p->N, nb, s, 1.0, mu));
     }
   }
   return GSP_OK;
@@ -865,9 +914,9 @@ extern "C" int gsp_fft_sample(gsp_fft_plan* p, int64_t R, const double* w, uint6
       GSP_CUDA_OK(ctx, cudaMemcpyAsync(d->inds.p, inds, (size_t)n_inds * sizeof(long long), cudaMemcpyHostToDevice, d->dc->stream));
     }
     for (int k = 0; k < 2; ++k) {
-      if (w && !d->win[k].p) GSP_CUDA_OK(ctx, d->win[k].alloc(d->dc->dev, (size_t)p->N * sizeof(double)));
-      if (!d->zout[k].p || d->zout[k].bytes < (size_t)nout * sizeof(double))
-        GSP_CUDA_OK(ctx, d->zout[k].alloc(d->dc->dev, (size_t)nout * sizeof(double)));
+      if (w && !d->win[k].p) GSP_CUDA_OK(ctx, d->win[k].alloc(d->dc->dev, (size_t)p->N * p->rb * sizeof(double)));
+      if (!d->zout[k].p || d->zout[k].bytes < (size_t)nout * p->rb * sizeof(double))
+        GSP_CUDA_OK(ctx, d->zout[k].alloc(d->dc->dev, (size_t)nout * p->rb * sizeof(double)));
     }
   }
   // software pipeline per device: H2D(r+1) | compute(r) | D2H(r-1) on three streams, double-buffered
@@ -893,31 +942,35 @@ extern "C" int gsp_fft_sample(gsp_fft_plan* p, int64_t R, const double* w, uint6
     cudaSetDevice(d0->dc->dev);
     cudaEventRecord(d0->ev0, d0->dc->stream);
   }
-  for (long long step = 0; step < maxshard && rc == GSP_OK; ++step) {
+  // one pipeline step = one chunk of up to p->rb realizations (1 for 3-D grids, a batch for 1-D / 2-D grids)
+  const long long rb = p->rb;
+  const long long nsteps = (maxshard + rb - 1) / rb;
+  for (long long step = 0; step < nsteps && rc == GSP_OK; ++step) {
     for (int i = 0; i < ndev && rc == GSP_OK; ++i) {
       const long long nloc = r0[i + 1] - r0[i];
-      if (step >= nloc) continue;
+      if (step * rb >= nloc) continue;
       FftDev* d = p->dev[i].get();
       cudaSetDevice(d->dc->dev);
       const int k = (int)(step & 1);
-      const long long r = r0[i] + step;
+      const long long r = r0[i] + step * rb;
+      const long long nbk = (nloc - step * rb < rb) ? nloc - step * rb : rb;
       const double* wdev = nullptr;
       if (w) {
         if (step >= 2) cudaStreamWaitEvent(d->dc->h2d, evs[i].in_free[k], 0);
-        cudaError_t e = cudaMemcpyAsync(d->win[k].p, w + r * p->N, (size_t)p->N * sizeof(double), cudaMemcpyHostToDevice, d->dc->h2d);
+        cudaError_t e = cudaMemcpyAsync(d->win[k].p, w + r * p->N, (size_t)p->N * nbk * sizeof(double), cudaMemcpyHostToDevice, d->dc->h2d);
         if (e != cudaSuccess) { rc = set_err(ctx, GSP_E_CUDA, cudaGetErrorString(e)); break; }
         cudaEventRecord(evs[i].in_ready[k], d->dc->h2d);
         cudaStreamWaitEvent(d->dc->stream, evs[i].in_ready[k], 0);
         wdev = d->win[k].as<double>();
       }
       if (step >= 2) cudaStreamWaitEvent(d->dc->stream, evs[i].drained[k], 0);
-      rc = sample_on_device(p, d, 1, wdev, seed, first_real + r, sill, mu, n_inds, d->inds.as<long long>(), d->zout[k].as<double>(),
+      rc = sample_on_device(p, d, nbk, wdev, seed, first_real + r, sill, mu, n_inds, d->inds.as<long long>(), d->zout[k].as<double>(),
                             &sw[i], &sz[i]);
       if (rc != GSP_OK) break;
       cudaEventRecord(evs[i].done[k], d->dc->stream);
       if (w) cudaEventRecord(evs[i].in_free[k], d->dc->stream);
       cudaStreamWaitEvent(d->dc->d2h, evs[i].done[k], 0);
-      cudaError_t e = cudaMemcpyAsync(out + r * nout, d->zout[k].p, (size_t)nout * sizeof(double), cudaMemcpyDeviceToHost, d->dc->d2h);
+      cudaError_t e = cudaMemcpyAsync(out + r * nout, d->zout[k].p, (size_t)nout * nbk * sizeof(double), cudaMemcpyDeviceToHost, d->dc->d2h);
       if (e != cudaSuccess) { rc = set_err(ctx, GSP_E_CUDA, cudaGetErrorString(e)); break; }
       cudaEventRecord(evs[i].drained[k], d->dc->d2h);
     }

@@ -166,7 +166,9 @@ struct StridedCfg {
   static constexpr size_t IN_BYTES = (size_t)N * B * sizeof(cplx);
   static constexpr size_t F_BYTES = 0;  // F goes global -> registers (issued before the forward transform): keeps 3 CTAs per SM
   static constexpr int STWF = p2_stw_size(N, false), STWI = p2_stw_size(N, true);  // per-stage twiddle tables
-  static constexpr size_t TW_BYTES = ((size_t)(STWF + STWI) * sizeof(cplx) + 127) / 128 * 128;
+  // long lines: the per-stage tables would not fit next to the data -> plain strided table exp(-2*pi*i*t/N) instead
+  static constexpr bool STW_OK = (size_t)(STWF + STWI) * sizeof(cplx) <= 40 * 1024;
+  static constexpr size_t TW_BYTES = ((size_t)(STW_OK ? STWF + STWI : N) * sizeof(cplx) + 127) / 128 * 128;
   static constexpr size_t SMEM = TW_BYTES + STAGES * (IN_BYTES + F_BYTES) + 2 * sizeof(mbar_t) + 16;
   static constexpr int MINB = (STAGES == 1 && THREADS <= 128) ? 4 : 1;  // register cap for 4 CTAs per SM
 };
@@ -174,8 +176,8 @@ struct StridedCfg {
 template <int N, int B, int FLAGS, int STAGES>
 __global__ void __launch_bounds__(StridedCfg<N, B, FLAGS, STAGES>::THREADS, StridedCfg<N, B, FLAGS, STAGES>::MINB)
     p2_strided_kernel(const GSP_GRID_CONSTANT TensorMap tmH, int line_axis,
-                                                                                     cplx* __restrict__ H, const cplx* __restrict__ stwfg,
-                                                                                     const cplx* __restrict__ stwig,
+                                                                                     cplx* __restrict__ H, const cplx* __restrict__ twg,
+                                                                                     const cplx* __restrict__ stwfg, const cplx* __restrict__ stwig,
                                                                                      long long es, int hx, int nbundles, long long nunits,
                                                                                      long long other_stride, const double* __restrict__ Fh,
                                                                                      long long esF, long long other_strideF, double s) {
@@ -183,8 +185,9 @@ __global__ void __launch_bounds__(StridedCfg<N, B, FLAGS, STAGES>::THREADS, Stri
   constexpr int SL = C::SL, TPU = C::THREADS;
   constexpr bool MUL = C::MUL;
   GSP_DYN_SMEM(smem);
-  cplx* stwf = reinterpret_cast<cplx*>(smem);  // per-stage twiddles, forward radix order
-  cplx* stwi = stwf + C::STWF;                 // ... inverse radix order
+  constexpr int TWS = C::STW_OK ? 0 : 1;
+  cplx* stwf = reinterpret_cast<cplx*>(smem);                   // per-stage twiddles, forward radix order (or the plain table)
+  cplx* stwi = C::STW_OK ? stwf + C::STWF : stwf;               // ... inverse radix order
   unsigned char* stage0 = smem + C::TW_BYTES;
   mbar_t* full = reinterpret_cast<mbar_t*>(stage0 + STAGES * (C::IN_BYTES + C::F_BYTES));
   const int tid = threadIdx.x;
@@ -194,10 +197,14 @@ __global__ void __launch_bounds__(StridedCfg<N, B, FLAGS, STAGES>::THREADS, Stri
     mbar_init(&full[1], 1);
     fence_mbar_init();
   }
-  if ((FLAGS & P2_FWD) != 0)
-    for (int i = tid; i < C::STWF; i += TPU) stwf[i] = stwfg[i];
-  if ((FLAGS & P2_INV) != 0)
-    for (int i = tid; i < C::STWI; i += TPU) stwi[i] = stwig[i];
+  if constexpr (C::STW_OK) {
+    if ((FLAGS & P2_FWD) != 0)
+      for (int i = tid; i < C::STWF; i += TPU) stwf[i] = stwfg[i];
+    if ((FLAGS & P2_INV) != 0)
+      for (int i = tid; i < C::STWI; i += TPU) stwi[i] = stwig[i];
+  } else {
+    for (int i = tid; i < N; i += TPU) stwf[i] = twg[i];
+  }
   __syncthreads();
 
   auto stage_in = [&](int sg) { return reinterpret_cast<cplx*>(stage0 + (size_t)sg * (C::IN_BYTES + C::F_BYTES)); };
@@ -252,7 +259,7 @@ __global__ void __launch_bounds__(StridedCfg<N, B, FLAGS, STAGES>::THREADS, Stri
     for (int q = 0; q < SL / R0; ++q)
 #pragma unroll
       for (int r = 0; r < R0; ++r) v[q * R0 + r] = buf[lay(p2_in_pos<N, FIRST_INV, 0>(t, q, r))];
-    if constexpr ((FLAGS & P2_FWD) != 0) p2_fft<N, false, 0>(v, t, buf, lay, stwf);
+    if constexpr ((FLAGS & P2_FWD) != 0) p2_fft<N, false, TWS>(v, t, buf, lay, stwf);
     if constexpr (MUL) {
       // slot (q, r) holds frequency f = p2_in_pos<N, true, 0>(t, q, r): P = s*F*W/|W|, angle(0) = 0 (fftsim.jl:125)
       constexpr int RI = p2_radix(N, true, 0);
@@ -271,7 +278,7 @@ __global__ void __launch_bounds__(StridedCfg<N, B, FLAGS, STAGES>::THREADS, Stri
           }
         }
     }
-    if constexpr ((FLAGS & P2_INV) != 0) p2_fft<N, true, 0>(v, t, buf, lay, stwi);
+    if constexpr ((FLAGS & P2_INV) != 0) p2_fft<N, true, TWS>(v, t, buf, lay, stwi);
     constexpr bool LAST_INV = (FLAGS & P2_INV) != 0;
     constexpr int RO = p2_radix(N, !LAST_INV, 0);
     if (valid) {
@@ -294,7 +301,7 @@ __global__ void __launch_bounds__(StridedCfg<N, B, FLAGS, STAGES>::THREADS, Stri
 #endif
 template <int HN, bool INV>
 struct XCfg {
-  static constexpr int STAGES = GSP_X_STAGES;  // 2: prefetch the next row group; 1: no prefetch, more resident CTAs
+  static constexpr int STAGES = HN >= 4096 ? 1 : GSP_X_STAGES;  // 2: prefetch the next row group; 1: no prefetch (also: nx = 8192 only fits once)
   static constexpr int NX = 2 * HN, HX = HN + 1;
   static constexpr int SL = p2_slots(HN);
   static constexpr int TPL = HN / SL;                       // threads per row
@@ -306,7 +313,8 @@ struct XCfg {
   static constexpr size_t EX_BYTES = (size_t)ROWS * ROWLEN * sizeof(cplx);
   // the exchange buffer overlays the (already consumed) input stage: 2 stages + twiddles = 74.5 KB at nx = 256 -> 3 CTAs per SM
   static constexpr size_t STAGE_BYTES = ((IN_BYTES > EX_BYTES ? IN_BYTES : EX_BYTES) + 127) / 128 * 128;
-  static constexpr int STW = p2_stw_size(HN, INV);  // per-stage twiddle entries (conflict-free layout)
+  static constexpr bool STW_OK = (size_t)p2_stw_size(HN, INV) * sizeof(cplx) <= 24 * 1024;
+  static constexpr int STW = STW_OK ? p2_stw_size(HN, INV) : 0;  // per-stage twiddle entries (conflict-free layout); 0: use tw with stride 2
   static constexpr size_t TW_BYTES = ((size_t)(NX + STW) * sizeof(cplx) + 127) / 128 * 128;
   static constexpr size_t SMEM = TW_BYTES + STAGES * STAGE_BYTES + 2 * sizeof(mbar_t) + 16;
   static constexpr int MINB = (STAGES == 1 && THREADS <= 128) ? 4 : 1;
@@ -365,7 +373,7 @@ __global__ void __launch_bounds__(XCfg<HN, false>::THREADS, XCfg<HN, false>::MIN
     for (int q = 0; q < SL / R0; ++q)
 #pragma unroll
       for (int r = 0; r < R0; ++r) v[q * R0 + r] = src[p2_in_pos<HN, false, 0>(t, q, r)];
-    p2_fft<HN, false, 0>(v, t, ex, lay, stw);
+    p2_fft<HN, false, C::STW_OK ? 0 : 2>(v, t, ex, lay, C::STW_OK ? stw : tw);
     // untangle: X[f] = E + w^f * O with E = (Z[f] + conj Z[h-f])/2, O = -i (Z[f] - conj Z[h-f])/2
     constexpr int RI = p2_radix(HN, true, 0);
     __syncthreads();
@@ -457,7 +465,7 @@ __global__ void __launch_bounds__(XCfg<HN, true>::THREADS, XCfg<HN, true>::MINB)
         const cplx tt = cmul(cconj(tw[m]), d);
         v[q * R0 + r] = cplx{sm.re - tt.im, sm.im + tt.re};
       }
-    p2_fft<HN, true, 0>(v, t, ex, lay, stw);
+    p2_fft<HN, true, C::STW_OK ? 0 : 2>(v, t, ex, lay, C::STW_OK ? stw : tw);
     constexpr int RO = p2_radix(HN, false, 0);
     if (valid) {
       double* dst = out + row * NX;

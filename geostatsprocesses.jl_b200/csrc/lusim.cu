@@ -209,8 +209,10 @@ extern "C" int gsp_lu_plan_create(gsp_ctx* ctx, const gsp_cov_model* cov, const 
 
   // ---- which devices build: one (factor there, copy L to the others) or all (multi-GPU block-cyclic factorization)
   const int ndev = (int)ctx->devs.size();
-  static int mg_min_blocks = -1, mg_pb_env = 0;
+  static int mg_min_blocks = -1, mg_pb_env = 0, mg_force = 0;
   if (mg_min_blocks < 0) {
+    const char* e3 = getenv("GSP_CHOL_MG_FORCE");  // use the panel algorithm even on one device (A/B against the recursive one)
+    mg_force = (e3 && e3[0] == '1') ? 1 : 0;
     const char* e1 = getenv("GSP_CHOL_MG_MIN_BLOCKS");
     const char* e2 = getenv("GSP_CHOL_MG_PB");
     mg_min_blocks = e1 ? atoi(e1) : 64;  // below ~8k nodes the panel chain dominates: replicate instead
@@ -219,7 +221,7 @@ extern "C" int gsp_lu_plan_create(gsp_ctx* ctx, const gsp_cov_model* cov, const 
   const int nb = (int)(p->Np / 128);
   // panel width in 128-blocks (measured on 2 B200: N = 33k: PB 4 -> 298 ms, PB 8 -> 251 ms; N = 16.5k: 49 ms vs 51 ms)
   const int mg_pb = mg_pb_env > 0 ? mg_pb_env : (nb >= 192 ? 8 : 4);
-  const bool mg = ndev > 1 && nb >= mg_min_blocks;
+  const bool mg = (ndev > 1 || mg_force) && nb >= mg_min_blocks;
   const int nbuild = mg ? ndev : 1;
 
   auto build_one = [&](LuDev* d, bool with_matrix) -> int {

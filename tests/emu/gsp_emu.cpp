@@ -86,6 +86,10 @@ void warp_exchange(uint64_t v, uint64_t out[32]) {
 // Plain launches use nblk = 1 (blocks one after the other); launch_coop runs the whole grid at once, which is
 // what persistent kernels with inter-CTA dependencies (spin-waits on global flags) need.
 static void run_blocks(State& st, dim3 grid, dim3 block, size_t smem, unsigned first, unsigned nblk) {
+  if (smem > 227 * 1024 || block.x * block.y * block.z > 1024) {
+    std::fprintf(stderr, "gsp_emu: launch exceeds the sm_100a limits (dynamic smem %zu bytes, %u threads)\n", smem, block.x * block.y * block.z);
+    std::abort();
+  }
   const int tpb = (int)(block.x * block.y * block.z);
   const int nwarp = (tpb + 31) / 32;
   st.nthreads = tpb * (int)nblk;

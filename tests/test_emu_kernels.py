@@ -263,3 +263,25 @@ def test_multi_device_block_cyclic_cholesky(emu_lib):
     env = dict(os.environ, GSP_CHOL_MG_MIN_BLOCKS="2", GSP_CHOL_MG_PB="1")
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=900)
     assert out.returncode == 0 and "OK" in out.stdout, out.stderr[-1500:]
+
+
+def test_fftsim_batched_realizations(emu_lib):
+    """1-D / 2-D grids push whole batches of realizations through one launch per pass (batch capacity 64 here)."""
+    rng = np.random.default_rng(21)
+    for dims, R in (((32, 16), 70), ((64,), 5), ((20, 12), 67)):
+        nd = len(dims)
+        st = iso(O.SPHERICAL, 1.3, 3.0, nd)
+        plan = gsp.FFTPlan(emu_lib, st, dims, [0.0] * nd, [1.0] * nd)
+        Fo = O.fftsim_preprocess(ostructs(st), dims, [0.0] * nd, [1.0] * nd)
+        N = int(np.prod(dims))
+        w = rng.random((R, N))
+        Z = plan.sample(R, w, sill=1.3, mu=-0.4)
+        for r in (0, 1, R // 2, R - 1):
+            assert relerr(Z[r], O.fftsim_sample(Fo, w[r], 1.3, -0.4)) < TOL, (dims, r)
+        inds1 = np.arange(1, N, 3)
+        Zs = plan.sample(R, w, sill=1.3, mu=-0.4, inds1=inds1)
+        assert np.array_equal(Zs, Z[:, inds1 - 1])
+        a = plan.sample(R, None, seed=4)
+        b = np.concatenate([plan.sample(3, None, seed=4), plan.sample(R - 3, None, seed=4, first_real=3)])
+        assert np.array_equal(a, b)
+        plan.close()

@@ -279,8 +279,30 @@ struct AxisPlan {
   TensorMap tmH, tmF; // strided fast passes: TMA tiles of the work spectrum / of F along this axis
 };
 
+// One realization in flight: its own stream and half-spectrum work buffer (3-D grids run several lanes concurrently so that
+// the small slab kernels of different realizations fill each other's launch gaps and tails).  Lane 0 = the compute stream + d->H.
+struct Lane {
+  cudaStream_t st = nullptr;
+  bool own_stream = false;
+  DevBuf Hbuf;
+  cplx* H = nullptr;
+  TensorMap tmH[3];
+  cudaEvent_t done = nullptr;
+};
+
+// sub-range of a strided pass: bundles [bx0, bx0 + nb) (nb == 0: all) for the indices [o0, o1) of the remaining axis (o1 == 0: all)
+struct Sub {
+  int bx0 = 0, nb = 0;
+  long long o0 = 0, o1 = 0;
+};
+
 struct FftDev {
   DevCtx* dc = nullptr;
+  std::vector<std::unique_ptr<Lane>> lanes;
+  cudaEvent_t ev_fork = nullptr;
+  int slab_mode = 0;     // 0: full-grid passes; 1: z-plane slabs for the x/y pairs; 2: kx-bundle groups for y fwd / z / y inv
+  int slab_planes = 32;  // mode 1
+  int slab_bundles = 4;  // mode 2
   DevBuf tw[3];
   DevBuf stw_fwd, stw_inv;  // x axis: per-stage twiddle tables of the length-nx/2 transform (forward / inverse radix order)
   DevBuf stw_ax_fwd[3], stw_ax_inv[3];  // strided axes: the same for the full-length transforms
@@ -322,12 +344,30 @@ const size_t kMaxSmem = 200 * 1024;
 #endif
 bool g_force_generic = false;  // GSP_FFT_GENERIC=1: use the mixed-radix kernels for every extent (A/B checks)
 
-// persistent grid: as many CTAs as are resident per SM (occupancy API, at most 4), never more than there are items
-template <class K>
-inline unsigned persistent_grid(K kfn, int threads, int sms, size_t smem, long long items) {
-  int per_sm = 1;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, threads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
-  if (per_sm > 4) per_sm = 4;
+// Per-kernel launch setup, done once per device: opt in to the dynamic shared memory and ask the occupancy API how many CTAs
+// are resident per SM (at most 4 are used).  Both calls cost microseconds of host time, which the slab schedules (dozens of
+// short launches per realization) cannot afford per launch.  SLOT is a distinct static per kernel instantiation.
+struct KernelSetup {
+  int per_sm[32] = {};
+  cudaError_t err = cudaSuccess;
+  template <class K>
+  int get(K kfn, int threads, size_t smem) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 31;
+    if (per_sm[dev] == 0) {
+      err = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (err != cudaSuccess) return 0;
+      int n = 1;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kfn, threads, smem) != cudaSuccess || n < 1) n = 1;
+      per_sm[dev] = n > 4 ? 4 : n;
+    }
+    return per_sm[dev];
+  }
+};
+
+// persistent grid: as many CTAs as are resident per SM, never more than there are items
+inline unsigned persistent_grid(int per_sm, int sms, long long items) {
   long long g = (long long)per_sm * sms;
   if (g > items) g = items;
   if (g < 1) g = 1;
@@ -338,11 +378,12 @@ template <int HN>
 cudaError_t launch_p2_xfwd(cudaStream_t st, int sms, const double* in, cplx* H, const cplx* tw, const cplx* stw, long long nrows) {
   using C = XCfg<HN, false>;
   auto kfn = p2_xfwd_kernel<HN>;
-  cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-  if (e != cudaSuccess) return e;
+  static KernelSetup ks;
+  const int per_sm = ks.get(kfn, C::THREADS, C::SMEM);
+  if (per_sm == 0) return ks.err;
   const long long ngroups = (nrows + C::ROWS - 1) / C::ROWS;
   ProfScope prof_("fft_xpass_fwd", st);
-  GSP_LAUNCH(kfn, dim3(persistent_grid(kfn, C::THREADS, sms, C::SMEM, ngroups)), dim3(C::THREADS), C::SMEM, st, in, H, tw, stw, nrows);
+  GSP_LAUNCH(kfn, dim3(persistent_grid(per_sm, sms, ngroups)), dim3(C::THREADS), C::SMEM, st, in, H, tw, stw, nrows);
   g_launches++;
   return cudaGetLastError();
 }
@@ -352,11 +393,12 @@ cudaError_t launch_p2_xinv(cudaStream_t st, int sms, const cplx* H, double* out,
                            double mu) {
   using C = XCfg<HN, true>;
   auto kfn = p2_xinv_kernel<HN>;
-  cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-  if (e != cudaSuccess) return e;
+  static KernelSetup ks;
+  const int per_sm = ks.get(kfn, C::THREADS, C::SMEM);
+  if (per_sm == 0) return ks.err;
   const long long ngroups = (nrows + C::ROWS - 1) / C::ROWS;
   ProfScope prof_("fft_xpass_inv", st);
-  GSP_LAUNCH(kfn, dim3(persistent_grid(kfn, C::THREADS, sms, C::SMEM, ngroups)), dim3(C::THREADS), C::SMEM, st, H, out, tw, stw, nrows, scale, mu);
+  GSP_LAUNCH(kfn, dim3(persistent_grid(per_sm, sms, ngroups)), dim3(C::THREADS), C::SMEM, st, H, out, tw, stw, nrows, scale, mu);
   g_launches++;
   return cudaGetLastError();
 }
@@ -364,18 +406,24 @@ cudaError_t launch_p2_xinv(cudaStream_t st, int sms, const cplx* H, double* out,
 template <int N, int FLAGS>
 cudaError_t launch_p2_strided_f(cudaStream_t st, int sms, const TensorMap& tmH, int axis, cplx* H, const cplx* twp, const cplx* tw, const cplx* twi,
                                 long long es, int hx,
-                                long long nother, long long other_stride, const double* Fh, long long esF, long long other_strideF, double s) {
+                                long long nother, long long other_stride, const double* Fh, long long esF, long long other_strideF, double s,
+                                const Sub& sub) {
   constexpr int B = p2_bundle(N);
   constexpr int STAGES = GSP_STRIDED_STAGES;
   using C = StridedCfg<N, B, FLAGS, STAGES>;
   auto kfn = p2_strided_kernel<N, B, FLAGS, STAGES>;
-  cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-  if (e != cudaSuccess) return e;
-  const int nbundles = (hx + B - 1) / B;
-  const long long nunits = (long long)nbundles * nother;
+  static KernelSetup ks;
+  const int per_sm = ks.get(kfn, C::THREADS, C::SMEM);
+  if (per_sm == 0) return ks.err;
+  const int nball = (hx + B - 1) / B;
+  int bx0 = sub.bx0, nbundles = sub.nb > 0 ? sub.nb : nball;
+  if (bx0 + nbundles > nball) nbundles = nball - bx0;
+  const long long o0 = sub.o0, o1 = sub.o1 > 0 ? sub.o1 : nother;
+  if (nbundles <= 0 || o1 <= o0) return cudaSuccess;
+  const long long ubeg = o0 * nbundles, uend = o1 * nbundles;
   ProfScope prof_((FLAGS & P2_MUL) ? "fft_strided_fwd_mul_inv" : ((FLAGS & P2_FWD) ? "fft_strided_fwd" : "fft_strided_inv"), st);
-  GSP_LAUNCH(kfn, dim3(persistent_grid(kfn, C::THREADS, sms, C::SMEM, nunits)), dim3(C::THREADS), C::SMEM, st, tmH, axis, H, twp, tw, twi, es, hx, nbundles, nunits,
-             other_stride, Fh, esF, other_strideF, s);
+  GSP_LAUNCH(kfn, dim3(persistent_grid(per_sm, sms, uend - ubeg)), dim3(C::THREADS), C::SMEM, st, tmH, axis, H, twp, tw, twi, es, hx, nbundles, uend,
+             other_stride, Fh, esF, other_strideF, s, bx0, ubeg);
   g_launches++;
   return cudaGetLastError();
 }
@@ -384,10 +432,10 @@ template <int N>
 cudaError_t launch_p2_strided(cudaStream_t st, int sms, int flags, const TensorMap& tmH, int axis, cplx* H, const cplx* twp, const cplx* tw,
                               const cplx* twi, long long es,
                               int hx, long long nother, long long other_stride, const double* Fh, long long esF, long long other_strideF,
-                              double s) {
-  if (flags == P2_FWD) return launch_p2_strided_f<N, P2_FWD>(st, sms, tmH, axis, H, twp, tw, twi, es, hx, nother, other_stride, Fh, esF, other_strideF, s);
-  if (flags == P2_INV) return launch_p2_strided_f<N, P2_INV>(st, sms, tmH, axis, H, twp, tw, twi, es, hx, nother, other_stride, Fh, esF, other_strideF, s);
-  return launch_p2_strided_f<N, P2_FWD | P2_MUL | P2_INV>(st, sms, tmH, axis, H, twp, tw, twi, es, hx, nother, other_stride, Fh, esF, other_strideF, s);
+                              double s, const Sub& sub) {
+  if (flags == P2_FWD) return launch_p2_strided_f<N, P2_FWD>(st, sms, tmH, axis, H, twp, tw, twi, es, hx, nother, other_stride, Fh, esF, other_strideF, s, sub);
+  if (flags == P2_INV) return launch_p2_strided_f<N, P2_INV>(st, sms, tmH, axis, H, twp, tw, twi, es, hx, nother, other_stride, Fh, esF, other_strideF, s, sub);
+  return launch_p2_strided_f<N, P2_FWD | P2_MUL | P2_INV>(st, sms, tmH, axis, H, twp, tw, twi, es, hx, nother, other_stride, Fh, esF, other_strideF, s, sub);
 }
 
 template <int HN, int NY, bool INV>
@@ -514,45 +562,49 @@ int setup_axes(gsp_ctx* ctx, gsp_fft_plan* p, FftDev* d) {
   return GSP_OK;
 }
 
-// `batch` > 1 (1-D / 2-D grids only): that many realizations, stored back to back, go through ONE launch
-cudaError_t run_xfwd(FftDev* d, gsp_fft_plan* p, const double* in, cplx* H, long long batch = 1) {
+// x passes over the rows [row0, row0 + nrows) of the lane's work spectrum (`in` / `out` point at the first of those rows).
+// 1-D / 2-D grids: a batch of realizations, stored back to back, is simply more rows of ONE launch.
+cudaError_t run_xfwd(FftDev* d, gsp_fft_plan* p, const Lane& L, const double* in, long long row0, long long nrows) {
   const AxisPlan& a = d->ax[0];
-  const long long nrows = p->dims[1] * p->dims[2] * batch;
+  cplx* H = L.H + row0 * p->hx;
   if (a.fast) {
-#define GSP_CALL(HN) launch_p2_xfwd<HN>(d->dc->stream, d->dc->sms, in, H, a.lp.tw, d->stw_fwd.as<cplx>(), nrows)
+#define GSP_CALL(HN) launch_p2_xfwd<HN>(L.st, d->dc->sms, in, H, a.lp.tw, d->stw_fwd.as<cplx>(), nrows)
     GSP_P2_SWITCH((int)p->dims[0] / 2, GSP_CALL)
 #undef GSP_CALL
   }
   auto kfn = xpass_fwd_kernel;
   cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.smem);
   if (e != cudaSuccess) return e;
-  ProfScope prof_("fft_xpass_fwd", d->dc->stream);
-  GSP_LAUNCH(kfn, dim3((unsigned)((nrows + a.B - 1) / a.B)), dim3(256), a.smem, d->dc->stream, a.lp, (int)p->dims[0], p->hx, nrows,
+  ProfScope prof_("fft_xpass_fwd", L.st);
+  GSP_LAUNCH(kfn, dim3((unsigned)((nrows + a.B - 1) / a.B)), dim3(256), a.smem, L.st, a.lp, (int)p->dims[0], p->hx, nrows,
              a.B, a.packed, in, H);
   g_launches++;
   return cudaGetLastError();
 }
 
-cudaError_t run_xinv(FftDev* d, gsp_fft_plan* p, const cplx* H, double* out, double scale, double mu, long long batch = 1) {
+cudaError_t run_xinv(FftDev* d, gsp_fft_plan* p, const Lane& L, double* out, long long row0, long long nrows, double scale, double mu) {
   const AxisPlan& a = d->ax[0];
-  const long long nrows = p->dims[1] * p->dims[2] * batch;
+  const cplx* H = L.H + row0 * p->hx;
   if (a.fast) {
-#define GSP_CALL(HN) launch_p2_xinv<HN>(d->dc->stream, d->dc->sms, H, out, a.lp.tw, d->stw_inv.as<cplx>(), nrows, scale, mu)
+#define GSP_CALL(HN) launch_p2_xinv<HN>(L.st, d->dc->sms, H, out, a.lp.tw, d->stw_inv.as<cplx>(), nrows, scale, mu)
     GSP_P2_SWITCH((int)p->dims[0] / 2, GSP_CALL)
 #undef GSP_CALL
   }
   auto kfn = xpass_inv_kernel;
   cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.smem);
   if (e != cudaSuccess) return e;
-  ProfScope prof_("fft_xpass_inv", d->dc->stream);
-  GSP_LAUNCH(kfn, dim3((unsigned)((nrows + a.B - 1) / a.B)), dim3(256), a.smem, d->dc->stream, a.lp, (int)p->dims[0], p->hx, nrows,
+  ProfScope prof_("fft_xpass_inv", L.st);
+  GSP_LAUNCH(kfn, dim3((unsigned)((nrows + a.B - 1) / a.B)), dim3(256), a.smem, L.st, a.lp, (int)p->dims[0], p->hx, nrows,
              a.B, a.packed, H, out, scale, mu);
   g_launches++;
   return cudaGetLastError();
 }
 
-cudaError_t run_strided(FftDev* d, gsp_fft_plan* p, int axis, cplx* H, int flags, const double* Fh, double s, long long batch = 1) {
+// `sub` (fast kernels only) restricts the pass to a slab; the generic kernels always run the whole grid
+cudaError_t run_strided(FftDev* d, gsp_fft_plan* p, const Lane& L, int axis, int flags, const double* Fh, double s, long long batch = 1,
+                        const Sub& sub = Sub()) {
   const AxisPlan& a = d->ax[axis];
+  cplx* H = L.H;
   const long long hx = p->hx;
   long long es, other_stride, nother, esF, other_strideF;
   const long long hxF = p->hxF;
@@ -575,9 +627,9 @@ cudaError_t run_strided(FftDev* d, gsp_fft_plan* p, int axis, cplx* H, int flags
   }
   if (a.fast) {
 #define GSP_CALL(NN) \
-  launch_p2_strided<NN>(d->dc->stream, d->dc->sms, flags, a.tmH, axis, H, a.lp.tw, d->stw_ax_fwd[axis].as<cplx>(), d->stw_ax_inv[axis].as<cplx>(), es, \
+  launch_p2_strided<NN>(L.st, d->dc->sms, flags, L.tmH[axis], axis, H, a.lp.tw, d->stw_ax_fwd[axis].as<cplx>(), d->stw_ax_inv[axis].as<cplx>(), es, \
                         (int)hx, \
-                        nother, other_stride, Fh, esF, other_strideF, s)
+                        nother, other_stride, Fh, esF, other_strideF, s, sub)
     GSP_P2_SWITCH(a.len, GSP_CALL)
 #undef GSP_CALL
   }
@@ -586,8 +638,8 @@ cudaError_t run_strided(FftDev* d, gsp_fft_plan* p, int axis, cplx* H, int flags
   if (e != cudaSuccess) return e;
   dim3 grid((unsigned)((hx + a.B - 1) / a.B), (unsigned)nother);
   ProfScope prof_((flags & PASS_MUL) ? "fft_strided_fwd_mul_inv" : ((flags & PASS_FWD) ? "fft_strided_fwd" : "fft_strided_inv"),
-                  d->dc->stream);
-  GSP_LAUNCH(kfn, grid, dim3(256), a.smem, d->dc->stream, a.lp, H, es, (int)hx, a.B, other_stride, flags, Fh, esF, other_strideF, s);
+                  L.st);
+  GSP_LAUNCH(kfn, grid, dim3(256), a.smem, L.st, a.lp, H, es, (int)hx, a.B, other_stride, flags, Fh, esF, other_strideF, s);
   g_launches++;
   return cudaGetLastError();
 }
@@ -604,68 +656,119 @@ cudaError_t run_plane_inv(FftDev* d, gsp_fft_plan* p, double* out, double scale,
 
 // forward transform of a real field into d->H (all axes)
 cudaError_t forward_all(FftDev* d, gsp_fft_plan* p, const double* in) {
+  const Lane& L = *d->lanes[0];
   if (d->fused_xy) {
     cudaError_t e = run_plane_fwd(d, p, in);
-    if (e == cudaSuccess) e = run_strided(d, p, 2, d->H.as<cplx>(), PASS_FWD, nullptr, 0.0);
+    if (e == cudaSuccess) e = run_strided(d, p, L, 2, PASS_FWD, nullptr, 0.0);
     return e;
   }
-  cudaError_t e = run_xfwd(d, p, in, d->H.as<cplx>());
-  for (int axis = 1; axis < p->ndim && e == cudaSuccess; ++axis) e = run_strided(d, p, axis, d->H.as<cplx>(), PASS_FWD, nullptr, 0.0);
+  cudaError_t e = run_xfwd(d, p, L, in, 0, p->dims[1] * p->dims[2]);
+  for (int axis = 1; axis < p->ndim && e == cudaSuccess; ++axis) e = run_strided(d, p, L, axis, PASS_FWD, nullptr, 0.0);
   return e;
 }
 
-// one realization: real noise (device) -> real field (device), full grid
-cudaError_t realization(FftDev* d, gsp_fft_plan* p, const double* w, double* out, double s, double scale_out, double mu) {
-  cplx* H = d->H.as<cplx>();
+// one realization on one lane: real noise (device) -> real field (device), full grid
+cudaError_t realization(FftDev* d, gsp_fft_plan* p, const Lane& L, const double* w, double* out, double s, double scale_out, double mu) {
   const double* Fh = d->Fh.as<double>();
+  const long long nrows = p->dims[1] * p->dims[2];
   if (d->fused_xy) {
     // 3 kernels per realization: (x+y forward) -> (z forward, spectral multiply, z inverse) -> (y+x inverse)
     cudaError_t e = run_plane_fwd(d, p, w);
-    if (e == cudaSuccess) e = run_strided(d, p, 2, H, PASS_FWD | PASS_MUL | PASS_INV, Fh, s);
+    if (e == cudaSuccess) e = run_strided(d, p, L, 2, PASS_FWD | PASS_MUL | PASS_INV, Fh, s);
     if (e == cudaSuccess) e = run_plane_inv(d, p, out, scale_out, mu);
     return e;
   }
-  cudaError_t e = run_xfwd(d, p, w, H);
+  cudaError_t e = cudaSuccess;
+  if (p->ndim == 3 && d->slab_mode == 1) {
+    // z-plane slabs: the x pass of a slab leaves its half-spectrum rows in L2, the y pass of the same slab picks them up
+    // there and overwrites them in place -> the x/y intermediate never makes a round trip through HBM (52 N instead of 84 N bytes)
+    const long long nz = p->dims[2], ny = p->dims[1], zs = d->slab_planes;
+    for (long long z0 = 0; z0 < nz && e == cudaSuccess; z0 += zs) {
+      const long long z1 = z0 + zs < nz ? z0 + zs : nz;
+      Sub sub;
+      sub.o0 = z0;
+      sub.o1 = z1;
+      e = run_xfwd(d, p, L, w + z0 * ny * p->dims[0], z0 * ny, (z1 - z0) * ny);
+      if (e == cudaSuccess) e = run_strided(d, p, L, 1, PASS_FWD, nullptr, 0.0, 1, sub);
+    }
+    if (e == cudaSuccess) e = run_strided(d, p, L, 2, PASS_FWD | PASS_MUL | PASS_INV, Fh, s);
+    for (long long z0 = 0; z0 < nz && e == cudaSuccess; z0 += zs) {
+      const long long z1 = z0 + zs < nz ? z0 + zs : nz;
+      Sub sub;
+      sub.o0 = z0;
+      sub.o1 = z1;
+      e = run_strided(d, p, L, 1, PASS_INV, nullptr, 0.0, 1, sub);
+      if (e == cudaSuccess) e = run_xinv(d, p, L, out + z0 * ny * p->dims[0], z0 * ny, (z1 - z0) * ny, scale_out, mu);
+    }
+    return e;
+  }
+  e = run_xfwd(d, p, L, w, 0, nrows);
   if (e != cudaSuccess) return e;
   const int last = p->ndim - 1;
   if (last == 0) {
     long long blocks = (p->nh + 255) / 256;
     if (blocks > (long long)d->dc->sms * 8) blocks = (long long)d->dc->sms * 8;
-    GSP_LAUNCH(spectral_mul_kernel, dim3((unsigned)blocks), dim3(256), 0, d->dc->stream, H, Fh, p->nh, p->nh, s);
+    GSP_LAUNCH(spectral_mul_kernel, dim3((unsigned)blocks), dim3(256), 0, L.st, L.H, Fh, p->nh, p->nh, s);
     g_launches++;
     e = cudaGetLastError();
+  } else if (p->ndim == 3 && d->slab_mode == 2) {
+    // kx-bundle groups: y forward, z (forward, multiply, inverse) and y inverse of one group of bundles back to back;
+    // the group's slab (group x ny x nz) stays in L2 between the three kernels
+    const int B = p2_bundle(d->ax[1].len);
+    const int nball = (p->hx + B - 1) / B;
+    for (int bx0 = 0; bx0 < nball && e == cudaSuccess; bx0 += d->slab_bundles) {
+      Sub sub;
+      sub.bx0 = bx0;
+      sub.nb = d->slab_bundles;
+      e = run_strided(d, p, L, 1, PASS_FWD, nullptr, 0.0, 1, sub);
+      if (e == cudaSuccess) e = run_strided(d, p, L, 2, PASS_FWD | PASS_MUL | PASS_INV, Fh, s, 1, sub);
+      if (e == cudaSuccess) e = run_strided(d, p, L, 1, PASS_INV, nullptr, 0.0, 1, sub);
+    }
   } else {
-    for (int axis = 1; axis < last && e == cudaSuccess; ++axis) e = run_strided(d, p, axis, H, PASS_FWD, nullptr, 0.0);
-    if (e == cudaSuccess) e = run_strided(d, p, last, H, PASS_FWD | PASS_MUL | PASS_INV, Fh, s);
-    for (int axis = last - 1; axis >= 1 && e == cudaSuccess; --axis) e = run_strided(d, p, axis, H, PASS_INV, nullptr, 0.0);
+    for (int axis = 1; axis < last && e == cudaSuccess; ++axis) e = run_strided(d, p, L, axis, PASS_FWD, nullptr, 0.0);
+    if (e == cudaSuccess) e = run_strided(d, p, L, last, PASS_FWD | PASS_MUL | PASS_INV, Fh, s);
+    for (int axis = last - 1; axis >= 1 && e == cudaSuccess; --axis) e = run_strided(d, p, L, axis, PASS_INV, nullptr, 0.0);
   }
   if (e != cudaSuccess) return e;
-  return run_xinv(d, p, H, out, scale_out, mu);
+  return run_xinv(d, p, L, out, 0, nrows, scale_out, mu);
 }
 
-// `nb` realizations at once (1-D / 2-D grids: one launch per pass for the whole batch; 3-D: one realization at a time)
+// `nb` realizations at once (1-D / 2-D grids: one launch per pass for the whole batch; 3-D: one realization per lane, the lanes
+// run concurrently and join the compute stream at the end)
 cudaError_t realization_batch(FftDev* d, gsp_fft_plan* p, const double* w, double* out, long long nb, double s, double scale_out, double mu) {
+  const Lane& L0 = *d->lanes[0];
   if (p->ndim == 3 || nb == 1) {
+    const long long nl = (long long)d->lanes.size() < nb ? (long long)d->lanes.size() : nb;
     cudaError_t e = cudaSuccess;
-    for (long long r = 0; r < nb && e == cudaSuccess; ++r) e = realization(d, p, w + r * p->N, out + r * p->N, s, scale_out, mu);
+    if (nl > 1) {
+      e = cudaEventRecord(d->ev_fork, L0.st);
+      for (long long l = 1; l < nl && e == cudaSuccess; ++l) e = cudaStreamWaitEvent(d->lanes[l]->st, d->ev_fork, 0);
+    }
+    for (long long r = 0; r < nb && e == cudaSuccess; ++r)
+      e = realization(d, p, *d->lanes[r % nl], w + r * p->N, out + r * p->N, s, scale_out, mu);
+    for (long long l = 1; l < nl; ++l) {  // always join, also after an error: nothing may outlive the call on a side stream
+      cudaError_t e2 = cudaEventRecord(d->lanes[l]->done, d->lanes[l]->st);
+      if (e2 == cudaSuccess) e2 = cudaStreamWaitEvent(L0.st, d->lanes[l]->done, 0);
+      if (e == cudaSuccess) e = e2;
+    }
     return e;
   }
-  cplx* H = d->H.as<cplx>();
   const double* Fh = d->Fh.as<double>();
-  cudaError_t e = run_xfwd(d, p, w, H, nb);
+  const long long nrows = p->dims[1] * p->dims[2] * nb;
+  cudaError_t e = run_xfwd(d, p, L0, w, 0, nrows);
   if (e != cudaSuccess) return e;
   if (p->ndim == 1) {
     const long long total = p->nh * nb;
     long long blocks = (total + 255) / 256;
     if (blocks > (long long)d->dc->sms * 8) blocks = (long long)d->dc->sms * 8;
-    GSP_LAUNCH(spectral_mul_kernel, dim3((unsigned)blocks), dim3(256), 0, d->dc->stream, H, Fh, p->nh, total, s);
+    GSP_LAUNCH(spectral_mul_kernel, dim3((unsigned)blocks), dim3(256), 0, L0.st, L0.H, Fh, p->nh, total, s);
     g_launches++;
     e = cudaGetLastError();
   } else {
-    e = run_strided(d, p, 1, H, PASS_FWD | PASS_MUL | PASS_INV, Fh, s, nb);
+    e = run_strided(d, p, L0, 1, PASS_FWD | PASS_MUL | PASS_INV, Fh, s, nb);
   }
   if (e != cudaSuccess) return e;
-  return run_xinv(d, p, H, out, scale_out, mu, nb);
+  return run_xinv(d, p, L0, out, 0, nrows, scale_out, mu);
 }
 
 int build_device(gsp_ctx* ctx, gsp_fft_plan* p, FftDev* d, const CovDev& cov, const DomDev& dom, long long eref) {
@@ -673,9 +776,41 @@ int build_device(gsp_ctx* ctx, gsp_fft_plan* p, FftDev* d, const CovDev& cov, co
   GSP_TRY(setup_axes(ctx, p, d));
   GSP_CUDA_OK(ctx, d->Fh.alloc(d->dc->dev, (size_t)p->nhF * sizeof(double)));
   GSP_CUDA_OK(ctx, cudaMemsetAsync(d->Fh.p, 0, (size_t)p->nhF * sizeof(double), d->dc->stream));
-  GSP_CUDA_OK(ctx, d->H.alloc(d->dc->dev, (size_t)p->nh * p->rb * sizeof(cplx)));
+  GSP_CUDA_OK(ctx, d->H.alloc(d->dc->dev, (size_t)p->nh * (p->ndim == 3 ? 1 : p->rb) * sizeof(cplx)));
   GSP_CUDA_OK(ctx, cudaEventCreate(&d->ev0));
   GSP_CUDA_OK(ctx, cudaEventCreate(&d->ev1));
+  GSP_CUDA_OK(ctx, cudaEventCreateWithFlags(&d->ev_fork, cudaEventDisableTiming));
+  // Lanes and slabs (3-D grids on the register-resident kernels only).  Defaults measured on B200 at 256^3; GSP_FFT_LANES,
+  // GSP_FFT_SLAB (0 | 1 | 2), GSP_FFT_SLAB_PLANES and GSP_FFT_SLAB_BUNDLES override them for A/B runs.
+  int nlanes = 1;
+  const bool all_fast = p->ndim == 3 && d->ax[0].fast && d->ax[1].fast && d->ax[2].fast;
+  if (all_fast) {
+    auto env_int = [](const char* name, int dflt) {
+      const char* v = getenv(name);
+      return v && v[0] ? atoi(v) : dflt;
+    };
+    nlanes = (int)p->rb;  // 3-D: realizations per chunk = concurrent lanes (gsp_fft_plan_create)
+    d->slab_mode = env_int("GSP_FFT_SLAB", 0);
+    if (d->slab_mode < 0 || d->slab_mode > 2) d->slab_mode = 0;
+    d->slab_planes = env_int("GSP_FFT_SLAB_PLANES", 32);
+    if (d->slab_planes < 1) d->slab_planes = 1;
+    d->slab_bundles = env_int("GSP_FFT_SLAB_BUNDLES", 4);
+    if (d->slab_bundles < 1) d->slab_bundles = 1;
+  }
+  for (int l = 0; l < nlanes; ++l) {
+    std::unique_ptr<Lane> L(new Lane);
+    if (l == 0) {
+      L->st = d->dc->stream;
+      L->H = d->H.as<cplx>();
+    } else {
+      GSP_CUDA_OK(ctx, cudaStreamCreateWithFlags(&L->st, cudaStreamNonBlocking));
+      L->own_stream = true;
+      GSP_CUDA_OK(ctx, L->Hbuf.alloc(d->dc->dev, (size_t)p->nh * sizeof(cplx)));
+      L->H = L->Hbuf.as<cplx>();
+      GSP_CUDA_OK(ctx, cudaEventCreateWithFlags(&L->done, cudaEventDisableTiming));
+    }
+    d->lanes.push_back(std::move(L));
+  }
   for (int axis = 1; axis < p->ndim; ++axis) {
     AxisPlan& a = d->ax[axis];
     if (!a.fast) continue;
@@ -686,7 +821,12 @@ int build_device(gsp_ctx* ctx, gsp_fft_plan* p, FftDev* d, const CovDev& cov, co
     const unsigned lbox = a.len < 256 ? (unsigned)a.len : 256u;
     const unsigned boxH[3] = {2 * B, axis == 1 ? lbox : 1u, axis == 2 ? lbox : 1u};
     const unsigned boxF[3] = {B, boxH[1], boxH[2]};
-    int r1 = make_tensor_map_f64(&a.tmH, d->H.p, dH, 16ull * p->hx, 16ull * p->hx * p->dims[1], boxH);
+    int r1 = 0;
+    for (auto& L : d->lanes) {
+      const int r = make_tensor_map_f64(&L->tmH[axis], L->H, dH, 16ull * p->hx, 16ull * p->hx * p->dims[1], boxH);
+      if (r != 0) r1 = r;
+    }
+    a.tmH = d->lanes[0]->tmH[axis];
     int r2 = make_tensor_map_f64(&a.tmF, d->Fh.p, dF, 8ull * p->hxF, 8ull * p->hxF * p->dims[1], boxF);
     if (r1 != 0 || r2 != 0) return set_err(ctx, GSP_E_CUDA, "cuTensorMapEncodeTiled failed for an FFT pass (code " + std::to_string(r1 ? r1 : r2) + ")");
   }
@@ -697,7 +837,7 @@ int build_device(gsp_ctx* ctx, gsp_fft_plan* p, FftDev* d, const CovDev& cov, co
     const char* env = getenv("GSP_FFT_FUSE");
     const bool allow = env && env[0] == '1';
     d->fused_xy = allow && p->ndim == 3 && d->ax[0].fast && d->ax[1].fast && d->ax[2].fast &&
-                  plane_supported((int)p->dims[0] / 2, (int)p->dims[1]);
+                  plane_supported((int)p->dims[0] / 2, (int)p->dims[1]) && d->lanes.size() == 1 && d->slab_mode == 0;
     GSP_CUDA_OK(ctx, d->cnt.alloc(d->dc->dev, (size_t)(2 * p->dims[2] + 2) * sizeof(int)));
     GSP_CUDA_OK(ctx, cudaMemsetAsync(d->cnt.p, 0, (size_t)(2 * p->dims[2] + 2) * sizeof(int), d->dc->stream));
   }
@@ -777,6 +917,17 @@ extern "C" int gsp_fft_plan_create(gsp_ctx* ctx, const gsp_cov_model* cov, const
     if (p->rb > 64) p->rb = 64;
     if (p->rb < 1) p->rb = 1;
   }
+  if (p->ndim == 3) {
+    // 3-D: a chunk = one realization per lane (concurrent streams with their own work spectrum); only the register-resident
+    // power-of-two kernels are worth it, everything else keeps one lane
+    bool fast = !g_force_generic && p->dims[0] % 2 == 0 && p2_supported((int)p->dims[0] / 2);
+    for (int a = 1; a < 3; ++a) fast = fast && p2_supported((int)p->dims[a]);
+    const char* env = getenv("GSP_FFT_LANES");
+    long long lanes = env && env[0] ? atoll(env) : 4;  // measured on B200 at 256^3: 1 lane 281 us, 2 lanes 258 us, 4 lanes 252 us per realization
+    if (lanes < 1) lanes = 1;
+    if (lanes > 8) lanes = 8;
+    p->rb = fast ? lanes : 1;
+  }
   for (auto& dc : ctx->devs) {
     std::unique_ptr<FftDev> d(new FftDev);
     d->dc = &dc;
@@ -794,6 +945,14 @@ extern "C" int gsp_fft_plan_destroy(gsp_fft_plan* p) {
     cudaStreamSynchronize(d->dc->stream);
     if (d->ev0) cudaEventDestroy(d->ev0);
     if (d->ev1) cudaEventDestroy(d->ev1);
+    if (d->ev_fork) cudaEventDestroy(d->ev_fork);
+    for (auto& L : d->lanes) {
+      if (L->own_stream) {
+        cudaStreamSynchronize(L->st);
+        cudaStreamDestroy(L->st);
+      }
+      if (L->done) cudaEventDestroy(L->done);
+    }
   }
   delete p;
   return GSP_OK;
@@ -899,6 +1058,9 @@ extern "C" int gsp_fft_sample(gsp_fft_plan* p, int64_t R, const double* w, uint6
       if (inds[q] < 1 || inds[q] > p->N) return set_err(ctx, -9, "inds out of range (1-based parent indices)");
   const long long nout = n_inds > 0 ? n_inds : p->N;
   const int ndev = (int)p->dev.size();
+  // host pipeline granularity: 3-D grids move one realization (8 N bytes each way) per step - PCIe is the bound there and a
+  // finer grain overlaps better; 1-D / 2-D grids move a batch
+  const long long hrb = p->ndim == 3 ? 1 : p->rb;
   // contiguous shards of realizations per device (the reference shards over worker processes, field.jl:103-121)
   std::vector<long long> r0(ndev + 1, 0);
   for (int i = 0; i < ndev; ++i) r0[i + 1] = r0[i] + (R / ndev) + (i < R % ndev ? 1 : 0);
@@ -914,9 +1076,9 @@ extern "C" int gsp_fft_sample(gsp_fft_plan* p, int64_t R, const double* w, uint6
       GSP_CUDA_OK(ctx, cudaMemcpyAsync(d->inds.p, inds, (size_t)n_inds * sizeof(long long), cudaMemcpyHostToDevice, d->dc->stream));
     }
     for (int k = 0; k < 2; ++k) {
-      if (w && !d->win[k].p) GSP_CUDA_OK(ctx, d->win[k].alloc(d->dc->dev, (size_t)p->N * p->rb * sizeof(double)));
-      if (!d->zout[k].p || d->zout[k].bytes < (size_t)nout * p->rb * sizeof(double))
-        GSP_CUDA_OK(ctx, d->zout[k].alloc(d->dc->dev, (size_t)nout * p->rb * sizeof(double)));
+      if (w && !d->win[k].p) GSP_CUDA_OK(ctx, d->win[k].alloc(d->dc->dev, (size_t)p->N * hrb * sizeof(double)));
+      if (!d->zout[k].p || d->zout[k].bytes < (size_t)nout * hrb * sizeof(double))
+        GSP_CUDA_OK(ctx, d->zout[k].alloc(d->dc->dev, (size_t)nout * hrb * sizeof(double)));
     }
   }
   // software pipeline per device: H2D(r+1) | compute(r) | D2H(r-1) on three streams, double-buffered
@@ -942,8 +1104,8 @@ extern "C" int gsp_fft_sample(gsp_fft_plan* p, int64_t R, const double* w, uint6
     cudaSetDevice(d0->dc->dev);
     cudaEventRecord(d0->ev0, d0->dc->stream);
   }
-  // one pipeline step = one chunk of up to p->rb realizations (1 for 3-D grids, a batch for 1-D / 2-D grids)
-  const long long rb = p->rb;
+  // one pipeline step = one chunk of up to hrb realizations (1 for 3-D grids, a batch for 1-D / 2-D grids)
+  const long long rb = hrb;
   const long long nsteps = (maxshard + rb - 1) / rb;
   for (long long step = 0; step < nsteps && rc == GSP_OK; ++step) {
     for (int i = 0; i < ndev && rc == GSP_OK; ++i) {

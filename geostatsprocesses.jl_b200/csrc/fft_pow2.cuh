@@ -180,7 +180,10 @@ __global__ void __launch_bounds__(StridedCfg<N, B, FLAGS, STAGES>::THREADS, Stri
                                                                                      const cplx* __restrict__ stwfg, const cplx* __restrict__ stwig,
                                                                                      long long es, int hx, int nbundles, long long nunits,
                                                                                      long long other_stride, const double* __restrict__ Fh,
-                                                                                     long long esF, long long other_strideF, double s) {
+                                                                                     long long esF, long long other_strideF, double s, int bx0,
+                                                                                     long long ubeg) {
+  // work units [ubeg, nunits): unit = o * nbundles + (bx - bx0), i.e. `nbundles` kx bundles starting at bundle bx0 for every
+  // index o along the remaining axis.  Sub-ranges (slabs of planes or groups of kx bundles) keep a slab resident in L2.
   using C = StridedCfg<N, B, FLAGS, STAGES>;
   constexpr int SL = C::SL, TPU = C::THREADS;
   constexpr bool MUL = C::MUL;
@@ -215,7 +218,7 @@ __global__ void __launch_bounds__(StridedCfg<N, B, FLAGS, STAGES>::THREADS, Stri
       // iteration ordered those accesses before this thread, the proxy fence orders them before the async-proxy fill
       fence_proxy_async();
       const long long o = unit / nbundles;
-      const int bx = (int)(unit - o * nbundles);
+      const int bx = bx0 + (int)(unit - o * nbundles);
       const int c1 = line_axis == 1 ? 0 : (int)o, c2 = line_axis == 1 ? (int)o : 0;
       mbar_arrive_expect_tx(&full[sg], (uint32_t)(C::IN_BYTES + C::F_BYTES));
       constexpr int LBOX = N < 256 ? N : 256;  // TMA boxes are limited to 256 elements per dimension
@@ -226,7 +229,7 @@ __global__ void __launch_bounds__(StridedCfg<N, B, FLAGS, STAGES>::THREADS, Stri
     }
   };
 
-  long long unit = blockIdx.x;
+  long long unit = ubeg + blockIdx.x;
   if (STAGES == 2 && unit < nunits) issue(unit, 0);
   for (int it = 0; unit < nunits; unit += gridDim.x, ++it) {
     const int cur = STAGES == 2 ? (it & 1) : 0;
@@ -236,7 +239,7 @@ __global__ void __launch_bounds__(StridedCfg<N, B, FLAGS, STAGES>::THREADS, Stri
       issue(unit, 0);
     }
     const long long o = unit / nbundles;
-    const int bx = (int)(unit - o * nbundles);
+    const int bx = bx0 + (int)(unit - o * nbundles);
     const bool valid = bx * B + b < hx;
     const long long base = o * other_stride + (long long)bx * B + b;
     cplx* buf = stage_in(cur);
@@ -249,7 +252,7 @@ __global__ void __launch_bounds__(StridedCfg<N, B, FLAGS, STAGES>::THREADS, Stri
 #pragma unroll
       for (int q = 0; q < SL / RI; ++q)
 #pragma unroll
-        for (int r = 0; r < RI; ++r) fv[q * RI + r] = valid ? __ldg(fp + (long long)p2_in_pos<N, true, 0>(t, q, r) * esF) : 0.0;
+        for (int r = 0; r < RI; ++r) fv[q * RI + r] = valid ? ld_keep(fp + (long long)p2_in_pos<N, true, 0>(t, q, r) * esF) : 0.0;
     }
     mbar_wait(&full[cur], (uint32_t)(STAGES == 2 ? ((it >> 1) & 1) : (it & 1)));
     constexpr bool FIRST_INV = (FLAGS & P2_FWD) == 0;
@@ -317,7 +320,10 @@ struct XCfg {
   static constexpr int STW = STW_OK ? p2_stw_size(HN, INV) : 0;  // per-stage twiddle entries (conflict-free layout); 0: use tw with stride 2
   static constexpr size_t TW_BYTES = ((size_t)(NX + STW) * sizeof(cplx) + 127) / 128 * 128;
   static constexpr size_t SMEM = TW_BYTES + STAGES * STAGE_BYTES + 2 * sizeof(mbar_t) + 16;
-  static constexpr int MINB = (STAGES == 1 && THREADS <= 128) ? 4 : 1;
+#ifndef GSP_X_MINB2
+#define GSP_X_MINB2 1  // CTAs per SM the register allocation of the 2-stage x kernels must allow
+#endif
+  static constexpr int MINB = (STAGES == 1 && THREADS <= 128) ? 4 : ((THREADS <= 128) ? GSP_X_MINB2 : 1);
 };
 
 template <int HN>

@@ -200,6 +200,27 @@ def test_fftsim_fused_plane_kernels(emu_lib, monkeypatch):
         plan.close()
 
 
+@pytest.mark.parametrize("mode,lanes,planes,bundles", [(1, 1, 4, 4), (1, 3, 5, 4), (2, 2, 4, 2), (2, 1, 4, 1), (0, 3, 4, 4)])
+def test_fftsim_slabs_and_lanes(emu_lib, monkeypatch, mode, lanes, planes, bundles):
+    """3-D schedules: z-plane slabs (x/y pairs through L2), kx-bundle groups (y/z/y through L2), concurrent lanes."""
+    monkeypatch.setenv("GSP_FFT_SLAB", str(mode))
+    monkeypatch.setenv("GSP_FFT_LANES", str(lanes))
+    monkeypatch.setenv("GSP_FFT_SLAB_PLANES", str(planes))
+    monkeypatch.setenv("GSP_FFT_SLAB_BUNDLES", str(bundles))
+    rng = np.random.default_rng(13)
+    dims = (64, 16, 16)
+    st = iso(O.SPHERICAL, 1.2, 5.0, 3)
+    plan = gsp.FFTPlan(emu_lib, st, dims, [0.0] * 3, [1.0] * 3)
+    Fo = O.fftsim_preprocess(ostructs(st), dims, [0.0] * 3, [1.0] * 3)
+    assert relerr(plan.spectrum(), Fo) < 1e-12
+    R = 4
+    w = rng.random((R, int(np.prod(dims))))
+    Z = plan.sample(R, w, sill=1.2, mu=-0.4)
+    for r in range(R):
+        assert relerr(Z[r], O.fftsim_sample(Fo, w[r], 1.2, -0.4)) < TOL
+    plan.close()
+
+
 def test_plan_times_and_profile(emu_lib):
     st = iso(O.SPHERICAL, 1.0, 4.0, 2)
     emu_lib.profile_enable(True)

@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(StridedCfg<N, B, FLAGS, STAGES>::THREADS, Stri
 #pragma unroll
       for (int q = 0; q < SL / RI; ++q)
 #pragma unroll
-        for (int r = 0; r < RI; ++r) fv[q * RI + r] = valid ? ld_keep(fp + (long long)p2_in_pos<N, true, 0>(t, q, r) * esF) : 0.0;
+        for (int r = 0; r < RI; ++r) fv[q * RI + r] = valid ? __ldg(fp + (long long)p2_in_pos<N, true, 0>(t, q, r) * esF) : 0.0;
     }
     mbar_wait(&full[cur], (uint32_t)(STAGES == 2 ? ((it >> 1) & 1) : (it & 1)));
     constexpr bool FIRST_INV = (FLAGS & P2_FWD) == 0;

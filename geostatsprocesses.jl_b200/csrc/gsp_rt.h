@@ -203,20 +203,6 @@ GSP_DEV double2 ld_stream2(const double* p) {
   return v;
 #endif
 }
-// read-only 8-byte load that asks L2 to keep the line (evict-last): data re-read by every realization (the spectrum F, 4 N
-// bytes <= L2) while the work spectrum streams through with the default policy
-GSP_DEV double ld_keep(const double* p) {
-#ifdef GSP_EMU
-  return *p;
-#else
-  double v;
-  asm volatile(
-      "{ .reg .b64 pol; createpolicy.fractional.L2::evict_last.b64 pol, 1.0; ld.global.nc.L2::cache_hint.f64 %0, [%1], pol; }"
-      : "=d"(v)
-      : "l"(p));
-  return v;
-#endif
-}
 GSP_DEV void st_stream2(double* p, double2 v) {
 #ifdef GSP_EMU
   p[0] = v.x;

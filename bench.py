@@ -287,6 +287,11 @@ def run_gpu(args):
     e2e_value = Re * world * e2e_steps / float(te[0])
     e2e_match = bool(torch.equal(hz[0], z[0].cpu()))
 
+    # ---- resident ensemble + statistics in HBM: what a user who wants mean / variance / quantile maps pays
+    ens_line = None
+    if rank == 0 and not args.skip_ensemble:
+        ens_line = bench_ensemble(lib, plan, Rg, N, r0)
+
     # ---- LUSIM 16k nodes (configs[2]) on rank 0's GPU, reported beside the headline
     lus = None
     if rank == 0 and not args.skip_lusim:
@@ -348,10 +353,53 @@ def run_gpu(args):
                                               f"(scipy.fft workers={os.cpu_count()}); Julia is absent so the restatement stands in for the reference CPU path"}
         if lus is not None:
             line["lusim"] = lus
+        if ens_line is not None:
+            line["ensemble_statistics"] = ens_line
         emit(line)
     plan.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def bench_ensemble(lib, plan, R, N, r0):
+    """R realizations (device RNG) simulated into a device-resident ensemble, then mean, variance, cdf and three quantile maps:
+    only the n-vectors of results cross PCIe (ensembles.jl:42-52 run in HBM instead of O(n R) host loops)."""
+    import torch
+
+    def timed(fn):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out = fn()
+        torch.cuda.synchronize()
+        return out, time.perf_counter() - t0
+
+    plan.sample_ensemble(4, None, seed=4, first_real=r0).close()  # warm-up
+    ens, t_sim = timed(lambda: plan.sample_ensemble(R, None, seed=4, first_real=r0))
+    ens.mean()  # warm-up of the statistics kernels
+    lib.profile_enable(True)
+    mean, t_mean = timed(ens.mean)
+    var, t_var = timed(ens.var)
+    cdf, t_cdf = timed(lambda: ens.cdf(0.0))
+    q, t_q = timed(lambda: ens.quantile([0.1, 0.5, 0.9]))
+    prof = lib.profile_read()
+    lib.profile_enable(False)
+    ens.close()
+    pk = peaks()
+    bytes_pass = 8.0 * N * R
+    out = {"workload": f"{R} FFTSIM 256^3 realizations (on-device Philox noise) resident in HBM; mean, var, cdf(0), quantile([.1,.5,.9]) per node",
+           "simulate_s": t_sim, "realizations_per_s_simulate_resident": R / t_sim,
+           "mean_s": t_mean, "var_s": t_var, "cdf_s": t_cdf, "quantile3_s": t_q,
+           "realizations_per_s_simulate_plus_mean_var": R / (t_sim + t_mean + t_var),
+           "d2h_bytes_per_statistic": 8 * N, "d2h_bytes_if_realizations_were_downloaded": 8 * N * R,
+           "kernel_ms": {k: round(v["ms"] / v["launches"], 3) for k, v in prof.items()},
+           "checks": {"mean_abs_max": float(np.abs(mean).max()), "var_mean": float(var.mean()), "cdf0_mean": float(cdf.mean()),
+                      "median_abs_mean": float(np.abs(q[1]).mean())}}
+    for k in ("ens_moments", "ens_count"):
+        if k in prof:
+            gbs = bytes_pass / (prof[k]["ms"] / prof[k]["launches"]) / 1e6
+            out[k + "_GBps"] = gbs
+            out[k + "_frac_of_hbm_peak"] = gbs / pk["hbm_gbs"]
+    return out
 
 
 def plan_nh(dims):
@@ -419,6 +467,7 @@ def main():
     ap.add_argument("--cpu-reals", type=int, default=4)
     ap.add_argument("--skip-lusim", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-ensemble", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -75,6 +75,19 @@ SIGNATURES = {
     "gsp_fft_plan_get": (C.c_int, [_vp, _vp]),
     "gsp_fft_sample": (C.c_int, [_vp, C.c_int64, _vp, C.c_uint64, C.c_int64, C.c_double, C.c_double, C.c_int64, _vp, _vp]),
     "gsp_fft_sample_dev": (C.c_int, [_vp, C.c_int64, _vp, C.c_uint64, C.c_int64, C.c_double, C.c_double, C.c_int64, _vp, _vp]),
+    "gsp_ensemble_create": (C.c_int, [_vp, C.c_int64, C.c_int64, C.POINTER(_vp)]),
+    "gsp_ensemble_destroy": (C.c_int, [_vp]),
+    "gsp_ensemble_sizes": (C.c_int, [_vp, C.POINTER(C.c_int64 * 2)]),
+    "gsp_ensemble_put": (C.c_int, [_vp, C.c_int64, C.c_int64, _vp]),
+    "gsp_ensemble_fetch": (C.c_int, [_vp, C.c_int64, C.c_int64, _vp]),
+    "gsp_fft_sample_ensemble": (C.c_int, [_vp, _vp, _vp, C.c_uint64, C.c_int64, C.c_double, C.c_double, C.c_int64, _vp]),
+    "gsp_lu_sample_ensemble": (C.c_int, [_vp, _vp, _vp, C.c_uint64, C.c_int32, C.c_int64, C.c_double, _vp]),
+    "gsp_ensemble_mean": (C.c_int, [_vp, _vp]),
+    "gsp_ensemble_var": (C.c_int, [_vp, _vp]),
+    "gsp_ensemble_cdf": (C.c_int, [_vp, C.c_double, _vp]),
+    "gsp_ensemble_ccdf": (C.c_int, [_vp, C.c_double, _vp]),
+    "gsp_ensemble_quantile": (C.c_int, [_vp, C.c_int64, _vp, _vp]),
+    "gsp_ensemble_moments": (C.c_int, [_vp, _vp, _vp]),
     "gsp_profile_enable": (C.c_int, [_vp, C.c_int32]),
     "gsp_profile_read": (C.c_int64, [_vp, C.c_char_p, C.c_int64]),
     "gsp_kernel_launches": (C.c_int64, []),
@@ -248,6 +261,18 @@ class LUPlan:
         self.lib.check(rc)
         return Z
 
+    def sample_ensemble(self, R: int, W: Optional[np.ndarray] = None, seed: int = 0, stream: int = 0, first_real: int = 0,
+                        rho: float = math.nan, W1: Optional[np.ndarray] = None) -> "DeviceEnsemble":
+        """like `sample`, but the realizations stay on the devices"""
+        if W is not None:
+            W = np.asfortranarray(W, dtype=np.float64).reshape(self.Ns, R, order="F")
+        if W1 is not None:
+            W1 = np.asfortranarray(W1, dtype=np.float64).reshape(self.Ns, R, order="F")
+        ens = DeviceEnsemble(self.lib, self.N, R)
+        rc = self.lib.lib.gsp_lu_sample_ensemble(self.h, ens.h, _ptr(W), seed, stream, first_real, float(rho), _ptr(W1))
+        self.lib.check(rc)
+        return ens
+
     def sample_dev(self, R, W_ptr, ldw, seed, stream, first_real, rho, W1_ptr, Z_ptr, ldz):
         rc = self.lib.lib.gsp_lu_sample_dev(self.h, R, W_ptr, ldw, seed, stream, first_real, float(rho), W1_ptr, Z_ptr, ldz)
         self.lib.check(rc)
@@ -255,6 +280,68 @@ class LUPlan:
     def close(self):
         if getattr(self, "h", None):
             self.lib.lib.gsp_lu_plan_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DeviceEnsemble:
+    """R realizations of n values resident on the context's devices (gsp_ensemble_*): the `reals` + `fetch` of
+    Ensemble(domain, reals; fetch) (src/ensembles.jl:10-16) with the statistics of ensembles.jl:42-52 computed in HBM."""
+
+    def __init__(self, lib: Library, n: int, R: int):
+        self.lib, self.n, self.R = lib, int(n), int(R)
+        h = _vp()
+        lib.check(lib.lib.gsp_ensemble_create(lib.ctx, self.n, self.R, C.byref(h)))
+        self.h = h
+
+    def put(self, Z: np.ndarray, r0: int = 0):
+        """Z: (nr, n) C-order (row r = realization r0 + r)."""
+        Z = np.ascontiguousarray(Z, dtype=np.float64).reshape(-1, self.n)
+        self.lib.check(self.lib.lib.gsp_ensemble_put(self.h, r0, Z.shape[0], _ptr(Z)))
+
+    def fetch(self, r0: int = 0, nr: Optional[int] = None) -> np.ndarray:
+        nr = self.R - r0 if nr is None else nr
+        Z = np.empty((nr, self.n))
+        self.lib.check(self.lib.lib.gsp_ensemble_fetch(self.h, r0, nr, _ptr(Z)))
+        return Z
+
+    def _vec(self, fn, *args) -> np.ndarray:
+        out = np.empty(self.n)
+        self.lib.check(fn(self.h, *args, _ptr(out)))
+        return out
+
+    def mean(self) -> np.ndarray:
+        return self._vec(self.lib.lib.gsp_ensemble_mean)
+
+    def var(self) -> np.ndarray:
+        return self._vec(self.lib.lib.gsp_ensemble_var)
+
+    def cdf(self, x: float) -> np.ndarray:
+        return self._vec(self.lib.lib.gsp_ensemble_cdf, float(x))
+
+    def ccdf(self, x: float) -> np.ndarray:
+        return self._vec(self.lib.lib.gsp_ensemble_ccdf, float(x))
+
+    def quantile(self, ps) -> np.ndarray:
+        """ps: sequence of probabilities -> (len(ps), n)."""
+        ps = np.ascontiguousarray(np.atleast_1d(ps), dtype=np.float64)
+        out = np.empty((len(ps), self.n))
+        self.lib.check(self.lib.lib.gsp_ensemble_quantile(self.h, len(ps), _ptr(ps), _ptr(out)))
+        return out
+
+    def moments(self):
+        mean, m2 = np.empty(self.n), np.empty(self.n)
+        self.lib.check(self.lib.lib.gsp_ensemble_moments(self.h, _ptr(mean), _ptr(m2)))
+        return mean, m2
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.lib.gsp_ensemble_destroy(self.h)
             self.h = None
 
     def __del__(self):
@@ -291,6 +378,18 @@ class FFTPlan:
         rc = self.lib.lib.gsp_fft_sample(self.h, R, _ptr(w), seed, first_real, float(sill), float(mu), n_inds, _ptr(inds1), _ptr(Z))
         self.lib.check(rc)
         return Z
+
+    def sample_ensemble(self, R: int, w: Optional[np.ndarray] = None, seed: int = 0, first_real: int = 0, sill: float = 1.0,
+                        mu: float = 0.0, inds1: Optional[np.ndarray] = None) -> "DeviceEnsemble":
+        """like `sample`, but the realizations stay on the devices"""
+        if w is not None:
+            w = np.ascontiguousarray(w, dtype=np.float64).reshape(R, self.N)
+        n_inds = 0 if inds1 is None else len(inds1)
+        inds1 = None if inds1 is None else np.ascontiguousarray(inds1, dtype=np.int64)
+        ens = DeviceEnsemble(self.lib, n_inds if n_inds else self.N, R)
+        rc = self.lib.lib.gsp_fft_sample_ensemble(self.h, ens.h, _ptr(w), seed, first_real, float(sill), float(mu), n_inds, _ptr(inds1))
+        self.lib.check(rc)
+        return ens
 
     def sample_dev(self, R, w_ptr, seed, first_real, sill, mu, n_inds, inds_ptr, out_ptr):
         rc = self.lib.lib.gsp_fft_sample_dev(self.h, R, w_ptr, seed, first_real, float(sill), float(mu), n_inds, inds_ptr, out_ptr)

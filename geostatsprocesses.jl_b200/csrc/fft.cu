@@ -16,6 +16,7 @@
 #include "fft_kernels.cuh"
 #include "fft_pow2.cuh"
 #include "fft_plane.cuh"
+#include "ensemble.h"
 #include "rng.cuh"
 
 namespace gsp {
@@ -1044,20 +1045,28 @@ extern "C" int gsp_fft_sample_dev(gsp_fft_plan* p, int64_t R, const double* w, u
   return GSP_OK;
 }
 
-extern "C" int gsp_fft_sample(gsp_fft_plan* p, int64_t R, const double* w, uint64_t seed, int64_t first_real, double sill,
-                              double mu, int64_t n_inds, const int64_t* inds, double* out) {
-  if (!p) return -1;
+namespace gsp {
+namespace {
+
+// Host-facing sampling core.  Realizations are sharded contiguously over the devices of the context; the result goes either
+// to the caller's host buffer `out` (3-stream H2D / compute / D2H pipeline per device) or stays on the devices in `ens`
+// (same sharding rule as gsp_ensemble_create), in which case nothing but the noise (if injected) crosses PCIe.
+int fft_sample_impl(gsp_fft_plan* p, int64_t R, const double* w, uint64_t seed, int64_t first_real, double sill, double mu, int64_t n_inds,
+                    const int64_t* inds, double* out, gsp_ensemble* ens) {
   gsp_ctx* ctx = p->ctx;
-  std::lock_guard<std::mutex> lk(p->mu);
   if (R < 0) return set_err(ctx, -2, "R < 0");
   if (!(sill > 0.0)) return set_err(ctx, -6, "sill must be positive");
-  if (!out) return set_err(ctx, -10, "out is NULL");
+  if (!out && !ens) return set_err(ctx, -10, "out is NULL");
   if (n_inds > 0 && !inds) return set_err(ctx, -9, "inds is NULL");
   if (n_inds > 0)
     for (long long q = 0; q < n_inds; ++q)
       if (inds[q] < 1 || inds[q] > p->N) return set_err(ctx, -9, "inds out of range (1-based parent indices)");
   const long long nout = n_inds > 0 ? n_inds : p->N;
   const int ndev = (int)p->dev.size();
+  if (ens) {
+    if (ens->ctx != ctx || (int)ens->dev.size() != ndev) return set_err(ctx, -11, "the ensemble belongs to a different context");
+    if (ens->n != nout || ens->R != R) return set_err(ctx, -11, "ensemble shape does not match (n = n_inds or prod(dims), R realizations)");
+  }
   // host pipeline granularity: 3-D grids move one realization (8 N bytes each way) per step - PCIe is the bound there and a
   // finer grain overlaps better; 1-D / 2-D grids move a batch
   const long long hrb = p->ndim == 3 ? 1 : p->rb;
@@ -1077,7 +1086,7 @@ extern "C" int gsp_fft_sample(gsp_fft_plan* p, int64_t R, const double* w, uint6
     }
     for (int k = 0; k < 2; ++k) {
       if (w && !d->win[k].p) GSP_CUDA_OK(ctx, d->win[k].alloc(d->dc->dev, (size_t)p->N * hrb * sizeof(double)));
-      if (!d->zout[k].p || d->zout[k].bytes < (size_t)nout * hrb * sizeof(double))
+      if (!ens && (!d->zout[k].p || d->zout[k].bytes < (size_t)nout * hrb * sizeof(double)))
         GSP_CUDA_OK(ctx, d->zout[k].alloc(d->dc->dev, (size_t)nout * hrb * sizeof(double)));
     }
   }
@@ -1104,8 +1113,9 @@ extern "C" int gsp_fft_sample(gsp_fft_plan* p, int64_t R, const double* w, uint6
     cudaSetDevice(d0->dc->dev);
     cudaEventRecord(d0->ev0, d0->dc->stream);
   }
-  // one pipeline step = one chunk of up to hrb realizations (1 for 3-D grids, a batch for 1-D / 2-D grids)
-  const long long rb = hrb;
+  // one pipeline step = one chunk of up to hrb realizations (1 for 3-D grids, a batch for 1-D / 2-D grids); a resident
+  // ensemble with on-device noise has nothing to pipeline: the whole shard is one step (all lanes busy)
+  const long long rb = (ens && !w) ? std::max<long long>(maxshard, 1) : hrb;
   const long long nsteps = (maxshard + rb - 1) / rb;
   for (long long step = 0; step < nsteps && rc == GSP_OK; ++step) {
     for (int i = 0; i < ndev && rc == GSP_OK; ++i) {
@@ -1124,6 +1134,13 @@ extern "C" int gsp_fft_sample(gsp_fft_plan* p, int64_t R, const double* w, uint6
         cudaEventRecord(evs[i].in_ready[k], d->dc->h2d);
         cudaStreamWaitEvent(d->dc->stream, evs[i].in_ready[k], 0);
         wdev = d->win[k].as<double>();
+      }
+      if (ens) {
+        rc = sample_on_device(p, d, nbk, wdev, seed, first_real + r, sill, mu, n_inds, d->inds.as<long long>(),
+                              ens->dev[i]->Z.as<double>() + step * rb * nout, &sw[i], &sz[i]);
+        if (rc != GSP_OK) break;
+        if (w) cudaEventRecord(evs[i].in_free[k], d->dc->stream);
+        continue;
       }
       if (step >= 2) cudaStreamWaitEvent(d->dc->stream, evs[i].drained[k], 0);
       rc = sample_on_device(p, d, nbk, wdev, seed, first_real + r, sill, mu, n_inds, d->inds.as<long long>(), d->zout[k].as<double>(),
@@ -1164,4 +1181,24 @@ extern "C" int gsp_fft_sample(gsp_fft_plan* p, int64_t R, const double* w, uint6
     ctx->last_sample_ms = ms;
   }
   return rc;
+}
+
+}  // namespace
+}  // namespace gsp
+
+extern "C" int gsp_fft_sample(gsp_fft_plan* p, int64_t R, const double* w, uint64_t seed, int64_t first_real, double sill,
+                              double mu, int64_t n_inds, const int64_t* inds, double* out) {
+  if (!p) return -1;
+  std::lock_guard<std::mutex> lk(p->mu);
+  if (!out) return set_err(p->ctx, -10, "out is NULL");
+  return fft_sample_impl(p, R, w, seed, first_real, sill, mu, n_inds, inds, out, nullptr);
+}
+
+extern "C" int gsp_fft_sample_ensemble(gsp_fft_plan* p, gsp_ensemble* ens, const double* w, uint64_t seed, int64_t first_real, double sill,
+                                       double mu, int64_t n_inds, const int64_t* inds) {
+  if (!p) return -1;
+  std::lock_guard<std::mutex> lk(p->mu);
+  if (!ens) return set_err(p->ctx, -2, "ensemble is NULL");
+  std::lock_guard<std::mutex> lk2(ens->mu);
+  return fft_sample_impl(p, ens->R, w, seed, first_real, sill, mu, n_inds, inds, nullptr, ens);
 }

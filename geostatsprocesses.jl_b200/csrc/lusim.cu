@@ -15,6 +15,7 @@
 #include <memory>
 
 #include "chol.h"
+#include "ensemble.h"
 #include "rng.cuh"
 
 namespace gsp {
@@ -411,13 +412,19 @@ extern "C" int gsp_lu_sample_dev(gsp_lu_plan* p, int64_t R, const double* W, int
   return GSP_OK;
 }
 
-extern "C" int gsp_lu_sample(gsp_lu_plan* p, int64_t R, const double* W, uint64_t seed, int32_t stream, int64_t first_real,
-                             double rho, const double* W1, double* Z) {
-  if (!p) return -1;
+namespace gsp {
+namespace {
+
+// host-facing sampling core: fields go to the caller's host buffer Z, or stay on the devices in `ens` (same sharding rule)
+int lu_sample_impl(gsp_lu_plan* p, int64_t R, const double* W, uint64_t seed, int32_t stream, int64_t first_real, double rho,
+                   const double* W1, double* Z, gsp_ensemble* ens) {
   gsp_ctx* ctx = p->ctx;
-  std::lock_guard<std::mutex> lk(p->mu_lock);
   if (R < 0) return set_err(ctx, -2, "R < 0");
-  if (!Z) return set_err(ctx, -9, "Z is NULL");
+  if (!Z && !ens) return set_err(ctx, -9, "Z is NULL");
+  if (ens) {
+    if (ens->ctx != ctx || ens->dev.size() != p->dev.size()) return set_err(ctx, -9, "the ensemble belongs to a different context");
+    if (ens->n != p->N || ens->R != R) return set_err(ctx, -9, "ensemble shape does not match (n = N nodes, R realizations)");
+  }
   const bool mix = !std::isnan(rho);
   if (mix && !(rho >= -1.0 && rho <= 1.0)) return set_err(ctx, -7, "rho must be in [-1, 1] (or NaN for the first variable)");
   if (mix && W && !W1) return set_err(ctx, -8, "W1 is required when W is given and rho is set");
@@ -460,9 +467,10 @@ extern "C" int gsp_lu_sample(gsp_lu_plan* p, int64_t R, const double* W, uint64_
         }
       }
       if (e != cudaSuccess) { rc = set_err(ctx, GSP_E_CUDA, cudaGetErrorString(e)); break; }
-      rc = sample_core(ctx, p, d, cols, Wd, p->Ns, seed, stream, first_real + ra, rho, W1d, d->Zc.as<double>(), p->N);
+      double* Zt = ens ? ens->dev[i]->Z.as<double>() + c0 * p->N : d->Zc.as<double>();
+      rc = sample_core(ctx, p, d, cols, Wd, p->Ns, seed, stream, first_real + ra, rho, W1d, Zt, p->N);
     }
-    for (int i = 0; i < ndev && rc == GSP_OK; ++i) {
+    for (int i = 0; i < ndev && rc == GSP_OK && !ens; ++i) {
       const long long nloc = r0[i + 1] - r0[i];
       if (c0 >= nloc) continue;
       LuDev* d = p->dev[i].get();
@@ -489,4 +497,24 @@ extern "C" int gsp_lu_sample(gsp_lu_plan* p, int64_t R, const double* W, uint64_
     ctx->last_sample_ms = ms;
   }
   return rc;
+}
+
+}  // namespace
+}  // namespace gsp
+
+extern "C" int gsp_lu_sample(gsp_lu_plan* p, int64_t R, const double* W, uint64_t seed, int32_t stream, int64_t first_real,
+                             double rho, const double* W1, double* Z) {
+  if (!p) return -1;
+  std::lock_guard<std::mutex> lk(p->mu_lock);
+  if (!Z) return set_err(p->ctx, -9, "Z is NULL");
+  return lu_sample_impl(p, R, W, seed, stream, first_real, rho, W1, Z, nullptr);
+}
+
+extern "C" int gsp_lu_sample_ensemble(gsp_lu_plan* p, gsp_ensemble* ens, const double* W, uint64_t seed, int32_t stream,
+                                      int64_t first_real, double rho, const double* W1) {
+  if (!p) return -1;
+  std::lock_guard<std::mutex> lk(p->mu_lock);
+  if (!ens) return set_err(p->ctx, -2, "ensemble is NULL");
+  std::lock_guard<std::mutex> lk2(ens->mu);
+  return lu_sample_impl(p, ens->R, W, seed, stream, first_real, rho, W1, nullptr, ens);
 }

@@ -177,10 +177,22 @@ def preprocess_lusim(process: GaussianProcess, method: LUSIM, init, domain, data
     return _LUPre(plans, names, rho)
 
 
-def rand_lusim(pre: _LUPre, nreals: int, rng, seed: int) -> Dict[str, np.ndarray]:
-    """randsingle + _lusim (lusim.jl:112-175) for all realizations at once.  Returns var -> (N, R) arrays."""
+def rand_lusim(pre: _LUPre, nreals: int, rng, seed: int, resident: bool = False) -> Dict[str, np.ndarray]:
+    """randsingle + _lusim (lusim.jl:112-175) for all realizations at once.  Returns var -> (N, R) arrays, or with
+    `resident` var -> DeviceEnsemble (the fields stay in HBM)."""
     p1 = pre.plans[0]
     out = {}
+    if resident:
+        W1 = W2 = None
+        nv = len(pre.plans)
+        if rng is not None:
+            W = rng.standard_normal((nreals, nv, p1.Ns))
+            W1 = np.asfortranarray(W[:, 0, :].T)
+            W2 = np.asfortranarray(W[:, 1, :].T) if nv == 2 else None
+        out[pre.names[0]] = p1.sample_ensemble(nreals, W1, seed=seed, stream=0)
+        if nv == 2:
+            out[pre.names[1]] = pre.plans[1].sample_ensemble(nreals, W2, seed=seed, stream=1, rho=pre.rho, W1=W1)
+        return out
     if rng is not None:
         # the reference's draw order: per realization w1 (Ns normals), then w2 (lusim.jl:160, randsingle :114-119)
         nv = len(pre.plans)
@@ -220,32 +232,42 @@ def preprocess_fftsim(process: GaussianProcess, method: FFTSIM, init, domain, da
     return _FFTPre(plan, var, domain.parentindices(), float(f.sill()))
 
 
-def rand_fftsim(pre: _FFTPre, process: GaussianProcess, nreals: int, rng, seed: int) -> Dict[str, np.ndarray]:
-    """fftsim.jl:109-139 for all realizations.  Returns var -> (n, R)."""
+def rand_fftsim(pre: _FFTPre, process: GaussianProcess, nreals: int, rng, seed: int, resident: bool = False) -> Dict[str, np.ndarray]:
+    """fftsim.jl:109-139 for all realizations.  Returns var -> (n, R), or with `resident` var -> DeviceEnsemble."""
     w = None
     if rng is not None:
         w = rng.random((nreals, pre.plan.N))  # rand(rng, Float64, dims) per realization (fftsim.jl:124), column-major dims
+    if resident:
+        return {pre.var: pre.plan.sample_ensemble(nreals, w, seed=seed, sill=pre.sill, mu=process.mean_of(0), inds1=pre.inds1)}
     Z = pre.plan.sample(nreals, w, seed=seed, sill=pre.sill, mu=process.mean_of(0), inds1=pre.inds1)
     return {pre.var: Z.T}
 
 
 # ------------------------------------------------------------------ ensemble
 class Ensemble:
-    """ensembles.jl:10-85.  `reals[var]` is an (n, R) array; `e[i]` is the i-th realization (0-based) as a GeoTable."""
+    """ensembles.jl:10-85.  `reals[var]` is an (n, R) host array, or a DeviceEnsemble when the realizations are resident
+    on the GPUs (`rand(..., resident=True)`): then `e[i]` fetches one realization (the reference's `fetch` hook,
+    ensembles.jl:16,27-31) and the statistics (ensembles.jl:42-52) run in HBM - only n-vectors come back.
+    `e[i]` is the i-th realization (0-based) as a GeoTable."""
 
-    def __init__(self, domain, reals: Dict[str, np.ndarray]):
+    def __init__(self, domain, reals: Dict[str, Union[np.ndarray, _lib.DeviceEnsemble]]):
         self.domain = domain
         self.reals = reals
 
+    @staticmethod
+    def _resident(a) -> bool:
+        return isinstance(a, _lib.DeviceEnsemble)
+
     def __len__(self):
-        return next(iter(self.reals.values())).shape[1]
+        a = next(iter(self.reals.values()))
+        return a.R if self._resident(a) else a.shape[1]
 
     def __getitem__(self, i):
         if isinstance(i, (list, tuple, np.ndarray, range)):
             return [self[k] for k in i]
         if i < 0 or i >= len(self):
             raise IndexError(i)
-        return georef({v: a[:, i] for v, a in self.reals.items()}, self.domain)
+        return georef({v: (a.fetch(i, 1)[0] if self._resident(a) else a[:, i]) for v, a in self.reals.items()}, self.domain)
 
     def __iter__(self):
         return (self[i] for i in range(len(self)))
@@ -253,37 +275,58 @@ class Ensemble:
     def variables(self):
         return tuple(self.reals.keys())
 
-    def _reduce(self, fn):
-        return georef({v: fn(a) for v, a in self.reals.items()}, self.domain)
+    def _reduce(self, host_fn, dev_fn):
+        return georef({v: (dev_fn(a) if self._resident(a) else host_fn(a)) for v, a in self.reals.items()}, self.domain)
 
     def mean(self):
-        return self._reduce(lambda a: a.mean(axis=1))
+        return self._reduce(lambda a: a.mean(axis=1), lambda d: d.mean())
 
     def var(self):
-        return self._reduce(lambda a: a.var(axis=1, ddof=1))
+        return self._reduce(lambda a: a.var(axis=1, ddof=1), lambda d: d.var())
 
     def cdf(self, x: float):
-        return self._reduce(lambda a: (a <= x).mean(axis=1))
+        return self._reduce(lambda a: (a <= x).mean(axis=1), lambda d: d.cdf(x))
 
     def ccdf(self, x: float):
-        return self._reduce(lambda a: (a > x).mean(axis=1))
+        return self._reduce(lambda a: (a > x).mean(axis=1), lambda d: d.ccdf(x))
 
     def quantile(self, p):
         if np.ndim(p) > 0:
             return [self.quantile(q) for q in p]
-        return self._reduce(lambda a: np.quantile(a, p, axis=1))
+        return self._reduce(lambda a: np.quantile(a, p, axis=1), lambda d: d.quantile([p])[0])
+
+    def close(self):
+        """release the device memory of a resident ensemble (also done when the object is collected)"""
+        for a in self.reals.values():
+            if self._resident(a):
+                a.close()
 
     def __repr__(self):
         return f"{self.domain.ndim}D Ensemble\n  domain:    {self.domain}\n  variables: {', '.join(self.variables())}\n  N° reals:  {len(self)}"
 
 
+def merge_moments(parts):
+    """Chan's update over per-rank partials [(count, mean, m2), ...] (gsp_ensemble_moments of every rank's shard, gathered
+    with torch.distributed.all_gather_object or an all-gather of device tensors): -> (R, mean, var) of the whole ensemble."""
+    cnt, mean, m2 = parts[0]
+    mean, m2 = np.array(mean, dtype=np.float64), np.array(m2, dtype=np.float64)
+    for c, m, q in parts[1:]:
+        tot = cnt + c
+        d = np.asarray(m) - mean
+        mean = mean + d * (c / tot)
+        m2 = m2 + np.asarray(q) + d * d * (cnt * c / tot)
+        cnt = tot
+    return cnt, mean, m2 / (cnt - 1)
+
+
 def rand(process: GaussianProcess, domain, nreals: Optional[int] = None, *, rng: Union[None, int, np.random.Generator] = None,
-         data: Optional[GeoTable] = None, method: Optional[FieldSimulationMethod] = None, init=None):
+         data: Optional[GeoTable] = None, method: Optional[FieldSimulationMethod] = None, init=None, resident: bool = False):
     """rand([rng], process, domain, [n]; data, method, init) - field.jl:47-124.
 
     rng: a numpy Generator -> noise is drawn on the host in the reference's order and injected
     (parity mode); None or an int seed -> on-device counter RNG (throughput mode).
-    Without `nreals` a single GeoTable is returned, with it an Ensemble."""
+    Without `nreals` a single GeoTable is returned, with it an Ensemble.  resident=True keeps the realizations on the
+    GPUs (Ensemble with the `fetch` hook, ensembles.jl:16): statistics run in HBM, `e[i]` downloads one realization."""
     init = init or NearestInit()
     smethod = method if method is not None else defaultsimulation(process, domain, data)
     gen = rng if isinstance(rng, np.random.Generator) else None
@@ -291,12 +334,12 @@ def rand(process: GaussianProcess, domain, nreals: Optional[int] = None, *, rng:
     n = 1 if nreals is None else int(nreals)
     if isinstance(smethod, LUSIM):
         pre = preprocess_lusim(process, smethod, init, domain, data)
-        reals = rand_lusim(pre, n, gen, seed)
+        reals = rand_lusim(pre, n, gen, seed, resident and nreals is not None)
         for p in pre.plans:
             p.close()
     elif isinstance(smethod, FFTSIM):
         pre = preprocess_fftsim(process, smethod, init, domain, data)
-        reals = rand_fftsim(pre, process, n, gen, seed)
+        reals = rand_fftsim(pre, process, n, gen, seed, resident and nreals is not None)
         pre.plan.close()
     else:
         raise TypeError(f"unsupported simulation method {smethod!r}")

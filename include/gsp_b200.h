@@ -150,6 +150,35 @@ int gsp_fft_sample(gsp_fft_plan* plan, int64_t R, const double* w, uint64_t seed
 int gsp_fft_sample_dev(gsp_fft_plan* plan, int64_t R, const double* w, uint64_t seed, int64_t first_real, double sill,
                        double mu, int64_t n_inds, const int64_t* inds_dev, double* out);
 
+/* ---- Device-resident ensembles: Ensemble(domain, reals; fetch) - src/ensembles.jl:10-16.
+ * R realizations of n values each stay in HBM, sharded contiguously over the devices of the context (the same rule
+ * gsp_*_sample uses); `fetch` is the reference's lazy per-realization hook (ensembles.jl:27-31) and the statistics
+ * replace the scalar `ereduce` loops of ensembles.jl:42-52,76-85: only n-vectors cross PCIe. */
+typedef struct gsp_ensemble gsp_ensemble;
+int gsp_ensemble_create(gsp_ctx* ctx, int64_t n, int64_t R, gsp_ensemble** out);
+int gsp_ensemble_destroy(gsp_ensemble* e);
+/* sizes[0] = n (values per realization), sizes[1] = R */
+int gsp_ensemble_sizes(gsp_ensemble* e, int64_t sizes[2]);
+/* realizations [r0, r0 + nr) (0-based) <-> host buffer n x nr column-major */
+int gsp_ensemble_put(gsp_ensemble* e, int64_t r0, int64_t nr, const double* Z);
+int gsp_ensemble_fetch(gsp_ensemble* e, int64_t r0, int64_t nr, double* Z);
+/* fill by simulation: the arguments of gsp_fft_sample / gsp_lu_sample (w / W host noise or NULL for the device RNG) with R and
+ * the output taken from the ensemble (n must equal n_inds or prod(dims), resp. N) */
+int gsp_fft_sample_ensemble(gsp_fft_plan* plan, gsp_ensemble* e, const double* w, uint64_t seed, int64_t first_real, double sill,
+                            double mu, int64_t n_inds, const int64_t* inds);
+int gsp_lu_sample_ensemble(gsp_lu_plan* plan, gsp_ensemble* e, const double* W, uint64_t seed, int32_t stream, int64_t first_real,
+                           double rho, const double* W1);
+/* mean(e), var(e) (corrected, R - 1), cdf(e, x) = count(<= x)/R, ccdf(e, x) = count(> x)/R - ensembles.jl:42-48; out: n */
+int gsp_ensemble_mean(gsp_ensemble* e, double* out);
+int gsp_ensemble_var(gsp_ensemble* e, double* out);
+int gsp_ensemble_cdf(gsp_ensemble* e, double x, double* out);
+int gsp_ensemble_ccdf(gsp_ensemble* e, double x, double* out);
+/* quantile(e, ps) - ensembles.jl:50-52, Statistics.quantile's default definition (alpha = beta = 1); out: n x np column-major */
+int gsp_ensemble_quantile(gsp_ensemble* e, int64_t np, const double* ps, double* out);
+/* per-node mean and centred sum of squares m2 = sum (z - mean)^2 over this context's R realizations (either may be NULL):
+ * the partials a multi-process job merges (Chan's update) after an all-gather over its ranks */
+int gsp_ensemble_moments(gsp_ensemble* e, double* mean, double* m2);
+
 /* Optional per-kernel-class device timing (CUDA events on the launching stream around every launch of
  * this library).  Off by default.  gsp_profile_read writes a JSON object {"kernel": {"ms": total, "launches": n}, ...}
  * accumulated since the last enable into buf and returns its length (or -needed if buflen is too small). */

@@ -28,6 +28,8 @@ and the oracle consume identical arrays.
 """
 from __future__ import annotations
 
+import math
+
 import os
 from dataclasses import dataclass, field
 from typing import Optional, Sequence
@@ -257,3 +259,38 @@ def fftsim_sample(F: np.ndarray, w: np.ndarray, sill: float, mu: float,
     Z = np.sqrt(sill / s2) * Z + mu                      # fftsim.jl:132
     z = Z.reshape(-1)
     return z if inds is None else z[np.asarray(inds)]    # fftsim.jl:135
+
+
+# ---------------------------------------------------------------------------------------------- ensemble statistics
+def julia_quantile(v: np.ndarray, p: float) -> float:
+    """Statistics.quantile(v, p) with Julia's defaults alpha = beta = 1 (definition 7), the call at src/ensembles.jl:50:
+    sort; m = alpha + p (1 - alpha - beta); aleph = n p + m; j = clamp(trunc(aleph), 1, n-1); g = clamp(aleph - j, 0, 1);
+    n == 1 ? v[1] : v[j] + g (v[j+1] - v[j])."""
+    v = np.sort(np.asarray(v, dtype=np.float64))
+    n = len(v)
+    if not (0.0 <= p <= 1.0):
+        raise ValueError("input probability out of [0,1] range")
+    m = 1.0 + p * (1.0 - 1.0 - 1.0)
+    aleph = n * p + m
+    j = int(min(max(math.trunc(aleph), 1), n - 1)) if n > 1 else 1
+    g = min(max(aleph - j, 0.0), 1.0)
+    if n == 1:
+        a = b = v[0]
+    else:
+        a, b = v[j - 1], v[j]
+    return a + g * (b - a)
+
+
+def ensemble_stats(Z: np.ndarray, x: float, ps: Sequence[float]):
+    """src/ensembles.jl:42-52 on an (R, n) array of realizations (row = realization): mean, var (corrected), cdf(x) =
+    count(<= x)/R, ccdf(x) = count(> x)/R and quantile(p) for p in ps, each per node.  Scalar loops like `ereduce`
+    (ensembles.jl:76-85) for the quantile; use small n."""
+    Z = np.asarray(Z, dtype=np.float64)
+    R, n = Z.shape
+    mean = Z.sum(axis=0) / R
+    var = ((Z - mean) ** 2).sum(axis=0) / (R - 1) if R > 1 else np.full(n, np.nan)
+    cdf = (Z <= x).sum(axis=0) / R
+    ccdf = (Z > x).sum(axis=0) / R
+    q = np.array([[julia_quantile(Z[:, i], p) for i in range(n)] for p in ps])
+    return mean, var, cdf, ccdf, q
+

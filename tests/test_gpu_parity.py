@@ -326,3 +326,72 @@ def test_rand_api_gpu(gpu_lib):
     vgrid = grid.view(range(1, 5001))
     real = gsp.rand(proc, vgrid, rng=rng, method=gsp.FFTSIM(library=gpu_lib))
     assert real.domain == vgrid and real.nrow == 5000
+
+
+# ------------------------------------------------------------------ §8f rank 1: device-resident ensembles (src/ensembles.jl:42-52)
+def test_ensemble_reference_pins_gpu(gpu_lib):
+    """the reference's value-level ensemble test (test/ensembles.jl:24-59) on the CUDA kernels"""
+    ens = gsp.DeviceEnsemble(gpu_lib, 9, 3)
+    ens.put(np.stack([i * np.ones(9) for i in (1.0, 2.0, 3.0)]))
+    ones = np.ones(9)
+    assert np.array_equal(ens.mean(), 2.0 * ones) and np.array_equal(ens.var(), ones)
+    for i in (1, 2, 3):
+        assert np.array_equal(ens.cdf(i), i / 3 * ones)
+        assert np.allclose(ens.ccdf(i), 1 - ens.cdf(i), rtol=1e-15, atol=1e-16)
+    q = ens.quantile([0.0, 0.5, 1.0])
+    assert np.array_equal(q, np.stack([ones, 2 * ones, 3 * ones]))
+    ens.close()
+
+
+@pytest.mark.parametrize("n,R", [(1000, 1), (4097, 2), (50_000, 257), (20_000, 1000), (300, 4096), (64, 10_000)])
+def test_ensemble_statistics_gpu(gpu_lib, n, R):
+    rng = np.random.default_rng(n + R)
+    Z = rng.standard_normal((R, n)) * 2.5 - 17.0
+    ens = gsp.DeviceEnsemble(gpu_lib, n, R)
+    ens.put(Z)
+    assert np.array_equal(ens.fetch(R - 1, 1)[0], Z[R - 1])
+    assert relerr(ens.mean(), Z.mean(axis=0)) < 1e-13
+    if R > 1:
+        assert relerr(ens.var(), Z.var(axis=0, ddof=1)) < 1e-12
+    x = -16.2
+    assert np.array_equal(ens.cdf(x), (Z <= x).sum(axis=0) / R) and np.array_equal(ens.ccdf(x), (Z > x).sum(axis=0) / R)
+    ps = [0.0, 0.05, 0.5, 0.777, 1.0]
+    q = ens.quantile(ps)
+    sub = slice(0, min(n, 64))  # scalar oracle (Julia's formula) on a few nodes, numpy on all of them
+    qo = np.array([[O.julia_quantile(Z[:, i], p) for i in range(n)[sub]] for p in ps])
+    assert relerr(q[:, sub], qo) < 1e-15
+    assert relerr(q, np.quantile(Z, ps, axis=0)) < 1e-14
+    ens.close()
+
+
+def test_ensemble_resident_simulation_gpu(gpu_lib):
+    """realizations simulated straight into a resident ensemble == the host-path fields; statistics of a conditional LUSIM
+    ensemble: data nodes have mean z1 and variance 0, free nodes converge to the simple-kriging mean d2."""
+    st = iso(O.SPHERICAL, 1.0, 8.0, 3)
+    plan = gsp.FFTPlan(gpu_lib, st, (64, 64, 32), [0.0] * 3, [1.0] * 3)
+    e = plan.sample_ensemble(9, None, seed=21, sill=1.0, mu=2.0)   # 9 realizations over 4 lanes: uneven last chunk
+    assert np.array_equal(e.fetch(), plan.sample(9, None, seed=21, sill=1.0, mu=2.0))
+    w = np.random.default_rng(2).random((3, 64 * 64 * 32))
+    e2 = plan.sample_ensemble(3, w, sill=1.0, mu=2.0)
+    assert np.array_equal(e2.fetch(), plan.sample(3, w, sill=1.0, mu=2.0))
+    assert abs(e.mean().mean() - 2.0) < 1e-12  # every realization has exact spatial mean mu (fftsim.jl:91)
+    e.close(), e2.close(), plan.close()
+    dims = (40, 40)
+    N = 1600
+    rng = np.random.default_rng(8)
+    dinds = np.sort(rng.choice(N, 60, replace=False))
+    z1 = rng.standard_normal(60)
+    st2 = iso(O.EXPONENTIAL, 1.0, 12.0, 2)
+    lp = gsp.LUPlan(gpu_lib, st2, grid_dom(dims), dinds + 1, z1, 0.0)
+    R = 4000
+    ens = lp.sample_ensemble(R, None, seed=3)
+    mean, var = ens.mean(), ens.var()
+    assert np.array_equal(mean[dinds], z1) and np.all(var[dinds] == 0.0)
+    d2, L22 = lp.get()
+    sinds = np.setdiff1d(np.arange(N), dinds)
+    cvar = (L22 ** 2).sum(axis=1)  # conditional variance = diag(L22 L22')
+    assert np.abs(mean[sinds] - d2).max() < 5.0 * np.sqrt(cvar.max() / R)
+    assert np.abs(var[sinds] / cvar - 1.0).max() < 0.15
+    med = ens.quantile([0.5])[0]
+    assert np.abs(med[sinds] - d2).max() < 6.0 * np.sqrt(cvar.max() / R)
+    ens.close(), lp.close()

@@ -75,6 +75,8 @@ SIGNATURES = {
     "gsp_fft_plan_get": (C.c_int, [_vp, _vp]),
     "gsp_fft_sample": (C.c_int, [_vp, C.c_int64, _vp, C.c_uint64, C.c_int64, C.c_double, C.c_double, C.c_int64, _vp, _vp]),
     "gsp_fft_sample_dev": (C.c_int, [_vp, C.c_int64, _vp, C.c_uint64, C.c_int64, C.c_double, C.c_double, C.c_int64, _vp, _vp]),
+    "gsp_fft_plan_condition": (C.c_int, [_vp, C.c_double, C.c_int32, C.c_int32, C.c_int64, _vp, _vp, C.c_int64, _vp, C.c_int64, _vp]),
+    "gsp_fft_plan_condmean": (C.c_int, [_vp, _vp]),
     "gsp_ensemble_create": (C.c_int, [_vp, C.c_int64, C.c_int64, C.POINTER(_vp)]),
     "gsp_ensemble_destroy": (C.c_int, [_vp]),
     "gsp_ensemble_sizes": (C.c_int, [_vp, C.POINTER(C.c_int64 * 2)]),
@@ -361,6 +363,24 @@ class FFTPlan:
         self.h = h
         self.dims = tuple(int(d) for d in dims)
         self.N = int(np.prod(self.dims))
+
+    def condition(self, mu: float, dcoords: np.ndarray, dvals: np.ndarray, knodes1: np.ndarray, inds1: Optional[np.ndarray] = None,
+                  minneighbors: int = 1, maxneighbors: int = 26):
+        """fftsim.jl:94-101: dcoords (nd, dim), dvals (nd); knodes1 = findall(mask) within the simulation domain (1-based);
+        inds1 = parentindices of the view (None: whole grid).  Afterwards `sample*` returns conditional realizations."""
+        X = np.ascontiguousarray(np.asarray(dcoords, dtype=np.float64).reshape(len(dvals), -1))
+        v = np.ascontiguousarray(dvals, dtype=np.float64)
+        kn = np.ascontiguousarray(knodes1, dtype=np.int64)
+        ii = None if inds1 is None else np.ascontiguousarray(inds1, dtype=np.int64)
+        rc = self.lib.lib.gsp_fft_plan_condition(self.h, float(mu), int(minneighbors), int(maxneighbors), len(v), _ptr(X), _ptr(v), len(kn),
+                                                 _ptr(kn), 0 if ii is None else len(ii), _ptr(ii))
+        self.lib.check(rc)
+        self.cond_n = self.N if ii is None else len(ii)
+
+    def condmean(self) -> np.ndarray:
+        z = np.empty(getattr(self, "cond_n", self.N))
+        self.lib.check(self.lib.lib.gsp_fft_plan_condmean(self.h, _ptr(z)))
+        return z
 
     def spectrum(self) -> np.ndarray:
         F = np.empty(self.N)

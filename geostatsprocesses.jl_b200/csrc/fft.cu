@@ -17,6 +17,7 @@
 #include "fft_pow2.cuh"
 #include "fft_plane.cuh"
 #include "ensemble.h"
+#include "krige.cuh"
 #include "rng.cuh"
 
 namespace gsp {
@@ -297,8 +298,19 @@ struct Sub {
   long long o0 = 0, o1 = 0;
 };
 
+// conditioning by Kriging of residuals (krige.cuh): per-node weight table of the second Kriging + the conditional mean
+struct CondDev {
+  DevBuf zbar;    // n
+  DevBuf lam;     // weight table, tile-major: [n / 32][kk][32]
+  DevBuf nbr;     // same layout, int32: index into the residual table
+  DevBuf knodes;  // nk: 0-based positions of the data nodes within sdom
+  DevBuf res;     // nk x chunk residuals
+  long long res_cap = 0;
+};
+
 struct FftDev {
   DevCtx* dc = nullptr;
+  CondDev cond;
   std::vector<std::unique_ptr<Lane>> lanes;
   cudaEvent_t ev_fork = nullptr;
   int slab_mode = 0;     // 0: full-grid passes; 1: z-plane slabs for the x/y pairs; 2: kx-bundle groups for y fwd / z / y inv
@@ -332,6 +344,13 @@ struct gsp_fft_plan {
   int hx = 1, hxF = 2;  // F rows are padded to an even length: 16-byte aligned rows for the bulk copies
   double sumF2 = 0.0;  // full-spectrum sum of F^2
   long long rb = 1;    // realizations per launch (1-D / 2-D grids are batched so that small grids still fill the GPU)
+  gsp::CovDev cov;     // the model and the parent grid (kept for gsp_fft_plan_condition)
+  gsp::DomDev dom;
+  // conditional simulation (gsp_fft_plan_condition): z = zbar + (zu - zbaru), fftsim.jl:140-153
+  bool cond = false;
+  double cond_mu = 0.0;
+  long long cond_n = 0, cond_nk = 0, cond_ninds = 0;
+  int cond_kk = 0;
   std::vector<std::unique_ptr<FftDev>> dev;
   std::mutex mu;
 };
@@ -889,6 +908,8 @@ extern "C" int gsp_fft_plan_create(gsp_ctx* ctx, const gsp_cov_model* cov, const
   GSP_TRY(make_cov_dev(ctx, cov, grid->dim, 2, &cd));
   std::unique_ptr<gsp_fft_plan> p(new gsp_fft_plan);
   p->ctx = ctx;
+  p->cov = cd;
+  p->dom = dom;
   p->ndim = grid->dim;
   p->N = 1;
   for (int a = 0; a < 3; ++a) {
@@ -986,6 +1007,42 @@ extern "C" int gsp_fft_plan_get(gsp_fft_plan* p, double* F) {
 namespace gsp {
 namespace {
 
+// z = zbar + (zu - zbaru) for the nb <= 32 unconditional realizations at Z (n x nb), in place (fftsim.jl:140-153)
+int apply_conditioning(gsp_fft_plan* p, FftDev* d, double* Z, long long nb, double mu) {
+  gsp_ctx* ctx = p->ctx;
+  CondDev& c = d->cond;
+  const long long n = p->cond_n, nk = p->cond_nk;
+  cudaStream_t st = d->dc->stream;
+  if (c.res_cap < nk * KRIGE_RB) {
+    GSP_CUDA_OK(ctx, c.res.alloc(d->dc->dev, (size_t)(nk * KRIGE_RB) * sizeof(double)));
+    c.res_cap = nk * KRIGE_RB;
+  }
+  long long blocks = (nk * KRIGE_RB + 255) / 256;
+  if (blocks > (long long)d->dc->sms * 8) blocks = (long long)d->dc->sms * 8;
+  {
+    ProfScope prof_("krige_residual", st);
+    GSP_LAUNCH(krige_residual_kernel, dim3((unsigned)blocks), dim3(256), 0, st, (const double*)Z, n, (const long long*)c.knodes.as<long long>(), nk,
+               nb, mu, c.res.as<double>());
+    g_launches++;
+  }
+  blocks = (n + 31) / 32;
+  if (blocks > (long long)d->dc->sms * 8) blocks = (long long)d->dc->sms * 8;
+  ProfScope prof_("krige_apply", st);
+  GSP_LAUNCH(krige_apply_kernel, dim3((unsigned)blocks), dim3(256), 0, st, Z, n, (int)nb, (const double*)c.zbar.as<double>(),
+             (const double*)c.lam.as<double>(), (const int*)c.nbr.as<int>(), p->cond_kk, (const double*)c.res.as<double>(), mu);
+  g_launches++;
+  GSP_CUDA_OK(ctx, cudaGetLastError());
+  return GSP_OK;
+}
+
+// conditional plans were built for ONE simulation domain (the view) and ONE mean
+int check_cond_args(gsp_fft_plan* p, double mu, long long n_inds) {
+  if (!p->cond) return GSP_OK;
+  if (n_inds != p->cond_ninds) return set_err(p->ctx, -8, "conditional plan: n_inds / inds differ from those given to gsp_fft_plan_condition");
+  if (mu != p->cond_mu) return set_err(p->ctx, -7, "conditional plan: mu differs from the mean given to gsp_fft_plan_condition");
+  return GSP_OK;
+}
+
 // sample R realizations on one device; w/out/inds are DEVICE pointers (w may be NULL => RNG into scratch)
 int sample_on_device(gsp_fft_plan* p, FftDev* d, long long R, const double* w, unsigned long long seed, long long first_real,
                      double sill, double mu, long long n_inds, const long long* inds_dev, double* out, DevBuf* scratch_w,
@@ -1017,6 +1074,11 @@ int sample_on_device(gsp_fft_plan* p, FftDev* d, long long R, const double* w, u
       GSP_CUDA_OK(ctx, realization_batch(d, p, wr, out + r * p->N, nb, s, 1.0, mu));
     }
   }
+  // conditioning runs over larger chunks than the simulation: a node's weight row (12 kk bytes) is read once per chunk
+  if (p->cond) {
+    const long long nout = n_inds > 0 ? n_inds : p->N, cb = KRIGE_RB;
+    for (long long r = 0; r < R; r += cb) GSP_TRY(apply_conditioning(p, d, out + r * nout, (R - r < cb) ? R - r : cb, mu));
+  }
   return GSP_OK;
 }
 
@@ -1032,6 +1094,7 @@ extern "C" int gsp_fft_sample_dev(gsp_fft_plan* p, int64_t R, const double* w, u
   if (!(sill > 0.0)) return set_err(ctx, -6, "sill must be positive");
   if (!out) return set_err(ctx, -10, "out is NULL");
   if (n_inds > 0 && !inds_dev) return set_err(ctx, -9, "inds is NULL");
+  GSP_TRY(check_cond_args(p, mu, n_inds));
   FftDev* d = p->dev[0].get();
   cudaSetDevice(d->dc->dev);
   DevBuf sw, sz;
@@ -1058,6 +1121,7 @@ int fft_sample_impl(gsp_fft_plan* p, int64_t R, const double* w, uint64_t seed, 
   if (!(sill > 0.0)) return set_err(ctx, -6, "sill must be positive");
   if (!out && !ens) return set_err(ctx, -10, "out is NULL");
   if (n_inds > 0 && !inds) return set_err(ctx, -9, "inds is NULL");
+  GSP_TRY(check_cond_args(p, mu, n_inds));
   if (n_inds > 0)
     for (long long q = 0; q < n_inds; ++q)
       if (inds[q] < 1 || inds[q] > p->N) return set_err(ctx, -9, "inds out of range (1-based parent indices)");
@@ -1202,3 +1266,115 @@ extern "C" int gsp_fft_sample_ensemble(gsp_fft_plan* p, gsp_ensemble* ens, const
   std::lock_guard<std::mutex> lk2(ens->mu);
   return fft_sample_impl(p, ens->R, w, seed, first_real, sill, mu, n_inds, inds, nullptr, ens);
 }
+
+// ------------------------------------------------------------------ conditional FFTSIM (fftsim.jl:94-101,140-153)
+extern "C" int gsp_fft_plan_condition(gsp_fft_plan* p, double mu, int32_t minneighbors, int32_t maxneighbors, int64_t nd,
+                                      const double* dcoords, const double* dvals, int64_t nk, const int64_t* knodes, int64_t n_inds,
+                                      const int64_t* inds) {
+  if (!p) return -1;
+  gsp_ctx* ctx = p->ctx;
+  std::lock_guard<std::mutex> lk(p->mu);
+  if (!std::isfinite(mu)) return set_err(ctx, -2, "mu is not finite");
+  if (nd < 1 || !dcoords || !dvals) return set_err(ctx, -5, "conditioning data: nd >= 1, dcoords and dvals are required");
+  if (nk < 1 || !knodes) return set_err(ctx, -8, "data nodes: nk >= 1 and knodes are required");
+  if (n_inds < 0 || (n_inds > 0 && !inds)) return set_err(ctx, -10, "inds is NULL");
+  const long long n = n_inds > 0 ? n_inds : p->N;
+  for (long long q = 0; q < n_inds; ++q)
+    if (inds[q] < 1 || inds[q] > p->N) return set_err(ctx, -10, "inds out of range (1-based parent indices)");
+  for (long long j = 0; j < nk; ++j)
+    if (knodes[j] < 1 || knodes[j] > n || (j > 0 && knodes[j] <= knodes[j - 1]))
+      return set_err(ctx, -8, "knodes must be strictly ascending 1-based positions within the simulation domain (findall(mask))");
+  // GeoStatsModels.fitpredict fixes the limits the same way: maxneighbors outside [1, nobs] -> nobs, minneighbors outside [1, max] -> 1
+  long long kmax_d = maxneighbors, kmax_k = maxneighbors;
+  if (kmax_d > nd || kmax_d < 1) kmax_d = nd;
+  if (kmax_k > nk || kmax_k < 1) kmax_k = nk;
+  (void)minneighbors;  // a k-nearest search always returns min(k, nobs) >= 1 neighbours: the minimum never binds
+  if (kmax_d > KRIGE_MAXK || kmax_k > KRIGE_MAXK)
+    return set_err(ctx, GSP_E_UNSUPPORTED, "maxneighbors (after clamping to the number of data) must be <= 32");
+  for (long long j = 0; j < nd; ++j)
+    if (!std::isfinite(dvals[j])) return set_err(ctx, -6, "dvals must be finite (drop missing rows before the call)");
+  // centroids of the data nodes: the samples of the second Kriging (view(sdom, dinds), fftsim.jl:143)
+  std::vector<double> kc((size_t)nk * p->ndim);
+  std::vector<long long> k0((size_t)nk);
+  for (long long j = 0; j < nk; ++j) {
+    const long long pos = knodes[j] - 1;
+    long long e = n_inds > 0 ? inds[pos] - 1 : pos;
+    k0[(size_t)j] = pos;
+    for (int a = 0; a < p->ndim; ++a) {
+      const long long ia = e % p->dom.dims[a];
+      e /= p->dom.dims[a];
+      kc[(size_t)j * p->ndim + a] = p->dom.origin[a] + ((double)ia + 0.5) * p->dom.spacing[a];
+    }
+  }
+  p->cond = false;
+  for (auto& dptr : p->dev) {
+    FftDev* d = dptr.get();
+    CondDev& c = d->cond;
+    cudaSetDevice(d->dc->dev);
+    cudaStream_t st = d->dc->stream;
+    DevBuf dx, dv, kx, di, info;
+    GSP_CUDA_OK(ctx, dx.alloc(d->dc->dev, (size_t)nd * p->ndim * sizeof(double)));
+    GSP_CUDA_OK(ctx, dv.alloc(d->dc->dev, (size_t)nd * sizeof(double)));
+    GSP_CUDA_OK(ctx, kx.alloc(d->dc->dev, kc.size() * sizeof(double)));
+    GSP_CUDA_OK(ctx, info.alloc(d->dc->dev, sizeof(int)));
+    GSP_CUDA_OK(ctx, cudaMemcpyAsync(dx.p, dcoords, (size_t)nd * p->ndim * sizeof(double), cudaMemcpyHostToDevice, st));
+    GSP_CUDA_OK(ctx, cudaMemcpyAsync(dv.p, dvals, (size_t)nd * sizeof(double), cudaMemcpyHostToDevice, st));
+    GSP_CUDA_OK(ctx, cudaMemcpyAsync(kx.p, kc.data(), kc.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    GSP_CUDA_OK(ctx, cudaMemsetAsync(info.p, 0, sizeof(int), st));
+    if (n_inds > 0) {
+      GSP_CUDA_OK(ctx, di.alloc(d->dc->dev, (size_t)n_inds * sizeof(long long)));
+      GSP_CUDA_OK(ctx, cudaMemcpyAsync(di.p, inds, (size_t)n_inds * sizeof(long long), cudaMemcpyHostToDevice, st));
+    }
+    GSP_CUDA_OK(ctx, c.zbar.alloc(d->dc->dev, (size_t)n * sizeof(double)));
+    const size_t nslots = (size_t)((n + 31) / 32) * 32 * (size_t)kmax_k;  // tile-major weight table, whole tiles
+    GSP_CUDA_OK(ctx, c.lam.alloc(d->dc->dev, nslots * sizeof(double)));
+    GSP_CUDA_OK(ctx, c.nbr.alloc(d->dc->dev, nslots * sizeof(int)));
+    GSP_CUDA_OK(ctx, c.knodes.alloc(d->dc->dev, (size_t)nk * sizeof(long long)));
+    GSP_CUDA_OK(ctx, cudaMemcpyAsync(c.knodes.p, k0.data(), (size_t)nk * sizeof(long long), cudaMemcpyHostToDevice, st));
+    const unsigned blocks = (unsigned)((n + 127) / 128);
+    const long long* dinds = n_inds > 0 ? di.as<long long>() : nullptr;
+    {
+      ProfScope prof_("krige_weights", st);
+      // first Kriging: the data where they are -> zbar (fftsim.jl:99); nothing else of it is needed later
+      GSP_LAUNCH(krige_weights_kernel, dim3(blocks), dim3(128), 0, st, p->cov, p->dom, dinds, n, (int)kmax_d, (long long)nd,
+                 (const double*)dx.as<double>(), (const double*)dv.as<double>(), mu, c.zbar.as<double>(), (double*)nullptr, (int*)nullptr,
+                 info.as<int>());
+      g_launches++;
+    }
+    {
+      ProfScope prof_("krige_weights", st);
+      // second Kriging: samples at the centroids of the data nodes -> weight table, applied to every realization
+      GSP_LAUNCH(krige_weights_kernel, dim3(blocks), dim3(128), 0, st, p->cov, p->dom, dinds, n, (int)kmax_k, (long long)nk,
+                 (const double*)kx.as<double>(), (const double*)nullptr, mu, (double*)nullptr, c.lam.as<double>(), c.nbr.as<int>(), info.as<int>());
+      g_launches++;
+    }
+    GSP_CUDA_OK(ctx, cudaGetLastError());
+    int h_info = 0;
+    GSP_CUDA_OK(ctx, cudaMemcpyAsync(&h_info, info.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    GSP_CUDA_OK(ctx, cudaStreamSynchronize(st));
+    if (h_info != 0)
+      return set_err(ctx, GSP_E_STATE, "Kriging matrix of element " + std::to_string(h_info) +
+                                           " is not positive definite (coincident data locations?): cholesky would throw PosDefException");
+  }
+  p->cond = true;
+  p->cond_mu = mu;
+  p->cond_n = n;
+  p->cond_nk = nk;
+  p->cond_ninds = n_inds;
+  p->cond_kk = (int)kmax_k;
+  return GSP_OK;
+}
+
+extern "C" int gsp_fft_plan_condmean(gsp_fft_plan* p, double* zbar) {
+  if (!p) return -1;
+  gsp_ctx* ctx = p->ctx;
+  std::lock_guard<std::mutex> lk(p->mu);
+  if (!zbar) return set_err(ctx, -2, "zbar is NULL");
+  if (!p->cond) return set_err(ctx, GSP_E_STATE, "the plan is unconditional (call gsp_fft_plan_condition first)");
+  FftDev* d = p->dev[0].get();
+  cudaSetDevice(d->dc->dev);
+  GSP_CUDA_OK(ctx, cudaMemcpyAsync(zbar, d->cond.zbar.p, (size_t)p->cond_n * sizeof(double), cudaMemcpyDeviceToHost, d->dc->stream));
+  GSP_CUDA_OK(ctx, cudaStreamSynchronize(d->dc->stream));
+  return GSP_OK;
+}
+

@@ -224,12 +224,21 @@ def preprocess_fftsim(process: GaussianProcess, method: FFTSIM, init, domain, da
     grid = domain.parent()
     if not isinstance(grid, CartesianGrid):
         raise ValueError("FFTSIM requires a (view of a) CartesianGrid")
-    if data is not None:
-        raise NotImplementedError("conditional FFTSIM (Kriging of residuals, fftsim.jl:94-101,140-153) is not built yet; "
-                                  "use LUSIM for conditional simulation")
     lib = method.library or default_library()
     plan = _lib.FFTPlan(lib, f.flat(), grid.dims, grid.origin, grid.spacing)
-    return _FFTPre(plan, var, domain.parentindices(), float(f.sill()))
+    inds1 = domain.parentindices()
+    if data is not None:
+        # fftsim.jl:94-104: zbar = simple Kriging of the data (where they are) onto sdom; dinds = findall(mask[var]);
+        # the per-realization Kriging of fftsim.jl:140-149 is prepared here as a weight table (geometry only)
+        if method.neighborhood is not None or method.distance is not None:
+            raise NotImplementedError("FFTSIM conditioning on the GPU supports the default search only "
+                                      "(k nearest neighbours, Euclidean distance)")
+        vals = np.asarray(data[var], dtype=np.float64)
+        keep = ~np.isnan(vals)
+        dinds0 = np.flatnonzero(mask[var])
+        plan.condition(process.mean_of(0), data.domain.centroids()[keep], vals[keep], dinds0 + 1, inds1,
+                       minneighbors=method.minneighbors, maxneighbors=method.maxneighbors)
+    return _FFTPre(plan, var, inds1, float(f.sill()))
 
 
 def rand_fftsim(pre: _FFTPre, process: GaussianProcess, nreals: int, rng, seed: int, resident: bool = False) -> Dict[str, np.ndarray]:

@@ -150,6 +150,24 @@ int gsp_fft_sample(gsp_fft_plan* plan, int64_t R, const double* w, uint64_t seed
 int gsp_fft_sample_dev(gsp_fft_plan* plan, int64_t R, const double* w, uint64_t seed, int64_t first_real, double sill,
                        double mu, int64_t n_inds, const int64_t* inds_dev, double* out);
 
+/* FFTSIM conditioning by simple Kriging of residuals - src/simulation/field/fftsim.jl:94-101 (preprocess:
+ * zbar = fitpredict(Kriging(f, mu), data, sdom; minneighbors, maxneighbors, distance)) and :140-153 (randsingle:
+ * z = zbar + (zu - zbaru), zbaru = the same Kriging of the unconditional values at the data nodes view(sdom, dinds)).
+ * GeoStatsModels' neighbourhood search is restated: the `maxneighbors` (default 26) nearest samples by Euclidean distance,
+ * ties -> lower sample index; simple Kriging lambda = C^-1 c0 of those samples.  Both weight sets depend on geometry only
+ * and are computed here once; afterwards every gsp_fft_sample* call on the plan returns CONDITIONAL realizations.
+ *   mu                 the process mean (must be passed again, unchanged, to gsp_fft_sample*)
+ *   nd, dcoords, dvals the conditioning table: locations as given (dim x nd column-major) and values (fftsim.jl:99)
+ *   nk, knodes         dinds = findall(mask) (fftsim.jl:104): 1-based, ascending positions WITHIN the simulation domain
+ *   n_inds, inds       the simulation domain as a view of the grid (parentindices, NULL: whole grid); the same n_inds / inds
+ *                      must be passed to gsp_fft_sample*
+ * maxneighbors outside [1, #samples] means "all samples" (as fitpredict fixes it); at most 32 after that clamp.
+ * Returns GSP_E_STATE if a Kriging matrix is not positive definite (the reference's cholesky would throw). */
+int gsp_fft_plan_condition(gsp_fft_plan* plan, double mu, int32_t minneighbors, int32_t maxneighbors, int64_t nd, const double* dcoords,
+                           const double* dvals, int64_t nk, const int64_t* knodes, int64_t n_inds, const int64_t* inds);
+/* inspection: zbar (n = n_inds or prod(dims) doubles), the posterior mean of src/expectation/field/gaussian.jl:21-25 */
+int gsp_fft_plan_condmean(gsp_fft_plan* plan, double* zbar);
+
 /* ---- Device-resident ensembles: Ensemble(domain, reals; fetch) - src/ensembles.jl:10-16.
  * R realizations of n values each stay in HBM, sharded contiguously over the devices of the context (the same rule
  * gsp_*_sample uses); `fetch` is the reference's lazy per-realization hook (ensembles.jl:27-31) and the statistics

@@ -271,6 +271,79 @@ function randsingle(rng::AbstractRNG, process::GaussianProcess, method::FFTSIM_B
   end
 end
 
-export LUSIM_B200, FFTSIM_B200
+# ------------------------------------------------------------------------------------------------
+# Device-resident ensembles: Ensemble(domain, reals; fetch) (src/ensembles.jl:10-16) whose realizations stay in
+# HBM.  `reals` are lightweight handles, `fetch` downloads one realization (ensembles.jl:27-31), and the
+# statistics of ensembles.jl:42-52 are overloaded to run on the device instead of the O(n R) `ereduce` loops.
+struct DeviceReals
+  ptr::Ptr{Cvoid}          # gsp_ensemble*
+  var::Symbol
+  n::Int
+  R::Int
+end
+struct DeviceReal          # element of `reals`
+  parent::DeviceReals
+  r::Int                   # 0-based
+end
+Base.length(d::DeviceReals) = d.R
+Base.getindex(d::DeviceReals, i::Int) = DeviceReal(d, i - 1)
+Base.first(d::DeviceReals) = d[1]
+
+function fetchreal(x::DeviceReal)
+  z = Vector{Float64}(undef, x.parent.n)
+  check(context(), ccall((:gsp_ensemble_fetch, LIB), Cint, (Ptr{Cvoid}, Int64, Int64, Ptr{Float64}), x.parent.ptr, x.r, 1, z))
+  (; x.parent.var => z)
+end
+
+"""
+    rand_resident(process, domain, nreals; method=FFTSIM_B200(seed=0), data=nothing, init=NearestInit())
+
+Like `rand(process, domain, nreals; method)` (src/simulation/field.jl:72-91) but the ensemble stays on the GPUs.
+"""
+function rand_resident(process::GaussianProcess, domain, nreals::Int; method=FFTSIM_B200(), data=nothing, init=NearestInit())
+  rng = Random.default_rng()
+  pre = preprocess(rng, process, method, init, domain, data)
+  ctx = context()
+  n = nelements(domain)
+  ref = Ref{Ptr{Cvoid}}(C_NULL)
+  check(ctx, ccall((:gsp_ensemble_create, LIB), Cint, (Ptr{Cvoid}, Int64, Int64, Ptr{Ptr{Cvoid}}), ctx.ptr, n, nreals, ref))
+  seed = something(method.seed, rand(rng, UInt64))
+  if method isa FFTSIM_B200
+    check(ctx, ccall((:gsp_fft_sample_ensemble, LIB), Cint,
+                     (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, UInt64, Int64, Float64, Float64, Int64, Ptr{Int64}),
+                     pre.plan, ref[], C_NULL, seed, 0, Float64(ustrip(sill(process.func))), Float64(ustrip(process.mean)),
+                     length(pre.inds), isempty(pre.inds) ? C_NULL : pre.inds))
+    var = pre.var
+  else  # LUSIM_B200, first variable (a second variable gets its own ensemble with stream = 1 and rho)
+    check(ctx, ccall((:gsp_lu_sample_ensemble, LIB), Cint,
+                     (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, UInt64, Int32, Int64, Float64, Ptr{Float64}),
+                     pre.plans[1], ref[], C_NULL, seed, 0, 0, NaN, C_NULL))
+    var = pre.names[1]
+  end
+  reals = DeviceReals(ref[], var, n, nreals)
+  Ensemble(domain, reals; fetch=fetchreal)
+end
+
+function devstat(e::Ensemble{<:Any,DeviceReals}, f::Symbol, args...)
+  z = Vector{Float64}(undef, e.reals.n)
+  argt = (Ptr{Cvoid}, map(_ -> Float64, args)..., Ptr{Float64})
+  check(context(), ccall((f, LIB), Cint, argt, e.reals.ptr, map(Float64, args)..., z))
+  georef((; e.reals.var => z), e.domain)
+end
+Statistics.mean(e::Ensemble{<:Any,DeviceReals}) = devstat(e, :gsp_ensemble_mean)            # ensembles.jl:42
+Statistics.var(e::Ensemble{<:Any,DeviceReals}) = devstat(e, :gsp_ensemble_var)              # ensembles.jl:44
+cdf(e::Ensemble{<:Any,DeviceReals}, x::Number) = devstat(e, :gsp_ensemble_cdf, x)           # ensembles.jl:46
+ccdf(e::Ensemble{<:Any,DeviceReals}, x::Number) = devstat(e, :gsp_ensemble_ccdf, x)         # ensembles.jl:48
+function Statistics.quantile(e::Ensemble{<:Any,DeviceReals}, ps::AbstractVector)            # ensembles.jl:50-52
+  n = e.reals.n
+  q = Matrix{Float64}(undef, n, length(ps))
+  check(context(), ccall((:gsp_ensemble_quantile, LIB), Cint, (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}),
+                         e.reals.ptr, length(ps), Float64.(ps), q))
+  [georef((; e.reals.var => q[:, k]), e.domain) for k in eachindex(ps)]
+end
+Statistics.quantile(e::Ensemble{<:Any,DeviceReals}, p::Number) = first(quantile(e, [p]))
+release!(e::Ensemble{<:Any,DeviceReals}) = ccall((:gsp_ensemble_destroy, LIB), Cint, (Ptr{Cvoid},), e.reals.ptr)
+
+export LUSIM_B200, FFTSIM_B200, rand_resident, release!
 
 end # module

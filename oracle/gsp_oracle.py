@@ -13,6 +13,9 @@ a line-by-line *restatement* in NumPy/SciPy float64 of
 
   src/simulation/field/lusim.jl:38-175      (preprocess, randsingle, _marginalize, _rho, _lusim)
   src/simulation/field/fftsim.jl:54-92,109-139 (unconditional preprocess + randsingle)
+  src/simulation/field/fftsim.jl:94-101,140-153 (conditioning: simple Kriging of residuals; GeoStatsModels' k-nearest
+                                            neighbourhood search restated, ties -> lower sample index)
+  src/ensembles.jl:42-52                    (ensemble statistics; pinned by the reference's test/ensembles.jl:24-59)
   src/utils.jl:50-62                        (_pairwise: sill - gamma for variograms)
   src/processes/field.jl:43-58, src/initialization/nearest.jl:12-34 (dinds ordering)
 
@@ -259,6 +262,59 @@ def fftsim_sample(F: np.ndarray, w: np.ndarray, sill: float, mu: float,
     Z = np.sqrt(sill / s2) * Z + mu                      # fftsim.jl:132
     z = Z.reshape(-1)
     return z if inds is None else z[np.asarray(inds)]    # fftsim.jl:135
+
+
+# ---------------------------------------------------------------------------------------------- conditional FFTSIM
+def krige_neighbors_weights(structs, targets: np.ndarray, scoords: np.ndarray, maxneighbors: int):
+    """GeoStatsModels.fitpredict's neighbourhood path for Kriging(f, mu) = simple Kriging, restated (the package is not
+    vendored): per target the `maxneighbors` nearest samples (KNearestSearch, Euclidean, sorted by distance; ties -> lower
+    sample index, i.e. a stable sort), covariance matrix C of those samples factorised with Cholesky, weights C^-1 c0.
+    maxneighbors outside [1, nobs] is reset to nobs like fitpredict does.  Returns (nbr (n, k) int, lam (n, k))."""
+    targets = np.atleast_2d(np.asarray(targets, dtype=np.float64))
+    scoords = np.atleast_2d(np.asarray(scoords, dtype=np.float64))
+    ns = scoords.shape[0]
+    k = maxneighbors if 1 <= maxneighbors <= ns else ns
+    n = targets.shape[0]
+    nbr = np.zeros((n, k), dtype=np.int64)
+    lam = np.zeros((n, k))
+    for i in range(n):
+        d2 = ((scoords - targets[i]) ** 2).sum(axis=1)
+        idx = np.argsort(d2, kind="stable")[:k]
+        X = scoords[idx]
+        C = cov_eval(structs, (X[:, None, :] - X[None, :, :]).reshape(-1, X.shape[1])).reshape(k, k)
+        c0 = cov_eval(structs, X - targets[i])
+        cf = scipy.linalg.cho_factor(C, lower=True)
+        nbr[i], lam[i] = idx, scipy.linalg.cho_solve(cf, c0)
+    return nbr, lam
+
+
+class FFTCond:
+    """what fftsim.jl:94-106 keeps for conditional simulation: zbar and dinds (+ the restated weight table)"""
+
+    def __init__(self, zbar, knodes, nbr, lam, mu):
+        self.zbar, self.knodes, self.nbr, self.lam, self.mu = zbar, knodes, nbr, lam, mu
+
+
+def fftsim_condition(structs, dims, origin, spacing, dcoords, dvals, knodes0, mu: float, maxneighbors: int = 26,
+                     inds0: Optional[np.ndarray] = None) -> FFTCond:
+    """fftsim.jl:94-104.  dcoords/dvals: the conditioning table where it is; knodes0: dinds = findall(mask), 0-based positions
+    within the simulation domain sdom (= the grid, or its view `inds0`).  zbar = mu + sum lambda (z - mu) per element of sdom."""
+    cent = grid_centroids(dims, origin, spacing)
+    tg = cent if inds0 is None else cent[np.asarray(inds0)]
+    nbr, lam = krige_neighbors_weights(structs, tg, dcoords, maxneighbors)
+    dvals = np.asarray(dvals, dtype=np.float64)
+    zbar = mu + (lam * (dvals[nbr] - mu)).sum(axis=1)
+    knodes0 = np.asarray(knodes0)
+    nbr2, lam2 = krige_neighbors_weights(structs, tg, tg[knodes0], maxneighbors)  # samples at the data nodes' centroids (:143)
+    return FFTCond(zbar, knodes0, nbr2, lam2, mu)
+
+
+def fftsim_sample_conditional(F: np.ndarray, w: np.ndarray, sill: float, cond: FFTCond, inds0: Optional[np.ndarray] = None) -> np.ndarray:
+    """fftsim.jl:124-153: unconditional realization zu, Kriging of zu[dinds] (same neighbourhoods, same weights), z = zbar + (zu - zbaru)."""
+    zu = fftsim_sample(F, w, sill, cond.mu, inds0)
+    zk = zu[cond.knodes]
+    zbaru = cond.mu + (cond.lam * (zk[cond.nbr] - cond.mu)).sum(axis=1)
+    return cond.zbar + (zu - zbaru)
 
 
 # ---------------------------------------------------------------------------------------------- ensemble statistics

@@ -28,6 +28,7 @@ struct double2 { double x, y; };
 struct int2 { int x, y; };
 struct uint2 { unsigned x, y; };
 struct uint4 { unsigned x, y, z, w; };
+struct int4 { int x, y, z, w; };
 struct alignas(16) longlong2 { long long x, y; };
 static inline double2 make_double2(double x, double y) { return double2{x, y}; }
 static inline int2 make_int2(int x, int y) { return int2{x, y}; }

@@ -395,3 +395,56 @@ def test_ensemble_resident_simulation_gpu(gpu_lib):
     med = ens.quantile([0.5])[0]
     assert np.abs(med[sinds] - d2).max() < 6.0 * np.sqrt(cvar.max() / R)
     ens.close(), lp.close()
+
+
+# ------------------------------------------------------------------ §8f rank 2: conditional FFTSIM (fftsim.jl:94-101,140-153)
+@pytest.mark.parametrize("dims,nd,kind,maxn,view", [((64, 64), 100, O.EXPONENTIAL, 26, False), ((32, 32, 16), 80, O.SPHERICAL, 26, False),
+                                                    ((48, 40), 60, O.CUBIC, 8, True), ((40, 40), 12, O.SPHERICAL, 26, False)])
+def test_fftsim_conditional_parity(gpu_lib, dims, nd, kind, maxn, view):
+    # (no GaussianCovariance here: its Kriging matrices are numerically singular, kappa ~ 1e12+, so the weights of two correct
+    #  implementations agree to ~1e-6 only - the same caveat SURVEY §7 records for LUSIM + Gaussian)
+    rng = np.random.default_rng(nd)
+    nd_ = len(dims)
+    st = iso(kind, 1.2, 6.0, nd_)
+    N = int(np.prod(dims))
+    mu = 0.4
+    inds0 = np.sort(rng.choice(N, N // 2, replace=False)) if view else None
+    cent = O.grid_centroids(dims, [0.0] * nd_, [1.0] * nd_)
+    tg = cent if inds0 is None else cent[inds0]
+    knodes0 = np.sort(rng.choice(tg.shape[0], nd, replace=False))
+    dcoords = tg[knodes0] + rng.uniform(-0.4, 0.4, (nd, nd_))
+    dvals = rng.standard_normal(nd) + mu
+    plan = gsp.FFTPlan(gpu_lib, st, dims, [0.0] * nd_, [1.0] * nd_)
+    inds1 = None if inds0 is None else inds0 + 1
+    plan.condition(mu, dcoords, dvals, knodes0 + 1, inds1, maxneighbors=maxn)
+    cond = O.fftsim_condition(ostructs(st), dims, [0.0] * nd_, [1.0] * nd_, dcoords, dvals, knodes0, mu, maxn, inds0)
+    assert relerr(plan.condmean(), cond.zbar) < 1e-10
+    Fo = O.fftsim_preprocess(ostructs(st), dims, [0.0] * nd_, [1.0] * nd_)
+    w = rng.random((5, N))
+    Z = plan.sample(5, w, sill=1.2, mu=mu, inds1=inds1)  # 5 realizations: one full chunk of 4 lanes + a remainder (3-D)
+    for r in range(5):
+        assert relerr(Z[r], O.fftsim_sample_conditional(Fo, w[r], 1.2, cond, inds0)) < TOL
+    plan.close()
+
+
+def test_fftsim_conditional_properties_large(gpu_lib):
+    """128^3 grid, 500 data at node centroids, default 26 neighbours: data honoured, ensemble mean -> zbar, far field unconditional"""
+    dims = (128, 128, 128)
+    N = 128 ** 3
+    rng = np.random.default_rng(17)
+    st = aniso3(O.SPHERICAL, 1.0, (20.0, 10.0, 5.0), 30.0)
+    knodes0 = np.sort(rng.choice(N, 500, replace=False))
+    cent_k = np.stack([(knodes0 % 128) + 0.5, ((knodes0 // 128) % 128) + 0.5, (knodes0 // 16384) + 0.5], axis=1)
+    dvals = rng.standard_normal(500)
+    plan = gsp.FFTPlan(gpu_lib, st, dims, [0.0] * 3, [1.0] * 3)
+    plan.condition(0.0, cent_k, dvals, knodes0 + 1)
+    zbar = plan.condmean()
+    assert np.abs(zbar[knodes0] - dvals).max() < 1e-10            # simple Kriging interpolates the data
+    ens = plan.sample_ensemble(48, None, seed=9, sill=1.0, mu=0.0)
+    Z3 = ens.fetch(0, 3)
+    assert np.abs(Z3[:, knodes0] - dvals[None, :]).max() < 1e-10  # every realization honours the data
+    mean, var = ens.mean(), ens.var()
+    assert np.abs(mean - zbar).max() < 6.0 / np.sqrt(48) + 0.05     # E[z] = zbar
+    assert var[knodes0].max() < 1e-18                             # no spread at the data
+    assert 0.8 < var.mean() < 1.05                                # most nodes are farther than a range from any datum
+    ens.close(), plan.close()

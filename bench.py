@@ -287,6 +287,22 @@ def run_gpu(args):
     e2e_value = Re * world * e2e_steps / float(te[0])
     e2e_match = bool(torch.equal(hz[0], z[0].cpu()))
 
+    # the same call with w = NULL: noise from the on-device counter RNG, as `rand(process, domain, n)` without an injected
+    # array would run (fields still go back to pinned host memory); reported beside the injected-noise figure, not instead of it
+    def e2e_rng_step():
+        lib.check(lib.lib.gsp_fft_sample(plan.h, Re, None, 4, r0, 1.0, 0.0, 0, None, hz.data_ptr()))
+
+    e2e_rng_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_rng_step()
+    barrier()
+    tr = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tr, op=dist.ReduceOp.MAX)
+    e2e_rng_value = Re * world * e2e_steps / float(tr[0])
+
     # ---- resident ensemble + statistics in HBM: what a user who wants mean / variance / quantile maps pays
     ens_line = None
     if rank == 0 and not args.skip_ensemble:
@@ -343,7 +359,10 @@ def run_gpu(args):
             "device_ms_per_step": dev_max / args.steps * 1e3,
             "e2e": {"value": e2e_value, "unit": "realizations/s", "h2d_bytes_per_step": 8 * N * Re, "d2h_bytes_per_step": 8 * N * Re,
                     "reals_per_step": Re, "steps": e2e_steps, "matches_device_path": e2e_match,
-                    "api": "gsp_fft_sample (host pointers, pinned), 3-stream H2D/compute/D2H pipeline"},
+                    "api": "gsp_fft_sample (host pointers, pinned), 3-stream H2D/compute/D2H pipeline",
+                    "device_rng_variant": {"value": e2e_rng_value, "unit": "realizations/s", "h2d_bytes_per_step": 0,
+                                           "d2h_bytes_per_step": 8 * N * Re,
+                                           "note": "same call with w = NULL (on-device Philox noise); PCIe carries only the fields"}},
             "gpu_launches": int(launches), "roofline": roof, "clocks": clocks,
             "invariants_ok": ok_invariants, "field_mean": mean0, "field_var": var0,
         }
@@ -362,9 +381,14 @@ def run_gpu(args):
 
 
 def bench_ensemble(lib, plan, R, N, r0):
-    """R realizations (device RNG) simulated into a device-resident ensemble, then mean, variance, cdf and three quantile maps:
-    only the n-vectors of results cross PCIe (ensembles.jl:42-52 run in HBM instead of O(n R) host loops)."""
+    """R realizations (device RNG) simulated into a device-resident ensemble, then mean, variance, cdf and three quantile maps
+    written into PINNED host buffers: only the n-vectors of results cross PCIe (ensembles.jl:42-52 run in HBM instead of O(n R)
+    host loops).  Timed through the C ABI (gsp_fft_sample_ensemble, gsp_ensemble_*)."""
     import torch
+
+    L = lib.lib
+    hbuf = torch.empty((3, N), dtype=torch.float64).pin_memory()
+    ps = np.array([0.1, 0.5, 0.9])
 
     def timed(fn):
         torch.cuda.synchronize()
@@ -375,25 +399,30 @@ def bench_ensemble(lib, plan, R, N, r0):
 
     plan.sample_ensemble(4, None, seed=4, first_real=r0).close()  # warm-up
     ens, t_sim = timed(lambda: plan.sample_ensemble(R, None, seed=4, first_real=r0))
-    ens.mean()  # warm-up of the statistics kernels
+    lib.check(L.gsp_ensemble_mean(ens.h, hbuf[0].data_ptr()))  # warm-up of the statistics kernels
     lib.profile_enable(True)
-    mean, t_mean = timed(ens.mean)
-    var, t_var = timed(ens.var)
-    cdf, t_cdf = timed(lambda: ens.cdf(0.0))
-    q, t_q = timed(lambda: ens.quantile([0.1, 0.5, 0.9]))
+    _, t_mean = timed(lambda: lib.check(L.gsp_ensemble_mean(ens.h, hbuf[0].data_ptr())))
+    mean_abs_max = float(hbuf[0].abs().max())
+    _, t_var = timed(lambda: lib.check(L.gsp_ensemble_var(ens.h, hbuf[1].data_ptr())))
+    var_mean = float(hbuf[1].mean())
+    _, t_cdf = timed(lambda: lib.check(L.gsp_ensemble_cdf(ens.h, 0.0, hbuf[2].data_ptr())))
+    cdf_mean = float(hbuf[2].mean())
+    _, t_q = timed(lambda: lib.check(L.gsp_ensemble_quantile(ens.h, 3, ps.ctypes.data, hbuf.data_ptr())))
+    med_abs_mean = float(hbuf[1].abs().mean())
     prof = lib.profile_read()
     lib.profile_enable(False)
     ens.close()
     pk = peaks()
     bytes_pass = 8.0 * N * R
-    out = {"workload": f"{R} FFTSIM 256^3 realizations (on-device Philox noise) resident in HBM; mean, var, cdf(0), quantile([.1,.5,.9]) per node",
+    out = {"workload": f"{R} FFTSIM 256^3 realizations (on-device Philox noise) resident in HBM; mean, var, cdf(0), quantile([.1,.5,.9]) "
+                       "per node into pinned host buffers",
            "simulate_s": t_sim, "realizations_per_s_simulate_resident": R / t_sim,
            "mean_s": t_mean, "var_s": t_var, "cdf_s": t_cdf, "quantile3_s": t_q,
            "realizations_per_s_simulate_plus_mean_var": R / (t_sim + t_mean + t_var),
+           "realizations_per_s_simulate_plus_all_statistics": R / (t_sim + t_mean + t_var + t_cdf + t_q),
            "d2h_bytes_per_statistic": 8 * N, "d2h_bytes_if_realizations_were_downloaded": 8 * N * R,
            "kernel_ms": {k: round(v["ms"] / v["launches"], 3) for k, v in prof.items()},
-           "checks": {"mean_abs_max": float(np.abs(mean).max()), "var_mean": float(var.mean()), "cdf0_mean": float(cdf.mean()),
-                      "median_abs_mean": float(np.abs(q[1]).mean())}}
+           "checks": {"mean_abs_max": mean_abs_max, "var_mean": var_mean, "cdf0_mean": cdf_mean, "median_abs_mean": med_abs_mean}}
     for k in ("ens_moments", "ens_count"):
         if k in prof:
             gbs = bytes_pass / (prof[k]["ms"] / prof[k]["launches"]) / 1e6

@@ -400,13 +400,14 @@ class FFTPlan:
         return Z
 
     def sample_ensemble(self, R: int, w: Optional[np.ndarray] = None, seed: int = 0, first_real: int = 0, sill: float = 1.0,
-                        mu: float = 0.0, inds1: Optional[np.ndarray] = None) -> "DeviceEnsemble":
-        """like `sample`, but the realizations stay on the devices"""
+                        mu: float = 0.0, inds1: Optional[np.ndarray] = None, ens: Optional["DeviceEnsemble"] = None) -> "DeviceEnsemble":
+        """like `sample`, but the realizations stay on the devices (`ens`: refill an existing ensemble of the same shape)"""
         if w is not None:
             w = np.ascontiguousarray(w, dtype=np.float64).reshape(R, self.N)
         n_inds = 0 if inds1 is None else len(inds1)
         inds1 = None if inds1 is None else np.ascontiguousarray(inds1, dtype=np.int64)
-        ens = DeviceEnsemble(self.lib, n_inds if n_inds else self.N, R)
+        if ens is None:
+            ens = DeviceEnsemble(self.lib, n_inds if n_inds else self.N, R)
         rc = self.lib.lib.gsp_fft_sample_ensemble(self.h, ens.h, _ptr(w), seed, first_real, float(sill), float(mu), n_inds, _ptr(inds1))
         self.lib.check(rc)
         return ens

@@ -367,6 +367,9 @@ bool g_force_generic = false;  // GSP_FFT_GENERIC=1: use the mixed-radix kernels
 // Per-kernel launch setup, done once per device: opt in to the dynamic shared memory and ask the occupancy API how many CTAs
 // are resident per SM (at most 4 are used).  Both calls cost microseconds of host time, which the slab schedules (dozens of
 // short launches per realization) cannot afford per launch.  SLOT is a distinct static per kernel instantiation.
+#ifndef GSP_MAX_PER_SM
+#define GSP_MAX_PER_SM 4
+#endif
 struct KernelSetup {
   int per_sm[32] = {};
   cudaError_t err = cudaSuccess;
@@ -380,7 +383,7 @@ struct KernelSetup {
       if (err != cudaSuccess) return 0;
       int n = 1;
       if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kfn, threads, smem) != cudaSuccess || n < 1) n = 1;
-      per_sm[dev] = n > 4 ? 4 : n;
+      per_sm[dev] = n > GSP_MAX_PER_SM ? GSP_MAX_PER_SM : n;
     }
     return per_sm[dev];
   }
@@ -394,18 +397,24 @@ inline unsigned persistent_grid(int per_sm, int sms, long long items) {
   return (unsigned)g;
 }
 
-template <int HN>
-cudaError_t launch_p2_xfwd(cudaStream_t st, int sms, const double* in, cplx* H, const cplx* tw, const cplx* stw, long long nrows) {
+template <int HN, bool RNG>
+cudaError_t launch_p2_xfwd_t(cudaStream_t st, int sms, const double* in, cplx* H, const cplx* tw, const cplx* stw, long long nrows, const XRng& rng) {
   using C = XCfg<HN, false>;
-  auto kfn = p2_xfwd_kernel<HN>;
+  auto kfn = p2_xfwd_kernel<HN, RNG>;
   static KernelSetup ks;
   const int per_sm = ks.get(kfn, C::THREADS, C::SMEM);
   if (per_sm == 0) return ks.err;
   const long long ngroups = (nrows + C::ROWS - 1) / C::ROWS;
-  ProfScope prof_("fft_xpass_fwd", st);
-  GSP_LAUNCH(kfn, dim3(persistent_grid(per_sm, sms, ngroups)), dim3(C::THREADS), C::SMEM, st, in, H, tw, stw, nrows);
+  ProfScope prof_(RNG ? "fft_xpass_fwd_rng" : "fft_xpass_fwd", st);
+  GSP_LAUNCH(kfn, dim3(persistent_grid(per_sm, sms, ngroups)), dim3(C::THREADS), C::SMEM, st, in, H, tw, stw, nrows, rng);
   g_launches++;
   return cudaGetLastError();
+}
+
+// in == nullptr: the noise comes from the counter RNG inside the kernel (rng describes which realization / rows)
+template <int HN>
+cudaError_t launch_p2_xfwd(cudaStream_t st, int sms, const double* in, cplx* H, const cplx* tw, const cplx* stw, long long nrows, const XRng& rng) {
+  return in ? launch_p2_xfwd_t<HN, false>(st, sms, in, H, tw, stw, nrows, rng) : launch_p2_xfwd_t<HN, true>(st, sms, in, H, tw, stw, nrows, rng);
 }
 
 template <int HN>
@@ -584,11 +593,15 @@ int setup_axes(gsp_ctx* ctx, gsp_fft_plan* p, FftDev* d) {
 
 // x passes over the rows [row0, row0 + nrows) of the lane's work spectrum (`in` / `out` point at the first of those rows).
 // 1-D / 2-D grids: a batch of realizations, stored back to back, is simply more rows of ONE launch.
-cudaError_t run_xfwd(FftDev* d, gsp_fft_plan* p, const Lane& L, const double* in, long long row0, long long nrows) {
+// in == nullptr (fast x axis only): noise of realization rng.first_real (+ row / rows_per_real) generated inside the kernel
+cudaError_t run_xfwd(FftDev* d, gsp_fft_plan* p, const Lane& L, const double* in, long long row0, long long nrows, XRng rng = XRng{}) {
   const AxisPlan& a = d->ax[0];
   cplx* H = L.H + row0 * p->hx;
+  rng.row_base = row0;
+  rng.rows_per_real = p->dims[1] * p->dims[2];
+  if (!in && !a.fast) return cudaErrorInvalidValue;
   if (a.fast) {
-#define GSP_CALL(HN) launch_p2_xfwd<HN>(L.st, d->dc->sms, in, H, a.lp.tw, d->stw_fwd.as<cplx>(), nrows)
+#define GSP_CALL(HN) launch_p2_xfwd<HN>(L.st, d->dc->sms, in, H, a.lp.tw, d->stw_fwd.as<cplx>(), nrows, rng)
     GSP_P2_SWITCH((int)p->dims[0] / 2, GSP_CALL)
 #undef GSP_CALL
   }
@@ -688,7 +701,9 @@ cudaError_t forward_all(FftDev* d, gsp_fft_plan* p, const double* in) {
 }
 
 // one realization on one lane: real noise (device) -> real field (device), full grid
-cudaError_t realization(FftDev* d, gsp_fft_plan* p, const Lane& L, const double* w, double* out, double s, double scale_out, double mu) {
+// w == nullptr: the forward x pass draws realization rng.first_real from the counter RNG itself (fast x axis, no fused planes)
+cudaError_t realization(FftDev* d, gsp_fft_plan* p, const Lane& L, const double* w, double* out, double s, double scale_out, double mu,
+                        XRng rng = XRng{}) {
   const double* Fh = d->Fh.as<double>();
   const long long nrows = p->dims[1] * p->dims[2];
   if (d->fused_xy) {
@@ -708,7 +723,7 @@ cudaError_t realization(FftDev* d, gsp_fft_plan* p, const Lane& L, const double*
       Sub sub;
       sub.o0 = z0;
       sub.o1 = z1;
-      e = run_xfwd(d, p, L, w + z0 * ny * p->dims[0], z0 * ny, (z1 - z0) * ny);
+      e = run_xfwd(d, p, L, w ? w + z0 * ny * p->dims[0] : nullptr, z0 * ny, (z1 - z0) * ny, rng);
       if (e == cudaSuccess) e = run_strided(d, p, L, 1, PASS_FWD, nullptr, 0.0, 1, sub);
     }
     if (e == cudaSuccess) e = run_strided(d, p, L, 2, PASS_FWD | PASS_MUL | PASS_INV, Fh, s);
@@ -722,7 +737,7 @@ cudaError_t realization(FftDev* d, gsp_fft_plan* p, const Lane& L, const double*
     }
     return e;
   }
-  e = run_xfwd(d, p, L, w, 0, nrows);
+  e = run_xfwd(d, p, L, w, 0, nrows, rng);
   if (e != cudaSuccess) return e;
   const int last = p->ndim - 1;
   if (last == 0) {
@@ -755,7 +770,8 @@ cudaError_t realization(FftDev* d, gsp_fft_plan* p, const Lane& L, const double*
 
 // `nb` realizations at once (1-D / 2-D grids: one launch per pass for the whole batch; 3-D: one realization per lane, the lanes
 // run concurrently and join the compute stream at the end)
-cudaError_t realization_batch(FftDev* d, gsp_fft_plan* p, const double* w, double* out, long long nb, double s, double scale_out, double mu) {
+cudaError_t realization_batch(FftDev* d, gsp_fft_plan* p, const double* w, double* out, long long nb, double s, double scale_out, double mu,
+                              XRng rng = XRng{}) {
   const Lane& L0 = *d->lanes[0];
   if (p->ndim == 3 || nb == 1) {
     const long long nl = (long long)d->lanes.size() < nb ? (long long)d->lanes.size() : nb;
@@ -764,8 +780,11 @@ cudaError_t realization_batch(FftDev* d, gsp_fft_plan* p, const double* w, doubl
       e = cudaEventRecord(d->ev_fork, L0.st);
       for (long long l = 1; l < nl && e == cudaSuccess; ++l) e = cudaStreamWaitEvent(d->lanes[l]->st, d->ev_fork, 0);
     }
-    for (long long r = 0; r < nb && e == cudaSuccess; ++r)
-      e = realization(d, p, *d->lanes[r % nl], w + r * p->N, out + r * p->N, s, scale_out, mu);
+    for (long long r = 0; r < nb && e == cudaSuccess; ++r) {
+      XRng rr = rng;
+      rr.first_real = rng.first_real + r;
+      e = realization(d, p, *d->lanes[r % nl], w ? w + r * p->N : nullptr, out + r * p->N, s, scale_out, mu, rr);
+    }
     for (long long l = 1; l < nl; ++l) {  // always join, also after an error: nothing may outlive the call on a side stream
       cudaError_t e2 = cudaEventRecord(d->lanes[l]->done, d->lanes[l]->st);
       if (e2 == cudaSuccess) e2 = cudaStreamWaitEvent(L0.st, d->lanes[l]->done, 0);
@@ -775,7 +794,7 @@ cudaError_t realization_batch(FftDev* d, gsp_fft_plan* p, const double* w, doubl
   }
   const double* Fh = d->Fh.as<double>();
   const long long nrows = p->dims[1] * p->dims[2] * nb;
-  cudaError_t e = run_xfwd(d, p, L0, w, 0, nrows);
+  cudaError_t e = run_xfwd(d, p, L0, w, 0, nrows, rng);
   if (e != cudaSuccess) return e;
   if (p->ndim == 1) {
     const long long total = p->nh * nb;
@@ -1043,6 +1062,16 @@ int check_cond_args(gsp_fft_plan* p, double mu, long long n_inds) {
   return GSP_OK;
 }
 
+// GSP_FFT_FUSED_RNG=0: draw the noise into a scratch array first (rng_fill_kernel) instead of inside the forward x pass (A/B runs)
+bool fused_rng_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* env = getenv("GSP_FFT_FUSED_RNG");
+    on = (env && env[0] == '0') ? 0 : 1;
+  }
+  return on != 0;
+}
+
 // sample R realizations on one device; w/out/inds are DEVICE pointers (w may be NULL => RNG into scratch)
 int sample_on_device(gsp_fft_plan* p, FftDev* d, long long R, const double* w, unsigned long long seed, long long first_real,
                      double sill, double mu, long long n_inds, const long long* inds_dev, double* out, DevBuf* scratch_w,
@@ -1053,8 +1082,14 @@ int sample_on_device(gsp_fft_plan* p, FftDev* d, long long R, const double* w, u
   for (long long r = 0; r < R; r += rb) {
     const long long nb = (R - r < rb) ? R - r : rb;
     const double* wr;
+    XRng rng{};
     if (w) {
       wr = w + r * p->N;
+    } else if (d->ax[0].fast && !d->fused_xy && fused_rng_enabled()) {
+      // no noise array at all: the forward x pass generates realization first_real + r (+ batch offset) in its registers
+      wr = nullptr;
+      rng.seed = seed;
+      rng.first_real = first_real + r;
     } else {
       if (!scratch_w->p) GSP_CUDA_OK(ctx, scratch_w->alloc(d->dc->dev, (size_t)p->N * rb * sizeof(double)));
       GSP_CUDA_OK(ctx, launch_rng_fill(d->dc->stream, d->dc->sms, scratch_w->as<double>(), p->N, p->N, nb, seed, 0,
@@ -1063,7 +1098,7 @@ int sample_on_device(gsp_fft_plan* p, FftDev* d, long long R, const double* w, u
     }
     if (n_inds > 0) {
       if (!scratch_z->p) GSP_CUDA_OK(ctx, scratch_z->alloc(d->dc->dev, (size_t)p->N * rb * sizeof(double)));
-      GSP_CUDA_OK(ctx, realization_batch(d, p, wr, scratch_z->as<double>(), nb, s, 1.0, mu));
+      GSP_CUDA_OK(ctx, realization_batch(d, p, wr, scratch_z->as<double>(), nb, s, 1.0, mu, rng));
       long long blocks = (n_inds * nb + 255) / 256;
       if (blocks > (long long)d->dc->sms * 8) blocks = (long long)d->dc->sms * 8;
       GSP_LAUNCH(gather_kernel, dim3((unsigned)blocks), dim3(256), 0, d->dc->stream, scratch_z->as<double>(), p->N, inds_dev, n_inds,
@@ -1071,7 +1106,7 @@ int sample_on_device(gsp_fft_plan* p, FftDev* d, long long R, const double* w, u
       g_launches++;
       GSP_CUDA_OK(ctx, cudaGetLastError());
     } else {
-      GSP_CUDA_OK(ctx, realization_batch(d, p, wr, out + r * p->N, nb, s, 1.0, mu));
+      GSP_CUDA_OK(ctx, realization_batch(d, p, wr, out + r * p->N, nb, s, 1.0, mu, rng));
     }
   }
   // conditioning runs over larger chunks than the simulation: a node's weight row (12 kk bytes) is read once per chunk

@@ -11,6 +11,7 @@
 // pad the row by one element per R0 to break the stride-R0 conflict of the first exchange.
 #pragma once
 #include "fft_kernels.cuh"
+#include "rng.cuh"
 
 namespace gsp {
 
@@ -170,7 +171,10 @@ struct StridedCfg {
   static constexpr bool STW_OK = (size_t)(STWF + STWI) * sizeof(cplx) <= 40 * 1024;
   static constexpr size_t TW_BYTES = ((size_t)(STW_OK ? STWF + STWI : N) * sizeof(cplx) + 127) / 128 * 128;
   static constexpr size_t SMEM = TW_BYTES + STAGES * (IN_BYTES + F_BYTES) + 2 * sizeof(mbar_t) + 16;
-  static constexpr int MINB = (STAGES == 1 && THREADS <= 128) ? 4 : 1;  // register cap for 4 CTAs per SM
+#ifndef GSP_STRIDED_MINB
+#define GSP_STRIDED_MINB 4
+#endif
+  static constexpr int MINB = (STAGES == 1 && THREADS <= 128) ? GSP_STRIDED_MINB : 1;  // register cap for that many CTAs per SM
 };
 
 template <int N, int B, int FLAGS, int STAGES>
@@ -326,10 +330,20 @@ struct XCfg {
   static constexpr int MINB = (STAGES == 1 && THREADS <= 128) ? 4 : ((THREADS <= 128) ? GSP_X_MINB2 : 1);
 };
 
-template <int HN>
+// noise source of the forward x pass when no array is injected: uniforms from the counter RNG (rng.cuh), generated straight into
+// the transform's registers - the 8 N bytes of noise are never written to or read from HBM.  Element pair p of realization
+// `real` is Philox(seed, stream 0, real, p), exactly what rng_fill_kernel would have stored at in[2p], in[2p + 1].
+struct XRng {
+  unsigned long long seed;
+  long long first_real;  // realization of row `row_base`
+  long long row_base;    // index, within that realization sequence, of the first row of this launch
+  long long rows_per_real;
+};
+
+template <int HN, bool RNG>
 __global__ void __launch_bounds__(XCfg<HN, false>::THREADS, XCfg<HN, false>::MINB) p2_xfwd_kernel(const double* __restrict__ in, cplx* __restrict__ H,
                                                                           const cplx* __restrict__ twg, const cplx* __restrict__ stwg,
-                                                                          long long nrows) {
+                                                                          long long nrows, XRng rng) {
   using C = XCfg<HN, false>;
   constexpr int NX = C::NX, HX = C::HX, SL = C::SL, TPL = C::TPL;
   GSP_DYN_SMEM(smem);
@@ -348,7 +362,7 @@ __global__ void __launch_bounds__(XCfg<HN, false>::THREADS, XCfg<HN, false>::MIN
   __syncthreads();
   const long long ngroups = (nrows + C::ROWS - 1) / C::ROWS;
   auto issue = [&](long long g, int sg) {
-    if (tid == 0) {
+    if (!RNG && tid == 0) {
       fence_proxy_async();  // see p2_strided_kernel: generic-proxy accesses of the stage precede the async-proxy fill
       const long long r0 = g * C::ROWS;
       const long long nv = (nrows - r0 < C::ROWS) ? nrows - r0 : C::ROWS;
@@ -372,13 +386,28 @@ __global__ void __launch_bounds__(XCfg<HN, false>::THREADS, XCfg<HN, false>::MIN
     const bool valid = row < nrows;
     cplx* ex = reinterpret_cast<cplx*>(stage0 + (size_t)cur * C::STAGE_BYTES);  // overlays the input once it is in registers
     const cplx* src = ex + (size_t)rl * HN;
-    mbar_wait(&full[cur], (uint32_t)(C::STAGES == 2 ? ((it >> 1) & 1) : (it & 1)));
     constexpr int R0 = p2_radix(HN, false, 0);
     cplx v[SL];
+    if constexpr (RNG) {
+      const long long grow = rng.row_base + row;
+      const long long rr = grow / rng.rows_per_real;
+      const unsigned long long real = (unsigned long long)(rng.first_real + rr);
+      const unsigned long long pair0 = (unsigned long long)(grow - rr * rng.rows_per_real) * HN;
 #pragma unroll
-    for (int q = 0; q < SL / R0; ++q)
+      for (int q = 0; q < SL / R0; ++q)
 #pragma unroll
-      for (int r = 0; r < R0; ++r) v[q * R0 + r] = src[p2_in_pos<HN, false, 0>(t, q, r)];
+        for (int r = 0; r < R0; ++r) {
+          double u0 = 0.0, u1 = 0.0;
+          if (valid) philox_uniform2(rng.seed, 0u, real, pair0 + (unsigned long long)p2_in_pos<HN, false, 0>(t, q, r), u0, u1);
+          v[q * R0 + r] = cplx{u0, u1};
+        }
+    } else {
+      mbar_wait(&full[cur], (uint32_t)(C::STAGES == 2 ? ((it >> 1) & 1) : (it & 1)));
+#pragma unroll
+      for (int q = 0; q < SL / R0; ++q)
+#pragma unroll
+        for (int r = 0; r < R0; ++r) v[q * R0 + r] = src[p2_in_pos<HN, false, 0>(t, q, r)];
+    }
     p2_fft<HN, false, C::STW_OK ? 0 : 2>(v, t, ex, lay, C::STW_OK ? stw : tw);
     // untangle: X[f] = E + w^f * O with E = (Z[f] + conj Z[h-f])/2, O = -i (Z[f] - conj Z[h-f])/2
     constexpr int RI = p2_radix(HN, true, 0);

@@ -15,8 +15,9 @@ z = torch.empty((R, N), dtype=torch.float64, device=dev)
 plan = gsp.FFTPlan(lib, st, dims, [0.0] * 3, [1.0] * 3)
 if os.environ.get("ONE_PROFILE"):
     lib.profile_enable(True)
+wp = None if os.environ.get("ONE_RNG") else w.data_ptr()
 for _ in range(int(os.environ.get("ONE_REPS", "2"))):
-    plan.sample_dev(R, w.data_ptr(), 0, 0, 1.0, 0.0, 0, None, z.data_ptr())
+    plan.sample_dev(R, wp, 0, 0, 1.0, 0.0, 0, None, z.data_ptr())
 print("ms/real", lib.last_sample_ms() / R)
 if os.environ.get("ONE_PROFILE"):
     for k, v in lib.profile_read().items():

@@ -80,7 +80,7 @@ int make_cov_dev(gsp_ctx* ctx, const gsp_cov_model* cov, int dim, int argpos, Co
   out->dim = dim;
   for (int s = 0; s < cov->nstruct; ++s) {
     const gsp_structure& st = cov->structs[s];
-    if (st.kind < GSP_NUGGET || st.kind > GSP_PENTASPHERICAL) return set_err(ctx, -argpos, "unknown structure kind");
+    if (st.kind < GSP_NUGGET || st.kind > GSP_CIRCULAR) return set_err(ctx, -argpos, "unknown structure kind");
     if (!(st.sill >= 0.0)) return set_err(ctx, -argpos, "structure sill must be >= 0");
     out->kind[s] = st.kind;
     out->sill[s] = st.sill;

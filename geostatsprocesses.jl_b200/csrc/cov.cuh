@@ -63,6 +63,14 @@ GSP_DEV double corr_eval(int kind, double u) {
       double u2 = u * u, u3 = u2 * u, u5 = u3 * u2;
       return 1.0 - (1.875 * u - 1.25 * u3 + 0.375 * u5);
     }
+    case GSP_SINEHOLE: {
+      if (u == 0.0) return 1.0;
+      return sinpi(u) / (3.141592653589793238462643383279502884 * u);
+    }
+    case GSP_CIRCULAR: {
+      if (u >= 1.0) return 0.0;
+      return 0.636619772367581343075535053490057448 * (acos(u) - u * sqrt(1.0 - u * u));
+    }
     default:
       return 0.0;
   }

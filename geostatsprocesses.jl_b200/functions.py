@@ -12,9 +12,9 @@ from typing import List, Optional, Sequence
 
 import numpy as np
 
-NUGGET, SPHERICAL, EXPONENTIAL, GAUSSIAN, CUBIC, PENTASPHERICAL = 0, 1, 2, 3, 4, 5
+NUGGET, SPHERICAL, EXPONENTIAL, GAUSSIAN, CUBIC, PENTASPHERICAL, SINEHOLE, CIRCULAR = 0, 1, 2, 3, 4, 5, 6, 7
 _NAMES = {NUGGET: "NuggetEffect", SPHERICAL: "Spherical", EXPONENTIAL: "Exponential", GAUSSIAN: "Gaussian", CUBIC: "Cubic",
-          PENTASPHERICAL: "Pentaspherical"}
+          PENTASPHERICAL: "Pentaspherical", SINEHOLE: "SineHole", CIRCULAR: "Circular"}
 
 
 def metric_matrix(range: float = 1.0, ranges: Optional[Sequence[float]] = None, rotation=None) -> np.ndarray:
@@ -130,6 +130,10 @@ def ExponentialCovariance(**kw): return _basic(EXPONENTIAL, False, **kw)
 def GaussianCovariance(**kw): return _basic(GAUSSIAN, False, **kw)
 def CubicCovariance(**kw): return _basic(CUBIC, False, **kw)
 def PentasphericalCovariance(**kw): return _basic(PENTASPHERICAL, False, **kw)
+def SineHoleCovariance(**kw): return _basic(SINEHOLE, False, **kw)
+def CircularCovariance(**kw): return _basic(CIRCULAR, False, **kw)
+def SineHoleVariogram(**kw): return _basic(SINEHOLE, True, **kw)
+def CircularVariogram(**kw): return _basic(CIRCULAR, True, **kw)
 def SphericalVariogram(**kw): return _basic(SPHERICAL, True, **kw)
 def ExponentialVariogram(**kw): return _basic(EXPONENTIAL, True, **kw)
 def GaussianVariogram(**kw): return _basic(GAUSSIAN, True, **kw)

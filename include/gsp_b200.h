@@ -41,7 +41,9 @@ enum gsp_kind {
   GSP_EXPONENTIAL = 2,    /* c * exp(-3u)                                   */
   GSP_GAUSSIAN = 3,       /* c * exp(-3u^2)                                 */
   GSP_CUBIC = 4,          /* c * (1 - 7u^2 + 8.75u^3 - 3.5u^5 + 0.75u^7) [u<1] */
-  GSP_PENTASPHERICAL = 5  /* c * (1 - 1.875u + 1.25u^3 - 0.375u^5) [u < 1]  */
+  GSP_PENTASPHERICAL = 5, /* c * (1 - 1.875u + 1.25u^3 - 0.375u^5) [u < 1]  */
+  GSP_SINEHOLE = 6,       /* c * sin(pi u) / (pi u)  (1 at u = 0)           */
+  GSP_CIRCULAR = 7        /* c * (2/pi) (acos(u) - u sqrt(1 - u^2)) [u < 1]  */
 };
 
 /* one nested structure: sill * rho(|A * delta|).  A is 3x3 ROW-major and maps a coordinate

@@ -45,9 +45,9 @@ struct CDomain
 end
 
 const KINDS = Dict(NuggetEffect => 0, SphericalCovariance => 1, ExponentialCovariance => 2, GaussianCovariance => 3,
-                   CubicCovariance => 4, PentasphericalCovariance => 5,
+                   CubicCovariance => 4, PentasphericalCovariance => 5, SineHoleCovariance => 6, CircularCovariance => 7,
                    SphericalVariogram => 1, ExponentialVariogram => 2, GaussianVariogram => 3,
-                   CubicVariogram => 4, PentasphericalVariogram => 5)
+                   CubicVariogram => 4, PentasphericalVariogram => 5, SineHoleVariogram => 6, CircularVariogram => 7)
 
 # ---------------------------------------------------------------- context (one per process, all visible GPUs)
 mutable struct Context

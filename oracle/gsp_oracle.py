@@ -45,7 +45,7 @@ import scipy.linalg
 # covariance models (GeoStatsFunctions formulas, restated from the published
 # definitions; the dependency is not vendored in /root/reference)
 # ----------------------------------------------------------------------------
-NUGGET, SPHERICAL, EXPONENTIAL, GAUSSIAN, CUBIC, PENTASPHERICAL = 0, 1, 2, 3, 4, 5
+NUGGET, SPHERICAL, EXPONENTIAL, GAUSSIAN, CUBIC, PENTASPHERICAL, SINEHOLE, CIRCULAR = 0, 1, 2, 3, 4, 5, 6, 7
 
 
 @dataclass
@@ -77,6 +77,11 @@ def corr(kind: int, u: np.ndarray) -> np.ndarray:
     if kind == PENTASPHERICAL:
         g = 1.875 * u - 1.25 * u**3 + 0.375 * u**5
         return np.where(u < 1, 1.0 - g, 0.0)
+    if kind == SINEHOLE:  # gamma = s (1 - sin(pi u) / (pi u))
+        return np.sinc(u)   # numpy's sinc is sin(pi x) / (pi x), 1 at 0
+    if kind == CIRCULAR:  # gamma = s (1 - (2/pi) acos(u) + (2u/pi) sqrt(1 - u^2)) for u < 1
+        uc = np.minimum(u, 1.0)
+        return np.where(u < 1, (2.0 / np.pi) * (np.arccos(uc) - uc * np.sqrt(1.0 - uc * uc)), 0.0)
     raise ValueError(f"unknown model kind {kind}")
 
 

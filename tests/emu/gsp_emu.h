@@ -200,6 +200,7 @@ static inline double __longlong_as_double(long long v) { double d; std::memcpy(&
 static inline long long __double_as_longlong(double d) { long long v; std::memcpy(&v, &d, 8); return v; }
 static inline int __clz(int x) { return x == 0 ? 32 : __builtin_clz((unsigned)x); }
 static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((uint64_t)a * b) >> 32); }
+static inline double sinpi(double x) { return std::sin(M_PI * x); }
 static inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
 static inline void sincospi(double x, double* s, double* c) { *s = std::sin(M_PI * x); *c = std::cos(M_PI * x); }
 static inline double __dsqrt_rn(double x) { return std::sqrt(x); }

@@ -19,7 +19,7 @@ def test_pairwise(emu_lib):
     X1, X2 = rng.uniform(0, 30, (150, 2)), rng.uniform(0, 30, (71, 2))
     assert relerr(emu_lib.pairwise(st, X1, X2), O.pairwise(ostructs(st), X1, X2)) < 1e-14
     assert relerr(emu_lib.pairwise(st, X1), O.pairwise(ostructs(st), X1)) < 1e-14
-    for kind in (O.EXPONENTIAL, O.GAUSSIAN, O.CUBIC, O.PENTASPHERICAL):
+    for kind in (O.EXPONENTIAL, O.GAUSSIAN, O.CUBIC, O.PENTASPHERICAL, O.SINEHOLE, O.CIRCULAR):
         st = aniso3(kind, 1.3, (9.0, 4.0, 2.0), 30.0)
         X = rng.uniform(0, 12, (65, 3))
         assert relerr(emu_lib.pairwise(st, X), O.pairwise(ostructs(st), X)) < 1e-14

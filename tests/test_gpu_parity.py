@@ -25,7 +25,7 @@ def grid_dom(dims):
 # ------------------------------------------------------------------ a1 / a2 pieces
 def test_pairwise_models(gpu_lib):
     rng = np.random.default_rng(0)
-    for kind in (O.SPHERICAL, O.EXPONENTIAL, O.GAUSSIAN, O.CUBIC, O.PENTASPHERICAL):
+    for kind in (O.SPHERICAL, O.EXPONENTIAL, O.GAUSSIAN, O.CUBIC, O.PENTASPHERICAL, O.SINEHOLE, O.CIRCULAR):
         st = aniso3(kind, 0.9, (9.0, 4.0, 2.0), 30.0) + [(O.NUGGET, 0.1, np.eye(3))]
         X1, X2 = rng.uniform(0, 12, (301, 3)), rng.uniform(0, 12, (77, 3))
         assert relerr(gpu_lib.pairwise(st, X1, X2), O.pairwise(ostructs(st), X1, X2)) < 1e-13

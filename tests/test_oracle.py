@@ -35,9 +35,12 @@ def test_model_known_values():
     assert np.allclose(O.corr(O.EXPONENTIAL, u), np.exp(-3 * u))
     assert np.allclose(O.corr(O.GAUSSIAN, u), np.exp(-3 * u * u))
     assert O.corr(O.NUGGET, u).tolist() == [1.0, 0.0, 0.0, 0.0]
-    for k in (O.CUBIC, O.PENTASPHERICAL):
+    for k in (O.CUBIC, O.PENTASPHERICAL, O.CIRCULAR):
         c = O.corr(k, u)
         assert c[0] == 1.0 and abs(c[2]) < 1e-15 and c[3] == 0.0
+    # circular: area of the lens of two unit-diameter discs at distance u, / (pi/4); sine hole: first zero at u = 1
+    assert abs(O.corr(O.CIRCULAR, np.array(0.5)) - (2 / np.pi) * (np.pi / 3 - 0.5 * np.sqrt(0.75))) < 1e-15
+    assert np.allclose(O.corr(O.SINEHOLE, u), [1.0, 2 / np.pi, 0.0, 0.0], atol=1e-15)
 
 
 def test_lusim_joint_cholesky_identity():

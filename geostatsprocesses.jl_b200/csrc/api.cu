@@ -1,6 +1,7 @@
 // Context management, argument marshalling and the small standalone entry points of the C ABI.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "chol.h"
@@ -22,11 +23,24 @@ void Prof::add(const std::string& n, double ms) {
 }
 
 void Prof::flush() {
+  // GSP_PROF_TIMELINE=1 (development): print "name start_ms duration_ms" of every launch, relative to the first pending one
+  static int timeline = -1;
+  if (timeline < 0) {
+    const char* env = getenv("GSP_PROF_TIMELINE");
+    timeline = (env && env[0] == '1') ? 1 : 0;
+  }
   for (auto& p : pending) {
     cudaEventSynchronize(p.e1);
     float ms = 0.f;
     cudaEventElapsedTime(&ms, p.e0, p.e1);
+    if (timeline) {
+      float t0 = 0.f;
+      cudaEventElapsedTime(&t0, pending.front().e0, p.e0);
+      fprintf(stderr, "TL %s %.4f %.4f\n", p.name.c_str(), t0, ms);
+    }
     add(p.name, ms);
+  }
+  for (auto& p : pending) {
     cudaEventDestroy(p.e0);
     cudaEventDestroy(p.e1);
   }

@@ -8,7 +8,7 @@ The directory name contains a dot, so import it through the `gsp_b200` shim at t
 """
 from ._lib import DEFAULT_LIB, DeviceEnsemble, FFTPlan, GspError, Library, LUPlan, PosDefException, SIGNATURES  # noqa: F401
 from .domains import CartesianGrid, GeoTable, GridView, PointSet, georef  # noqa: F401
-from .functions import (CircularCovariance, CircularVariogram, SineHoleCovariance, SineHoleVariogram, CubicCovariance, CubicVariogram, ExponentialCovariance, ExponentialVariogram,  # noqa: F401
+from .functions import (MaternCovariance, MaternVariogram, CircularCovariance, CircularVariogram, SineHoleCovariance, SineHoleVariogram, CubicCovariance, CubicVariogram, ExponentialCovariance, ExponentialVariogram,  # noqa: F401
                         GaussianCovariance, GaussianVariogram, GeoStatsFunction, NuggetEffect, PentasphericalCovariance,
                         PentasphericalVariogram, SphericalCovariance, SphericalVariogram, metric_matrix)
 from .processes import (FFTSIM, LUSIM, Ensemble, ExplicitInit, FieldSimulationMethod, GaussianProcess, NearestInit,  # noqa: F401

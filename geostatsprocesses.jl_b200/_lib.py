@@ -36,7 +36,7 @@ class PosDefException(ArithmeticError):
 
 
 class _Structure(C.Structure):
-    _fields_ = [("kind", C.c_int32), ("reserved", C.c_int32), ("sill", C.c_double), ("A", C.c_double * 9)]
+    _fields_ = [("kind", C.c_int32), ("reserved", C.c_int32), ("sill", C.c_double), ("A", C.c_double * 9), ("param", C.c_double)]
 
 
 class _CovModel(C.Structure):
@@ -102,10 +102,12 @@ def _ptr(a: Optional[np.ndarray]):
 
 
 def make_cov(structs: Sequence[tuple]) -> tuple:
-    """structs: sequence of (kind, sill, A 3x3 row-major ndarray).  Returns (model, keepalive)."""
+    """structs: sequence of (kind, sill, A 3x3 row-major ndarray[, param]); param = Matern order.  Returns (model, keepalive)."""
     n = len(structs)
     arr = (_Structure * n)()
-    for i, (kind, sill, A) in enumerate(structs):
+    for i, st in enumerate(structs):
+        kind, sill, A = st[0], st[1], st[2]
+        arr[i].param = float(st[3]) if len(st) > 3 else 0.0
         arr[i].kind = int(kind)
         arr[i].sill = float(sill)
         A = np.asarray(A, dtype=np.float64).reshape(3, 3)

@@ -94,7 +94,12 @@ int make_cov_dev(gsp_ctx* ctx, const gsp_cov_model* cov, int dim, int argpos, Co
   out->dim = dim;
   for (int s = 0; s < cov->nstruct; ++s) {
     const gsp_structure& st = cov->structs[s];
-    if (st.kind < GSP_NUGGET || st.kind > GSP_CIRCULAR) return set_err(ctx, -argpos, "unknown structure kind");
+    if (st.kind < GSP_NUGGET || st.kind > GSP_MATERN) return set_err(ctx, -argpos, "unknown structure kind");
+    if (st.kind == GSP_MATERN) {
+      if (!(st.param > 0.0) || !(st.param <= 100.0)) return set_err(ctx, -argpos, "Matern order must be in (0, 100]");
+      out->param[s] = st.param;
+      out->aux[s] = std::exp2(1.0 - st.param) / std::tgamma(st.param);  // 2^(1-nu) / Gamma(nu)
+    }
     if (!(st.sill >= 0.0)) return set_err(ctx, -argpos, "structure sill must be >= 0");
     out->kind[s] = st.kind;
     out->sill[s] = st.sill;

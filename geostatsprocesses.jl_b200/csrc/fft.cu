@@ -290,6 +290,7 @@ struct Lane {
   cplx* H = nullptr;
   TensorMap tmH[3];
   cudaEvent_t done = nullptr;
+  DevBuf syncbuf;  // fused x+y kernels: [claim counter, nz plane counters] forward, then the same for the inverse
 };
 
 // sub-range of a strided pass: bundles [bx0, bx0 + nb) (nb == 0: all) for the indices [o0, o1) of the remaining axis (o1 == 0: all)
@@ -324,8 +325,6 @@ struct FftDev {
   DevBuf win[2], zout[2];  // staging for host-pointer sampling
   DevBuf inds;
   long long inds_cap = 0;
-  DevBuf cnt;              // plane counters of the fused x+y kernels: [0, nz) forward, [nz, 2nz) inverse
-  int epoch_fwd = 0, epoch_inv = 0;
   bool fused_xy = false;   // 3-D grids whose x and y extents are covered by p2_plane_kernel
   AxisPlan ax[3];
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -361,6 +360,9 @@ namespace {
 const size_t kMaxSmem = 200 * 1024;
 #ifndef GSP_STRIDED_STAGES
 #define GSP_STRIDED_STAGES 1  // measured on B200 at 256^3: z pass 93 -> 76 us, y passes unchanged
+#endif
+#ifndef GSP_FFT_FUSE_DEFAULT
+#define GSP_FFT_FUSE_DEFAULT 0
 #endif
 bool g_force_generic = false;  // GSP_FFT_GENERIC=1: use the mixed-radix kernels for every extent (A/B checks)
 
@@ -467,30 +469,25 @@ cudaError_t launch_p2_strided(cudaStream_t st, int sms, int flags, const TensorM
   return launch_p2_strided_f<N, P2_FWD | P2_MUL | P2_INV>(st, sms, tmH, axis, H, twp, tw, twi, es, hx, nother, other_stride, Fh, esF, other_strideF, s, sub);
 }
 
-template <int HN, int NY, bool INV>
+template <int HN, int NY, bool INV, bool RNG>
 cudaError_t launch_plane(cudaStream_t st, int sms, const TensorMap& tmHy, const double* in, double* out, cplx* H, const cplx* twx,
-                         const cplx* twy, int nz, int* cnt, int epoch, double scale, double mu) {
+                         const cplx* stwx, const cplx* stwy, int nz, int* sync, double scale, double mu, const XRng& rng) {
   using C = PlaneCfg<HN, NY, INV>;
   if constexpr (!C::OK) {
     return cudaErrorInvalidValue;
   } else {
-    auto kfn = p2_plane_kernel<HN, NY, INV>;
-    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-    if (e != cudaSuccess) return e;
-    int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, PLANE_THREADS, C::SMEM);
-    if (e != cudaSuccess) return e;
-    if (per_sm < 1) return cudaErrorInvalidValue;
-    if (per_sm > 4) per_sm = 4;
-    // every CTA must be resident: CTAs wait on each other's planes
-    constexpr int NBUN = (C::HX + C::B - 1) / C::B;
-    constexpr int PB = C::XI + (NBUN + C::U - 1) / C::U;
+    auto kfn = p2_plane_kernel<HN, NY, INV, RNG>;
+    static KernelSetup ks;
+    const int per_sm = ks.get(kfn, PLANE_THREADS, C::SMEM);
+    if (per_sm == 0) return ks.err;
     long long grid = (long long)per_sm * sms;
-    if (grid > (long long)nz * PB) grid = (long long)nz * PB;
-    // items in flight or being prefetched span 2*grid consecutive item numbers: lag the dependent kind beyond that
-    const int lag = (int)((2 * grid + PB - 1) / PB) + 1;
-    ProfScope prof_(INV ? "fft_plane_yx_inv" : "fft_plane_xy_fwd", st);
-    GSP_LAUNCH_COOP(kfn, dim3((unsigned)grid), dim3(PLANE_THREADS), C::SMEM, st, tmHy, in, out, H, twx, twy, nz, lag, cnt, epoch, scale, mu);
+    if (grid > (long long)nz * C::PB) grid = (long long)nz * C::PB;
+    // every CTA holds one claimed item: lag the dependent kind beyond the window of items in flight
+    const int lag = (int)((grid + C::PB - 1) / C::PB) + 2;
+    ProfScope prof_(INV ? "fft_plane_yx_inv" : (RNG ? "fft_plane_xy_fwd_rng" : "fft_plane_xy_fwd"), st);
+    // (claims are dynamic, so no co-residency is needed on the GPU; the emulator runs the CTAs concurrently to exercise the waits)
+    GSP_LAUNCH_COOP(kfn, dim3((unsigned)grid), dim3(PLANE_THREADS), C::SMEM, st, tmHy, in, out, H, twx, stwx, stwy, nz, lag, sync, scale, mu,
+                    rng);
     g_launches++;
     return cudaGetLastError();
   }
@@ -499,11 +496,12 @@ cudaError_t launch_plane(cudaStream_t st, int sms, const TensorMap& tmHy, const 
 // (HN, NY) combinations compiled for the fused x+y kernels; everything else runs the separate passes
 inline bool plane_supported(int hn, int ny) { return (hn == 64 || hn == 128 || hn == 256) && (ny == 128 || ny == 256); }
 
-template <bool INV>
+template <bool INV, bool RNG>
 cudaError_t launch_plane_dispatch(int hn, int ny, cudaStream_t st, int sms, const TensorMap& tmHy, const double* in, double* out, cplx* H,
-                                  const cplx* twx, const cplx* twy, int nz, int* cnt, int epoch, double scale, double mu) {
+                                  const cplx* twx, const cplx* stwx, const cplx* stwy, int nz, int* sync, double scale, double mu,
+                                  const XRng& rng) {
 #define GSP_PL(HN_, NY_) \
-  if (hn == HN_ && ny == NY_) return launch_plane<HN_, NY_, INV>(st, sms, tmHy, in, out, H, twx, twy, nz, cnt, epoch, scale, mu);
+  if (hn == HN_ && ny == NY_) return launch_plane<HN_, NY_, INV, RNG>(st, sms, tmHy, in, out, H, twx, stwx, stwy, nz, sync, scale, mu, rng);
   GSP_PL(64, 128) GSP_PL(64, 256) GSP_PL(128, 128) GSP_PL(128, 256) GSP_PL(256, 128) GSP_PL(256, 256)
 #undef GSP_PL
   return cudaErrorInvalidValue;
@@ -677,21 +675,30 @@ cudaError_t run_strided(FftDev* d, gsp_fft_plan* p, const Lane& L, int axis, int
   return cudaGetLastError();
 }
 
-cudaError_t run_plane_fwd(FftDev* d, gsp_fft_plan* p, const double* in) {
-  return launch_plane_dispatch<false>((int)p->dims[0] / 2, (int)p->dims[1], d->dc->stream, d->dc->sms, d->ax[1].tmH, in, nullptr,
-                                      d->H.as<cplx>(), d->ax[0].lp.tw, d->ax[1].lp.tw, (int)p->dims[2], d->cnt.as<int>(), ++d->epoch_fwd, 0.0, 0.0);
+// fused x+y forward of one realization on a lane; in == nullptr: noise from the counter RNG.  Zeroes the lane's claim / plane
+// counters first (`both`: also those of the inverse kernel that follows in `realization`).
+cudaError_t run_plane_fwd(FftDev* d, gsp_fft_plan* p, const Lane& L, const double* in, const XRng& rng, bool both) {
+  const int nz = (int)p->dims[2];
+  cudaError_t e = cudaMemsetAsync(L.syncbuf.p, 0, (size_t)(both ? 2 : 1) * (nz + 1) * sizeof(int), L.st);
+  if (e != cudaSuccess) return e;
+  const int hn = (int)p->dims[0] / 2, ny = (int)p->dims[1];
+  const cplx *twx = d->ax[0].lp.tw, *stwx = d->stw_fwd.as<cplx>(), *stwy = d->stw_ax_fwd[1].as<cplx>();
+  // The RNG = true instantiation (noise drawn inside the x items) passes the emulator but hung on the B200 (session 3, cause not
+  // found): not instantiated; the opt-in fused mode takes its noise from rng_fill_kernel's scratch array instead.
+  if (!in) return cudaErrorInvalidValue;
+  return launch_plane_dispatch<false, false>(hn, ny, L.st, d->dc->sms, L.tmH[1], in, nullptr, L.H, twx, stwx, stwy, nz, L.syncbuf.as<int>(), 0.0, 0.0, rng);
 }
-cudaError_t run_plane_inv(FftDev* d, gsp_fft_plan* p, double* out, double scale, double mu) {
-  return launch_plane_dispatch<true>((int)p->dims[0] / 2, (int)p->dims[1], d->dc->stream, d->dc->sms, d->ax[1].tmH, nullptr, out,
-                                     d->H.as<cplx>(), d->ax[0].lp.tw, d->ax[1].lp.tw, (int)p->dims[2], d->cnt.as<int>() + p->dims[2],
-                                     ++d->epoch_inv, scale, mu);
+cudaError_t run_plane_inv(FftDev* d, gsp_fft_plan* p, const Lane& L, double* out, double scale, double mu) {
+  const int nz = (int)p->dims[2];
+  return launch_plane_dispatch<true, false>((int)p->dims[0] / 2, (int)p->dims[1], L.st, d->dc->sms, L.tmH[1], nullptr, out, L.H, d->ax[0].lp.tw,
+                                            d->stw_inv.as<cplx>(), d->stw_ax_inv[1].as<cplx>(), nz, L.syncbuf.as<int>() + nz + 1, scale, mu, XRng{});
 }
 
 // forward transform of a real field into d->H (all axes)
 cudaError_t forward_all(FftDev* d, gsp_fft_plan* p, const double* in) {
   const Lane& L = *d->lanes[0];
   if (d->fused_xy) {
-    cudaError_t e = run_plane_fwd(d, p, in);
+    cudaError_t e = run_plane_fwd(d, p, L, in, XRng{}, false);
     if (e == cudaSuccess) e = run_strided(d, p, L, 2, PASS_FWD, nullptr, 0.0);
     return e;
   }
@@ -708,9 +715,12 @@ cudaError_t realization(FftDev* d, gsp_fft_plan* p, const Lane& L, const double*
   const long long nrows = p->dims[1] * p->dims[2];
   if (d->fused_xy) {
     // 3 kernels per realization: (x+y forward) -> (z forward, spectral multiply, z inverse) -> (y+x inverse)
-    cudaError_t e = run_plane_fwd(d, p, w);
+    XRng rr = rng;
+    rr.row_base = 0;
+    rr.rows_per_real = nrows;
+    cudaError_t e = run_plane_fwd(d, p, L, w, rr, true);
     if (e == cudaSuccess) e = run_strided(d, p, L, 2, PASS_FWD | PASS_MUL | PASS_INV, Fh, s);
-    if (e == cudaSuccess) e = run_plane_inv(d, p, out, scale_out, mu);
+    if (e == cudaSuccess) e = run_plane_inv(d, p, L, out, scale_out, mu);
     return e;
   }
   cudaError_t e = cudaSuccess;
@@ -870,15 +880,13 @@ int build_device(gsp_ctx* ctx, gsp_fft_plan* p, FftDev* d, const CovDev& cov, co
     if (r1 != 0 || r2 != 0) return set_err(ctx, GSP_E_CUDA, "cuTensorMapEncodeTiled failed for an FFT pass (code " + std::to_string(r1 ? r1 : r2) + ")");
   }
   {
-    // Opt-in (GSP_FFT_FUSE=1): measured on B200 at 256^3 the fused x+y kernels halve the HBM traffic of those passes but
-    // run at 146 us + 121 us against 126 us + 105 us for the four separate passes - with 8 warps per SM the items'
-    // shared-memory / FP64 / wait phases do not overlap enough (profiles/r01_fused_plane_notes.md).
+    // Fused x+y kernels (fft_plane.cuh): GSP_FFT_FUSE=1 turns them on, =0 off (A/B runs).
     const char* env = getenv("GSP_FFT_FUSE");
-    const bool allow = env && env[0] == '1';
-    d->fused_xy = allow && p->ndim == 3 && d->ax[0].fast && d->ax[1].fast && d->ax[2].fast &&
-                  plane_supported((int)p->dims[0] / 2, (int)p->dims[1]) && d->lanes.size() == 1 && d->slab_mode == 0;
-    GSP_CUDA_OK(ctx, d->cnt.alloc(d->dc->dev, (size_t)(2 * p->dims[2] + 2) * sizeof(int)));
-    GSP_CUDA_OK(ctx, cudaMemsetAsync(d->cnt.p, 0, (size_t)(2 * p->dims[2] + 2) * sizeof(int), d->dc->stream));
+    const bool allow = env && env[0] ? env[0] == '1' : GSP_FFT_FUSE_DEFAULT != 0;
+    d->fused_xy = allow && all_fast && plane_supported((int)p->dims[0] / 2, (int)p->dims[1]) && d->slab_mode == 0;
+    if (d->fused_xy) {
+      for (auto& L : d->lanes) GSP_CUDA_OK(ctx, L->syncbuf.alloc(d->dc->dev, (size_t)(2 * p->dims[2] + 2) * sizeof(int)));
+    }
   }
   DevBuf C, partial, total;
   GSP_CUDA_OK(ctx, C.alloc(d->dc->dev, (size_t)p->N * sizeof(double)));

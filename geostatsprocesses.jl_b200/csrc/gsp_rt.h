@@ -20,6 +20,7 @@
 #endif
 
 #define GSP_DEV __device__ __forceinline__
+#define GSP_DEV_NOINLINE static __device__ __noinline__  // big scalar routines (bessel_k): one copy per kernel, not one per call site
 
 namespace gsp {
 
@@ -76,6 +77,7 @@ GSP_DEV void mbar_wait(mbar_t* b, uint32_t parity) {
 }
 GSP_DEV void fence_mbar_init() {}
 GSP_DEV void fence_proxy_async() {}
+GSP_DEV void fence_proxy_async_all() {}
 // dst: shared, src: global, bytes % 16 == 0, both 16-byte aligned
 GSP_DEV void bulk_g2s(void* dst, const void* src, uint32_t bytes, mbar_t* b) {
   if ((((uintptr_t)dst) & 15) || (((uintptr_t)src) & 15) || (bytes & 15)) {
@@ -94,6 +96,8 @@ GSP_DEV void mbar_init(mbar_t* b, int count) {
 }
 GSP_DEV void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 GSP_DEV void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// all state spaces: global data written through the generic proxy (plain stores, possibly by another CTA) before TMA reads it
+GSP_DEV void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 GSP_DEV void mbar_arrive(mbar_t* b) {
   asm volatile("{ .reg .b64 st; mbarrier.arrive.shared::cta.b64 st, [%0]; }" ::"r"(smem_u32(b)) : "memory");
 }

@@ -12,8 +12,8 @@ from typing import List, Optional, Sequence
 
 import numpy as np
 
-NUGGET, SPHERICAL, EXPONENTIAL, GAUSSIAN, CUBIC, PENTASPHERICAL, SINEHOLE, CIRCULAR = 0, 1, 2, 3, 4, 5, 6, 7
-_NAMES = {NUGGET: "NuggetEffect", SPHERICAL: "Spherical", EXPONENTIAL: "Exponential", GAUSSIAN: "Gaussian", CUBIC: "Cubic",
+NUGGET, SPHERICAL, EXPONENTIAL, GAUSSIAN, CUBIC, PENTASPHERICAL, SINEHOLE, CIRCULAR, MATERN = 0, 1, 2, 3, 4, 5, 6, 7, 8
+_NAMES = {MATERN: "Matern", NUGGET: "NuggetEffect", SPHERICAL: "Spherical", EXPONENTIAL: "Exponential", GAUSSIAN: "Gaussian", CUBIC: "Cubic",
           PENTASPHERICAL: "Pentaspherical", SINEHOLE: "SineHole", CIRCULAR: "Circular"}
 
 
@@ -39,6 +39,10 @@ class _Struct:
     C: np.ndarray          # nv x nv contribution
     A: np.ndarray          # 3x3 metric
     maxrange: float
+    param: float = 0.0     # Matern: order nu
+
+    def flat(self, sill: float) -> tuple:
+        return (self.kind, sill, self.A, self.param) if self.kind == MATERN else (self.kind, sill, self.A)
 
 
 @dataclass
@@ -83,7 +87,7 @@ class GeoStatsFunction:
                 if s.C.shape != (1, 1):
                     raise ValueError("matrix scaling needs a univariate function")
                 C = c * s.C[0, 0]
-            out.append(_Struct(s.kind, np.atleast_2d(C), s.A, s.maxrange))
+            out.append(_Struct(s.kind, np.atleast_2d(C), s.A, s.maxrange, s.param))
         return GeoStatsFunction(out, self.variogram)
 
     def __add__(self, other: "GeoStatsFunction"):
@@ -95,8 +99,8 @@ class GeoStatsFunction:
 
     # --- boundary flattening
     def marginal(self, j: int) -> list:
-        """_marginalize (lusim.jl:132-137) flattened to [(kind, sill, A)]."""
-        out = [(s.kind, float(s.C[j, j]), s.A) for s in self.structs if not (s.kind == NUGGET and s.C[j, j] == 0.0)]
+        """_marginalize (lusim.jl:132-137) flattened to [(kind, sill, A[, order])]."""
+        out = [s.flat(float(s.C[j, j])) for s in self.structs if not (s.kind == NUGGET and s.C[j, j] == 0.0)]
         return out
 
     def flat(self) -> list:
@@ -116,10 +120,16 @@ class GeoStatsFunction:
         return " + ".join(parts)
 
 
-def _basic(kind: int, variogram: bool, range=1.0, sill=1.0, nugget=0.0, ranges=None, rotation=None) -> GeoStatsFunction:
+def _basic(kind: int, variogram: bool, range=1.0, sill=1.0, nugget=0.0, ranges=None, rotation=None, order=None) -> GeoStatsFunction:
     A = metric_matrix(range, ranges, rotation)
     mr = float(range) if ranges is None else float(max(ranges))
-    structs = [_Struct(kind, np.array([[float(sill) - float(nugget)]]), A, mr)]
+    if kind == MATERN:
+        order = 1.0 if order is None else float(order)  # GeoStatsFunctions' default
+        if not order > 0.0:
+            raise ValueError("Matern order must be positive")
+    elif order is not None:
+        raise TypeError("`order` is a Matern parameter")
+    structs = [_Struct(kind, np.array([[float(sill) - float(nugget)]]), A, mr, order or 0.0)]
     if nugget != 0.0:
         structs.append(_Struct(NUGGET, np.array([[float(nugget)]]), np.eye(3), 0.0))
     return GeoStatsFunction(structs, variogram)
@@ -132,6 +142,8 @@ def CubicCovariance(**kw): return _basic(CUBIC, False, **kw)
 def PentasphericalCovariance(**kw): return _basic(PENTASPHERICAL, False, **kw)
 def SineHoleCovariance(**kw): return _basic(SINEHOLE, False, **kw)
 def CircularCovariance(**kw): return _basic(CIRCULAR, False, **kw)
+def MaternCovariance(**kw): return _basic(MATERN, False, **kw)
+def MaternVariogram(**kw): return _basic(MATERN, True, **kw)
 def SineHoleVariogram(**kw): return _basic(SINEHOLE, True, **kw)
 def CircularVariogram(**kw): return _basic(CIRCULAR, True, **kw)
 def SphericalVariogram(**kw): return _basic(SPHERICAL, True, **kw)

@@ -43,7 +43,8 @@ enum gsp_kind {
   GSP_CUBIC = 4,          /* c * (1 - 7u^2 + 8.75u^3 - 3.5u^5 + 0.75u^7) [u<1] */
   GSP_PENTASPHERICAL = 5, /* c * (1 - 1.875u + 1.25u^3 - 0.375u^5) [u < 1]  */
   GSP_SINEHOLE = 6,       /* c * sin(pi u) / (pi u)  (1 at u = 0)           */
-  GSP_CIRCULAR = 7        /* c * (2/pi) (acos(u) - u sqrt(1 - u^2)) [u < 1]  */
+  GSP_CIRCULAR = 7,       /* c * (2/pi) (acos(u) - u sqrt(1 - u^2)) [u < 1]  */
+  GSP_MATERN = 8          /* c * 2^(1-nu)/Gamma(nu) d^nu K_nu(d), d = sqrt(2 nu) 3u; nu = param > 0 (1 at u = 0) */
 };
 
 /* one nested structure: sill * rho(|A * delta|).  A is 3x3 ROW-major and maps a coordinate
@@ -54,6 +55,7 @@ typedef struct gsp_structure {
   int32_t reserved;
   double sill;
   double A[9];
+  double param; /* GSP_MATERN: the order nu (GeoStatsFunctions' `order`, default 1.0); ignored by the other kinds */
 } gsp_structure;
 
 #define GSP_MAX_STRUCTS 8

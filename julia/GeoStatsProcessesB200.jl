@@ -26,6 +26,7 @@ struct CStructure
   reserved::Int32
   sill::Float64
   A::NTuple{9,Float64}     # 3x3 row-major, u = |A * delta|
+  param::Float64           # MaternCovariance / MaternVariogram: order nu; 0 otherwise
 end
 
 struct CCovModel
@@ -46,6 +47,7 @@ end
 
 const KINDS = Dict(NuggetEffect => 0, SphericalCovariance => 1, ExponentialCovariance => 2, GaussianCovariance => 3,
                    CubicCovariance => 4, PentasphericalCovariance => 5, SineHoleCovariance => 6, CircularCovariance => 7,
+                   MaternCovariance => 8, MaternVariogram => 8,
                    SphericalVariogram => 1, ExponentialVariogram => 2, GaussianVariogram => 3,
                    CubicVariogram => 4, PentasphericalVariogram => 5, SineHoleVariogram => 6, CircularVariogram => 7)
 
@@ -92,9 +94,10 @@ function flatten(f, j)
   cₒ, cs, fs = GeoStatsFunctions.structures(f)
   out = CStructure[]
   nug = ustrip(cₒ[j, j])
-  iszero(nug) || push!(out, CStructure(0, 0, nug, ntuple(i -> i in (1, 5, 9) ? 1.0 : 0.0, 9)))
+  iszero(nug) || push!(out, CStructure(0, 0, nug, ntuple(i -> i in (1, 5, 9) ? 1.0 : 0.0, 9), 0.0))
   for (c, g) in zip(cs, fs)
-    push!(out, CStructure(KINDS[typeof(g).name.wrapper], 0, ustrip(c[j, j]), metricmatrix(g)))
+    k = KINDS[typeof(g).name.wrapper]
+    push!(out, CStructure(k, 0, ustrip(c[j, j]), metricmatrix(g), k == 8 ? Float64(g.order) : 0.0))
   end
   out
 end

@@ -45,7 +45,7 @@ import scipy.linalg
 # covariance models (GeoStatsFunctions formulas, restated from the published
 # definitions; the dependency is not vendored in /root/reference)
 # ----------------------------------------------------------------------------
-NUGGET, SPHERICAL, EXPONENTIAL, GAUSSIAN, CUBIC, PENTASPHERICAL, SINEHOLE, CIRCULAR = 0, 1, 2, 3, 4, 5, 6, 7
+NUGGET, SPHERICAL, EXPONENTIAL, GAUSSIAN, CUBIC, PENTASPHERICAL, SINEHOLE, CIRCULAR, MATERN = 0, 1, 2, 3, 4, 5, 6, 7, 8
 
 
 @dataclass
@@ -58,11 +58,22 @@ class Structure:
     kind: int
     sill: float
     A: np.ndarray = field(default_factory=lambda: np.eye(3))
+    param: float = 0.0   # Matern: order nu
 
 
-def corr(kind: int, u: np.ndarray) -> np.ndarray:
+def corr(kind: int, u: np.ndarray, param: float = 0.0) -> np.ndarray:
     """Correlation rho(u) of the basic models at normalised lag u = h / range."""
     u = np.asarray(u, dtype=np.float64)
+    if kind == MATERN:
+        # GeoStatsFunctions MaternVariogram: delta = sqrt(2 nu) 3 h/r, Omega = 2^(1-nu)/Gamma(nu) delta^nu, gamma = s (1 - Omega K_nu(delta)).
+        # The reference evaluates at h + eps() to avoid 0 * Inf at the origin; rho(0) = 1 here (difference <= 1e-15).
+        import scipy.special
+        nu = float(param)
+        d = np.sqrt(2.0 * nu) * 3.0 * u
+        with np.errstate(invalid="ignore", over="ignore", divide="ignore"):
+            r = (2.0 ** (1.0 - nu) / scipy.special.gamma(nu)) * d**nu * scipy.special.kv(nu, d)
+        r = np.where(np.isfinite(r), r, 1.0)
+        return np.where(u == 0, 1.0, np.minimum(r, 1.0))
     if kind == NUGGET:
         return (u == 0).astype(np.float64)
     if kind == SPHERICAL:
@@ -101,7 +112,7 @@ def cov_eval(structs: Sequence[Structure], delta: np.ndarray) -> np.ndarray:
         A = np.asarray(s.A, dtype=np.float64)[:dim, :dim]
         t = delta @ A.T
         u = np.sqrt(np.sum(t * t, axis=-1))
-        out = out + s.sill * corr(s.kind, u)
+        out = out + s.sill * corr(s.kind, u, s.param)
     return out
 
 

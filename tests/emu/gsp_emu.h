@@ -155,6 +155,7 @@ inline int lane() { return (int)(g_threadIdx.x + g_blockDim.x * (g_threadIdx.y +
 #define __device__
 #define __host__
 #define __forceinline__ inline
+#define __noinline__
 #define __shared__ static
 #define __launch_bounds__(...)
 #define __constant__ static
@@ -206,7 +207,7 @@ static inline void sincospi(double x, double* s, double* c) { *s = std::sin(M_PI
 static inline double __dsqrt_rn(double x) { return std::sqrt(x); }
 static inline double __ddiv_rn(double a, double b) { return a / b; }
 static inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c); }
-using std::fma; using std::sqrt; using std::exp; using std::fabs; using std::log; using std::floor; using std::fmin; using std::fmax;
+using std::pow; using std::sinh; using std::cosh; using std::sin; using std::fma; using std::sqrt; using std::exp; using std::fabs; using std::log; using std::floor; using std::fmin; using std::fmax;
 
 namespace emu {
 // arguments are evaluated eagerly (like a real launch) and copied into the per-thread closure

@@ -23,6 +23,14 @@ def test_pairwise(emu_lib):
         st = aniso3(kind, 1.3, (9.0, 4.0, 2.0), 30.0)
         X = rng.uniform(0, 12, (65, 3))
         assert relerr(emu_lib.pairwise(st, X), O.pairwise(ostructs(st), X)) < 1e-14
+    # Matern: the device K_nu (Temme series / Steed CF2 + recurrence) against SciPy's AMOS kv, entry by entry
+    X = np.concatenate([rng.uniform(0, 12, (60, 3)), rng.uniform(0, 0.05, (8, 3)), rng.uniform(0, 200, (8, 3))])
+    for nu in (0.3, 0.5, 1.0, 1.5, 2.5, 3.2, 7.0):
+        st = aniso3(O.MATERN, 1.3, (9.0, 4.0, 2.0), 30.0, order=nu)
+        G, Go = emu_lib.pairwise(st, X), O.pairwise(ostructs(st), X)
+        assert np.abs(G - Go).max() < 1e-13 * 1.3, nu
+        big = Go > 1e-200
+        assert np.abs(G[big] / Go[big] - 1).max() < 2e-12, nu
 
 
 @pytest.mark.parametrize("n", [1, 7, 128, 200])
@@ -184,20 +192,29 @@ def test_fftsim_pow2_fast_path(emu_lib):
         plan.close()
 
 
-def test_fftsim_fused_plane_kernels(emu_lib, monkeypatch):
-    """opt-in fused x+y kernels (fft_plane.cuh): inter-CTA plane dependencies, counters reused across realizations."""
-    monkeypatch.setenv("GSP_FFT_FUSE", "1")
+@pytest.mark.parametrize("lanes,dims,R", [(1, (256, 128, 2), 2), (3, (128, 128, 4), 3)])
+def test_fftsim_fused_plane_kernels(emu_lib, monkeypatch, lanes, dims, R):
+    """fused x+y kernels (fft_plane.cuh): dynamic item claims, inter-CTA plane dependencies, counters zeroed per realization,
+    several lanes, device noise through the scratch array; bit-identical to the separate passes."""
+    monkeypatch.setenv("GSP_FFT_LANES", str(lanes))
     rng = np.random.default_rng(12)
-    for dims in ((128, 128, 6), (256, 128, 3)):
+    if True:
         st = iso(O.EXPONENTIAL, 1.0, 6.0, 3)
+        monkeypatch.setenv("GSP_FFT_FUSE", "0")
+        ref = gsp.FFTPlan(emu_lib, st, dims, [0.0] * 3, [1.0] * 3)
+        monkeypatch.setenv("GSP_FFT_FUSE", "1")
         plan = gsp.FFTPlan(emu_lib, st, dims, [0.0] * 3, [1.0] * 3)
         Fo = O.fftsim_preprocess(ostructs(st), dims, [0.0] * 3, [1.0] * 3)
         assert relerr(plan.spectrum(), Fo) < 1e-12
-        w = rng.random((3, int(np.prod(dims))))
-        Z = plan.sample(3, w, sill=1.0, mu=0.0)
-        for r in range(3):
+        assert np.array_equal(plan.spectrum(), ref.spectrum())
+        w = rng.random((R, int(np.prod(dims))))
+        Z = plan.sample(R, w, sill=1.0, mu=0.0)
+        for r in range(R):
             assert relerr(Z[r], O.fftsim_sample(Fo, w[r], 1.0, 0.0)) < TOL
+        assert np.array_equal(Z, ref.sample(R, w, sill=1.0, mu=0.0))
+        assert np.array_equal(plan.sample(R, None, seed=21, first_real=3), ref.sample(R, None, seed=21, first_real=3))
         plan.close()
+        ref.close()
 
 
 @pytest.mark.parametrize("mode,lanes,planes,bundles", [(1, 1, 4, 4), (1, 3, 5, 4), (2, 2, 4, 2), (2, 1, 4, 1), (0, 3, 4, 4)])

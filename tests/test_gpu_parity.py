@@ -30,6 +30,14 @@ def test_pairwise_models(gpu_lib):
         X1, X2 = rng.uniform(0, 12, (301, 3)), rng.uniform(0, 12, (77, 3))
         assert relerr(gpu_lib.pairwise(st, X1, X2), O.pairwise(ostructs(st), X1, X2)) < 1e-13
         assert relerr(gpu_lib.pairwise(st, X1), O.pairwise(ostructs(st), X1)) < 1e-13
+    # Matern (K_nu evaluated on the device) against SciPy's kv: absolute and entry-wise relative agreement
+    X = np.concatenate([rng.uniform(0, 12, (300, 3)), rng.uniform(0, 0.05, (20, 3)), rng.uniform(0, 200, (20, 3))])
+    for nu in (0.3, 0.5, 1.0, 1.5, 2.5, 3.2, 7.0):
+        st = aniso3(O.MATERN, 0.9, (9.0, 4.0, 2.0), 30.0, order=nu) + [(O.NUGGET, 0.1, np.eye(3))]
+        G, Go = gpu_lib.pairwise(st, X), O.pairwise(ostructs(st), X)
+        assert np.abs(G - Go).max() < 1e-13, nu
+        big = Go > 1e-200
+        assert np.abs(G[big] / Go[big] - 1).max() < 2e-12, nu
 
 
 @pytest.mark.parametrize("n", [1, 5, 127, 128, 129, 1000, 2048])

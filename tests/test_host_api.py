@@ -52,6 +52,30 @@ def test_lusim_api(emu_lib):  # test/field.jl:17-71 (smaller grids: the emulator
     assert all(r.Cu[j] == 0.0 and r.Zn[j] == 0.1 for r in ens)
 
 
+def test_matern_through_rand(emu_lib):
+    """MaternCovariance / MaternVariogram (order = nu) cross the boundary with their parameter: nu = 1/2 reproduces the
+    exponential model of the same range draw for draw, through LUSIM and FFTSIM."""
+    grid = gsp.CartesianGrid(12, 9)
+    data = gsp.georef({"Z": [1.0, -0.5, 0.3]}, [(2.5, 2.5), (9.5, 4.5), (5.5, 7.5)])
+    lu = gsp.LUSIM(library=emu_lib)
+    a = gsp.rand(gsp.GaussianProcess(gsp.MaternCovariance(range=6.0, sill=1.4, order=0.5)), grid, 3, rng=np.random.default_rng(4), method=lu, data=data)
+    b = gsp.rand(gsp.GaussianProcess(gsp.ExponentialCovariance(range=6.0, sill=1.4)), grid, 3, rng=np.random.default_rng(4), method=lu, data=data)
+    for ra, rb in zip(a, b):
+        assert np.abs(ra.Z - rb.Z).max() < 1e-10
+    ff = gsp.FFTSIM(library=emu_lib)
+    a = gsp.rand(gsp.GaussianProcess(gsp.MaternVariogram(range=6.0, order=0.5)), grid, 2, rng=np.random.default_rng(5), method=ff)
+    b = gsp.rand(gsp.GaussianProcess(gsp.ExponentialVariogram(range=6.0)), grid, 2, rng=np.random.default_rng(5), method=ff)
+    for ra, rb in zip(a, b):
+        assert np.abs(ra.field - rb.field).max() < 1e-10
+    assert gsp.MaternCovariance().structs[0].param == 1.0          # GeoStatsFunctions' default order
+    with pytest.raises(ValueError):
+        gsp.MaternCovariance(order=0.0)
+    with pytest.raises(TypeError):
+        gsp.SphericalCovariance(order=1.0)
+    with pytest.raises(ValueError, match="Matern order"):            # the C ABI rejects a non-positive order itself
+        emu_lib.pairwise([(8, 1.0, np.eye(3), -1.0)], np.zeros((2, 2)))
+
+
 def test_lusim_rejects_variograms(emu_lib):  # lusim.jl:44-50
     proc = gsp.GaussianProcess(gsp.SphericalVariogram(range=10.0))
     with pytest.raises(ValueError, match="stationary, symmetric and banded"):

@@ -43,6 +43,19 @@ def test_model_known_values():
     assert np.allclose(O.corr(O.SINEHOLE, u), [1.0, 2 / np.pi, 0.0, 0.0], atol=1e-15)
 
 
+def test_matern_known_values():
+    """Matern closed forms at half-integer orders (delta = sqrt(2 nu) 3u): nu = 1/2 IS the exponential model of the same range."""
+    u = np.array([0.0, 1e-9, 0.01, 0.2, 0.5, 1.0, 2.0, 10.0])
+    assert np.allclose(O.corr(O.MATERN, u, 0.5), O.corr(O.EXPONENTIAL, u), rtol=1e-13, atol=1e-300)
+    d = np.sqrt(3.0) * 3 * u
+    assert np.allclose(O.corr(O.MATERN, u, 1.5), (1 + d) * np.exp(-d), rtol=1e-12, atol=1e-300)
+    d = np.sqrt(5.0) * 3 * u
+    assert np.allclose(O.corr(O.MATERN, u, 2.5), (1 + d + d * d / 3) * np.exp(-d), rtol=1e-12, atol=1e-300)
+    c = O.corr(O.MATERN, u, 1.0)   # GeoStatsFunctions' default order
+    assert c[0] == 1.0 and np.all(np.diff(c) < 0) and c[-1] < 1e-15
+    assert O.corr(O.MATERN, np.array([300.0]), 0.7)[0] == 0.0   # K underflows: exactly zero, not NaN
+
+
 def test_lusim_joint_cholesky_identity():
     """lusim.jl:95-103 equals the blocks of ONE Cholesky of the joint matrix [data; sim]."""
     rng = np.random.default_rng(0)

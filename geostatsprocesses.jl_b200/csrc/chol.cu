@@ -13,22 +13,24 @@
 namespace gsp {
 
 constexpr int DB = 128;   // diagonal block
-constexpr int DLD = 129;  // padded smem leading dimension (row-major S[r][c])
+constexpr int DLD = 132;  // smem leading dimension of the COLUMN-major block S[c * DLD + r]: DMMA fragment loads of both kinds
+                          // (8 consecutive rows x 4 columns, 4 consecutive rows x 8 columns) are bank-conflict-free for DLD = 4 mod 16
 constexpr int DPW = 16;   // inner panel width
-constexpr int DIAG_SMEM = (DB * DLD + DPW * (DPW + 1) + DPW) * 8;
+constexpr int DVL = 20;   // leading dimension of the 16x16 inverse blocks (transposed), = 4 mod 16
+constexpr int DIAG_SMEM = (DB * DLD + (DB / DPW) * DPW * DVL) * 8;
 
 // 16x16 diagonal block of a panel, factorised by ONE warp in registers (lane l < 16 owns row l), right-looking,
-// no block barriers: per column one shuffle broadcasts the pivot, rsqrt gives 1/L_jj, the remaining columns are
-// updated with shuffled L_kj.  Fully unrolled through the template recursion (static register indexing).
+// no block barriers: per column one shuffle broadcasts the pivot, rsqrt gives 1/L_jj (kept by every lane in rd[]), the
+// remaining columns are updated with shuffled L_kj.  Fully unrolled through the template recursion (static register indexing).
 template <int J>
-GSP_DEV void diag16_cols(double (&row)[DPW], int l, double* rdiag, int* info, int gpos) {
+GSP_DEV void diag16_cols(double (&row)[DPW], double (&rd)[DPW], int l, int* info, int gpos) {
   if constexpr (J < DPW) {
     const double piv = __shfl_sync(0xffffffffu, row[J], J);
     if (!(piv > 0.0) && l == 0) atomicCAS(info, 0, gpos + J + 1);
     const double rinv = rsqrt(piv);
+    rd[J] = rinv;
     if (l == J) {
       row[J] = piv * rinv;
-      rdiag[J] = rinv;
     } else if (l > J) {
       row[J] *= rinv;
     }
@@ -37,146 +39,141 @@ GSP_DEV void diag16_cols(double (&row)[DPW], int l, double* rdiag, int* info, in
       const double lkj = __shfl_sync(0xffffffffu, row[J], k);
       if (l >= k) row[k] -= row[J] * lkj;
     }
-    diag16_cols<J + 1>(row, l, rdiag, info, gpos);
+    diag16_cols<J + 1>(row, rd, l, info, gpos);
   }
 }
 
-// rows below the diagonal block: x * D^T = b, one row per thread, D (16x16 lower) broadcast from shared memory
-template <int C_>
-GSP_DEV void diag_row_solve(double (&x)[DPW], const double* D16, const double* rdiag) {
-  if constexpr (C_ < DPW) {
-    double t0 = x[C_], t1 = 0.0, t2 = 0.0, t3 = 0.0;
+// inverse of that 16x16 factor, same warp: lane j solves L x = e_j by forward substitution (x[i] = inv[i][j]), the entries of L
+// come from their owner lanes by shuffle
+template <int I>
+GSP_DEV void diag16_inverse(const double (&row)[DPW], const double (&rd)[DPW], double (&x)[DPW], int l) {
+  if constexpr (I < DPW) {
+    double s0 = (l == I) ? 1.0 : 0.0, s1 = 0.0;
 #pragma unroll
-    for (int k = 0; k < C_; ++k) {
-      const double pr = x[k] * D16[C_ * (DPW + 1) + k];
-      if ((k & 3) == 0) t0 -= pr;
-      else if ((k & 3) == 1) t1 -= pr;
-      else if ((k & 3) == 2) t2 -= pr;
-      else t3 -= pr;
+    for (int k = 0; k < I; ++k) {
+      const double lik = __shfl_sync(0xffffffffu, row[k], I);
+      if (k & 1)
+        s1 -= lik * x[k];
+      else
+        s0 -= lik * x[k];
     }
-    x[C_] = ((t0 + t1) + (t2 + t3)) * rdiag[C_];
-    diag_row_solve<C_ + 1>(x, D16, rdiag);
+    x[I] = (s0 + s1) * rd[I];
+    diag16_inverse<I + 1>(row, rd, x, l);
   }
 }
 
-// X21 = -inv(C) * B * inv(A) for the pair of diagonal sub-blocks A = S[o:o+h, o:o+h], C = S[o+h:o+2h, o+h:o+2h]
-// (both already replaced by their inverses) and B = S[o+h:o+2h, o:o+h]; in place.  All 256 threads call this
-// with the same h; `pairs` pairs are processed at once (pairs * h == 64).
-template <int H>
-GSP_DEV void diag_inverse_level(double* S, int tid) {
-  constexpr int PAIRS = DB / (2 * H);
-  constexpr int TPP = 256 / PAIRS;          // threads per pair
-  constexpr int CG = (H * H) / TPP;          // outputs per thread (a run of CG columns of one row)
-  constexpr int CGS = CG < H ? CG : H;       // columns per thread in a row
-  static_assert(CG >= 1 && CG <= H, "tiling");
-  const int pr = tid / TPP, lt = tid - pr * TPP;
-  const int o = pr * 2 * H;
-  const int i = lt % H;                      // row within B
-  const int j0 = (lt / H) * CGS;             // first output column
-  double* Bm = S + (o + H) * DLD + o;        // B[i][k]   = Bm[i*DLD + k]
-  const double* Am = S + o * DLD + o;        // invA[k][j]
-  const double* Cm = S + (o + H) * DLD + o + H;  // invC[i][k]
-  double acc[CGS];
-  // T = B * invA  (invA lower triangular: k >= j)
-#pragma unroll
-  for (int c = 0; c < CGS; ++c) acc[c] = 0.0;
-  for (int k = j0; k < H; ++k) {
-    const double b = Bm[i * DLD + k];
-#pragma unroll
-    for (int c = 0; c < CGS; ++c)
-      if (k >= j0 + c) acc[c] += b * Am[k * DLD + j0 + c];
-  }
-  __syncthreads();
-#pragma unroll
-  for (int c = 0; c < CGS; ++c) Bm[i * DLD + j0 + c] = acc[c];
-  __syncthreads();
-  // X21 = -invC * T  (invC lower triangular: k <= i)
-#pragma unroll
-  for (int c = 0; c < CGS; ++c) acc[c] = 0.0;
-  for (int k = 0; k <= i; ++k) {
-    const double cv = Cm[i * DLD + k];
-#pragma unroll
-    for (int c = 0; c < CGS; ++c) acc[c] += cv * Bm[k * DLD + j0 + c];
-  }
-  __syncthreads();
-#pragma unroll
-  for (int c = 0; c < CGS; ++c) Bm[i * DLD + j0 + c] = -acc[c];
-  __syncthreads();
-}
+// DMMA fragment addressing on the column-major block: element (r, c) lives at S[c * DLD + r]
+//   A fragment (8 rows x 4 k):  lane holds M[r0 + lane/4][k0 + lane%4]
+//   B fragment (4 k x 8 cols):  lane holds M[k0 + lane%4][c0 + lane/4]          (row-type: B = a sub-block itself)
+//   B^T fragment:               lane holds M[c0 + lane/4][k0 + lane%4]          (B[k][n] = M[n][k]: same addressing as A)
+//   C fragment (8 x 8):         lane holds M[r0 + lane/4][c0 + 2*(lane%4) + {0,1}]
+GSP_DEV double frag_a(const double* S, int r0, int k0, int lane) { return S[(k0 + (lane & 3)) * DLD + r0 + (lane >> 2)]; }
+GSP_DEV double frag_b(const double* S, int k0, int c0, int lane) { return S[(c0 + (lane >> 2)) * DLD + k0 + (lane & 3)]; }
 
 // Factor A[blk,blk] (128x128, lower) in place -> L (strict upper zeroed), write inv(L) to invD.
+// One CTA, 8 warps.  Left-looking over 16-wide panels; everything but the 16x16 diagonal blocks runs on DMMA 8x8x4 tiles out of
+// shared memory:  (U) panel -= L[:, :c0] * L[c0:c0+16, :c0]^T   (F) warp 0 factors and inverts the 16x16 block in registers
+// (S) rows below = panel * inv(L16)^T.  The inverse of the whole block is then assembled from the eight 16x16 inverses by
+// X21 = -inv(C) * B * inv(A) over 16 -> 32 -> 64 wide halves, again on DMMA tiles (one 8-row block per warp and level).
 __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(double* __restrict__ A, long long lda, long long blk,
                                                             double* __restrict__ invD, int* __restrict__ info) {
   GSP_DYN_SMEM(smem);
-  double* S = reinterpret_cast<double*>(smem);   // [DB][DLD]
-  double* P = S + DB * DLD;                      // [DPW][DPW+1] pivot rows of the current panel
-  double* rinv = P + DPW * (DPW + 1);            // [DPW]
-  const int tid = threadIdx.x;
+  double* S = reinterpret_cast<double*>(smem);   // [DB cols][DLD]
+  double* Dv = S + DB * DLD;                     // [8 panels][16 k][DVL]: Dv[p][k * DVL + n] = inv(L16_p)[n][k]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   double* Ab = A + blk * DB * (lda + 1);
 
-  for (int idx = tid; idx < DB * DB; idx += 256) {
-    const int r = idx & (DB - 1), c = idx >> 7;
-    S[r * DLD + c] = (r >= c) ? Ab[r + (long long)c * lda] : 0.0;
+  // load the lower triangle (zeros above): 16 independent loads in flight per thread - a single CTA is latency-bound here.
+  // (One bulk async copy per column was measured SLOWER on the B200: 87 vs 65 us per block; 128 small, 16-byte-aligned copies
+  // from one SM serialise in the TMA unit.)
+  for (int base = 0; base < DB * DB; base += 16 * 256) {
+    double v[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int idx = base + u * 256 + tid;
+      const int r = idx & (DB - 1), c = idx >> 7;
+      v[u] = (r >= c) ? Ab[r + (long long)c * lda] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int idx = base + u * 256 + tid;
+      S[(idx >> 7) * DLD + (idx & (DB - 1))] = v[u];
+    }
   }
   __syncthreads();
 
   for (int p = 0; p < DB / DPW; ++p) {
     const int c0 = p * DPW;
-    // (a) 16x16 diagonal block in the registers of warp 0, then the rows below it, one per thread
-    if (tid < 32) {
-      const int l = tid;
-      double row[DPW];
+    // (U) left-looking update of the panel's rows c0..127 with the finished columns [0, c0).  Warp 0 takes the 16 diagonal rows
+    // and goes straight on to (F); warps 1-7 share the rows below meanwhile (they read rows c0..c0+15 only in columns < c0,
+    // which (F) does not touch).
+    if (p > 0) {
+      const int mb0 = c0 / 8 + (warp == 0 ? 0 : 1 + warp), mbstep = warp == 0 ? 1 : 7, mbend = warp == 0 ? c0 / 8 + 2 : DB / 8;
+      for (int mb = mb0; mb < mbend; mb += mbstep) {
+        const int r0 = mb * 8;
+        double acc[2][2];
 #pragma unroll
-      for (int k = 0; k < DPW; ++k) row[k] = (l < DPW) ? S[(c0 + l) * DLD + c0 + k] : 0.0;
-      diag16_cols<0>(row, l, rinv, info, (int)(blk * DB) + c0);
+        for (int nb = 0; nb < 2; ++nb) {
+          const double* cp = S + (c0 + nb * 8 + 2 * (lane & 3)) * DLD + r0 + (lane >> 2);
+          acc[nb][0] = cp[0];
+          acc[nb][1] = cp[DLD];
+        }
+        for (int k0 = 0; k0 < c0; k0 += 4) {
+          const double a = -frag_a(S, r0, k0, lane);
+          dmma884(acc[0][0], acc[0][1], a, frag_a(S, c0, k0, lane));       // B[k][n] = L[c0 + n][k0 + k]
+          dmma884(acc[1][0], acc[1][1], a, frag_a(S, c0 + 8, k0, lane));
+        }
+#pragma unroll
+        for (int nb = 0; nb < 2; ++nb) {
+          double* cp = S + (c0 + nb * 8 + 2 * (lane & 3)) * DLD + r0 + (lane >> 2);
+          cp[0] = acc[nb][0];
+          cp[DLD] = acc[nb][1];
+        }
+      }
+      __syncwarp();
+    }
+    // (F) 16x16 diagonal block: factor + inverse in the registers of warp 0
+    if (warp == 0) {
+      const int l = lane;
+      double row[DPW], rd[DPW], x[DPW];
+#pragma unroll
+      for (int k = 0; k < DPW; ++k) row[k] = (l < DPW) ? S[(c0 + k) * DLD + c0 + l] : 0.0;
+      diag16_cols<0>(row, rd, l, info, (int)(blk * DB) + c0);
+      diag16_inverse<0>(row, rd, x, l);
       if (l < DPW) {
+        double* dv = Dv + p * DPW * DVL + l * DVL;
 #pragma unroll
         for (int k = 0; k < DPW; ++k) {
-          const double v = (k <= l) ? row[k] : 0.0;
-          S[(c0 + l) * DLD + c0 + k] = v;
-          P[l * (DPW + 1) + k] = v;
+          S[(c0 + k) * DLD + c0 + l] = (k <= l) ? row[k] : 0.0;
+          dv[k] = (k >= l) ? x[k] : 0.0;   // inv[k][l], zero above the diagonal
         }
       }
     }
     __syncthreads();
-    if (tid < DB && tid >= c0 + DPW) {
-      double x[DPW];
-      double* srow = S + tid * DLD + c0;
-#pragma unroll
-      for (int k = 0; k < DPW; ++k) x[k] = srow[k];
-      diag_row_solve<0>(x, P, rinv);
-#pragma unroll
-      for (int k = 0; k < DPW; ++k) srow[k] = x[k];
-    }
-    __syncthreads();
-    // (b) trailing update of the lower triangle right of the panel (rank-16)
+    // (S) rows below the diagonal block: X = P * inv(L16)^T, in place (a warp only touches its own rows)
     {
-      const int ti = tid & 15, tk = tid >> 4;
-      for (int a = p + 1; a < DB / DPW; ++a) {
-        const int i = ti + DPW * a;
-        double ra[DPW];
+      const double* dv = Dv + p * DPW * DVL;
+      for (int mb = (c0 + DPW) / 8 + warp; mb < DB / 8; mb += 8) {
+        const int r0 = mb * 8;
+        double af[4];
 #pragma unroll
-        for (int c = 0; c < DPW; ++c) ra[c] = S[i * DLD + c0 + c];
-        // two output columns per iteration, four independent partial sums each: short dependent FMA chains
-        for (int b = p + 1; b <= a; b += 2) {
-          const int k0 = tk + DPW * b, k1 = k0 + DPW;
-          const bool do0 = i >= k0, do1 = (b + 1 <= a) && i >= k1;
-          const double* s0 = S + k0 * DLD + c0;
-          const double* s1 = S + (do1 ? k1 : k0) * DLD + c0;
-          double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
+        for (int ks = 0; ks < 4; ++ks) af[ks] = frag_a(S, r0, c0 + 4 * ks, lane);
+        double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
 #pragma unroll
-          for (int c = 0; c < DPW; c += 4) {
-            a0 += ra[c] * s0[c];
-            a1 += ra[c + 1] * s0[c + 1];
-            a2 += ra[c + 2] * s0[c + 2];
-            a3 += ra[c + 3] * s0[c + 3];
-            b0 += ra[c] * s1[c];
-            b1 += ra[c + 1] * s1[c + 1];
-            b2 += ra[c + 2] * s1[c + 2];
-            b3 += ra[c + 3] * s1[c + 3];
+        for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+          for (int nb = 0; nb < 2; ++nb) {
+            // B[k][n] = inv(L16)[n][k] = dv[k * DVL + n]
+            const double bf = dv[(4 * ks + (lane & 3)) * DVL + nb * 8 + (lane >> 2)];
+            dmma884(acc[nb][0], acc[nb][1], af[ks], bf);
           }
-          if (do0) S[i * DLD + k0] -= (a0 + a1) + (a2 + a3);
-          if (do1) S[i * DLD + k1] -= (b0 + b1) + (b2 + b3);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int nb = 0; nb < 2; ++nb) {
+          double* cp = S + (c0 + nb * 8 + 2 * (lane & 3)) * DLD + r0 + (lane >> 2);
+          cp[0] = acc[nb][0];
+          cp[DLD] = acc[nb][1];
         }
       }
     }
@@ -186,40 +183,74 @@ __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(double* __restrict__
   // write L (upper triangle explicitly zero)
   for (int idx = tid; idx < DB * DB; idx += 256) {
     const int r = idx & (DB - 1), c = idx >> 7;
-    Ab[r + (long long)c * lda] = (r >= c) ? S[r * DLD + c] : 0.0;
+    Ab[r + (long long)c * lda] = (r >= c) ? S[c * DLD + r] : 0.0;
   }
   __syncthreads();
 
-  // inverse of the lower-triangular block, blocked: 16x16 diagonal blocks first (one per warp, one column per lane) ...
-  {
-    const int w = tid >> 5, l = tid & 31;
-    const int o = w * DPW;
-    double x[DPW];
-    if (l < DPW) {
+  // inverse: the 16x16 diagonal inverses go in place ...
+  for (int idx = tid; idx < (DB / DPW) * DPW * DPW; idx += 256) {
+    const int p = idx >> 8, j = (idx >> 4) & 15, i = idx & 15;   // element inv_p[i][j]
+    S[(p * DPW + j) * DLD + p * DPW + i] = Dv[p * DPW * DVL + j * DVL + i];
+  }
+  __syncthreads();
+  // ... then X21 = -inv(C) B inv(A) level by level; the B blocks of a level have 64 rows in total: one 8-row block per warp
+  for (int H = DPW; H < DB; H *= 2) {
+    const int per = H / 8;                       // 8-row blocks per pair
+    const int o = (warp / per) * 2 * H;          // the pair's origin
+    const int i0 = (warp % per) * 8;             // this warp's rows within B / X21
+    const int rB = o + H + i0;                   // global row of the block
+    const int nblk = H / 8;
+    double acc[8][2];
+    {
+      // T = B * inv(A): T[i][n] = sum_{k >= n} B[i][k] invA[k][n]; own rows only -> in place
+      double af[16];
 #pragma unroll
-      for (int i = 0; i < DPW; ++i) {
-        double sacc = (i == l) ? 1.0 : 0.0;
+      for (int ks = 0; ks < 16; ++ks) af[ks] = (ks < H / 4) ? frag_a(S, rB, o + 4 * ks, lane) : 0.0;
 #pragma unroll
-        for (int k = 0; k < i; ++k) sacc -= S[(o + i) * DLD + o + k] * x[k];
-        x[i] = sacc / S[(o + i) * DLD + o + i];
+      for (int nb = 0; nb < 8; ++nb) {
+        acc[nb][0] = acc[nb][1] = 0.0;
+        if (nb < nblk) {
+#pragma unroll
+          for (int ks = 0; ks < 16; ++ks)
+            if (ks < H / 4 && ks >= 2 * nb) dmma884(acc[nb][0], acc[nb][1], af[ks], frag_b(S, o + 4 * ks, o + nb * 8, lane));
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int nb = 0; nb < 8; ++nb)
+        if (nb < nblk) {
+          double* cp = S + (o + nb * 8 + 2 * (lane & 3)) * DLD + rB + (lane >> 2);
+          cp[0] = acc[nb][0];
+          cp[DLD] = acc[nb][1];
+        }
+    }
+    __syncthreads();
+    {
+      // X21 = -inv(C) * T: X[i][n] = -sum_{k <= i} invC[i][k] T[k][n]; every warp reads all of T before anyone overwrites it
+#pragma unroll
+      for (int nb = 0; nb < 8; ++nb) acc[nb][0] = acc[nb][1] = 0.0;
+      for (int k0 = 0; k0 < i0 + 8; k0 += 4) {
+        const double a = -frag_a(S, rB, o + H + k0, lane);
+#pragma unroll
+        for (int nb = 0; nb < 8; ++nb)
+          if (nb < nblk) dmma884(acc[nb][0], acc[nb][1], a, frag_b(S, o + H + k0, o + nb * 8, lane));
       }
     }
     __syncthreads();
-    if (l < DPW) {
 #pragma unroll
-      for (int i = 0; i < DPW; ++i) S[(o + i) * DLD + o + l] = x[i];  // column l of the inverse (zero above the diagonal)
-    }
+    for (int nb = 0; nb < 8; ++nb)
+      if (nb < nblk) {
+        double* cp = S + (o + nb * 8 + 2 * (lane & 3)) * DLD + rB + (lane >> 2);
+        cp[0] = acc[nb][0];
+        cp[DLD] = acc[nb][1];
+      }
     __syncthreads();
   }
-  // ... then X21 = -inv(C) B inv(A) level by level (16 -> 32 -> 64 -> 128)
-  diag_inverse_level<16>(S, tid);
-  diag_inverse_level<32>(S, tid);
-  diag_inverse_level<64>(S, tid);
 
   double* Xo = invD + blk * DB * DB;
   for (int idx = tid; idx < DB * DB; idx += 256) {
     const int r = idx & (DB - 1), c = idx >> 7;
-    Xo[r + c * DB] = (r >= c) ? S[r * DLD + c] : 0.0;
+    Xo[r + c * DB] = (r >= c) ? S[c * DLD + r] : 0.0;
   }
 }
 

@@ -12,6 +12,9 @@
 
 namespace gsp {
 
+#ifndef GSP_CHOL_RESERVE_DEFAULT
+#define GSP_CHOL_RESERVE_DEFAULT 8  // measured on B200: C3 66.4 -> 64.6 ms, 32k nodes 394 -> 385 ms (tools/gpu_cholreserve.py); 16-24 the same, 48 worse
+#endif
 constexpr int DB = 128;   // diagonal block
 constexpr int DLD = 132;  // smem leading dimension of the COLUMN-major block S[c * DLD + r]: DMMA fragment loads of both kinds
                           // (8 consecutive rows x 4 columns, 4 consecutive rows x 8 columns) are bank-conflict-free for DLD = 4 mod 16
@@ -311,6 +314,7 @@ struct Chol {
   int* info;
   cudaError_t err = cudaSuccess;
   std::vector<cudaEvent_t> events;
+  int side_ctas = 0;  // > 0: look-ahead GEMMs run as persistent grids of this many CTAs, the other SMs stay free for the main stream
 
   double* at(int br, int bc) const { return A + (long long)br * DB + (long long)bc * DB * ld; }
 
@@ -344,6 +348,7 @@ struct Chol {
       g.B = at(br, bc + k0); g.ldb = ld;
       g.C = at(cr, cc); g.ldc = ld;
       g.mt = mt; g.nt = nt; g.K = kk * DB; g.tri = tri ? 1 : 0;
+      g.max_ctas = sliced ? side_ctas : 0;
       check(launch_gemm<GEMM_SUB, false>(s, g));
     }
   }
@@ -415,6 +420,20 @@ cudaError_t chol_factor(cudaStream_t st, cudaStream_t* side, int nside, double* 
     lookahead = (env && env[0] == '0') ? 0 : 1;
   }
   if (!lookahead) c.nside = 0;
+  // GSP_CHOL_RESERVE=r: SMs kept free of look-ahead work.  A one-CTA-per-tile look-ahead GEMM fills every SM for the length of
+  // a tile (1.2 ms at K = 8192), and the short kernels of the critical path queue behind it whatever their stream priority.
+  static int reserve = -1;
+  if (reserve < 0) {
+    const char* env = getenv("GSP_CHOL_RESERVE");
+    reserve = env ? atoi(env) : GSP_CHOL_RESERVE_DEFAULT;
+    if (reserve < 0) reserve = 0;
+  }
+  if (reserve > 0) {
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    c.side_ctas = sms - reserve > 8 ? sms - reserve : 8;
+  }
   c.potrf(0, nblocks, nullptr, 0);
   // every side stream was joined into `st` by the events waited on above, except possibly none: nothing left pending
   for (cudaEvent_t ev : c.events) cudaEventDestroy(ev);

@@ -51,6 +51,8 @@ struct GemmArgs {
   const long long* sinds;
   double addmu;
   long long Ns, R;
+  long long ntiles;  // filled by launch_gemm_cfg
+  int max_ctas;      // > 0: persistent grid of at most this many CTAs walking the tiles (look-ahead streams leave SMs free)
 };
 
 template <int MODE, bool BK, int TM, int TN, int WM, int WN>
@@ -62,10 +64,18 @@ __global__ void __launch_bounds__(GemmCfg<TM, TN, WM, WN>::THREADS, 1) gemm_dmma
   mbar_t* full = reinterpret_cast<mbar_t*>(smem + GSTAGES * C_::STAGE_BYTES);
   mbar_t* empty = full + GSTAGES;
 
-  // tile coordinates
-  int ti, tj;
-  {
-    const long long t = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < GSTAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], CW);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  // tile t -> (ti, tj, chunks of K)
+  auto decode = [&](long long t, int& ti, int& tj, int& nchunks) {
     if (g.tri) {
       int i = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
       while ((long long)(i + 1) * (i + 2) / 2 <= t) ++i;
@@ -80,31 +90,27 @@ __global__ void __launch_bounds__(GemmCfg<TM, TN, WM, WN>::THREADS, 1) gemm_dmma
       ti = (int)(t % g.mt);
       tj = (int)(t / g.mt);
     }
-  }
-  int kend = g.K;
-  if (g.klimit) {
-    long long lim = (long long)(ti + 1) * TM;
-    if (lim < kend) kend = (int)lim;
-  }
-  const int nchunks = kend / GKC;
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < GSTAGES; ++s) {
-      mbar_init(&full[s], 1);
-      mbar_init(&empty[s], CW);
+    int kend = g.K;
+    if (g.klimit) {
+      long long lim = (long long)(ti + 1) * TM;
+      if (lim < kend) kend = (int)lim;
     }
-    fence_mbar_init();
-  }
-  __syncthreads();
+    nchunks = kend / GKC;
+  };
+  // The grid is either one CTA per tile or (max_ctas) a persistent one walking the tiles; `cg` numbers the K chunks of all the
+  // tiles a CTA processes, so the ring and its mbarrier phases simply keep running across tiles.
 
   if (warp == CW) {
     // ------------------------------------------------------------ producer
+    long long cg = 0;
+    for (long long t = blockIdx.x; t < g.ntiles; t += gridDim.x) {
+    int ti, tj, nchunks;
+    decode(t, ti, tj, nchunks);
     const double* Abase = g.A + (long long)ti * TM;
     const double* Bbase = BK ? g.B + (long long)tj * TN * g.ldb : g.B + (long long)tj * TN;
-    for (int c = 0; c < nchunks; ++c) {
-      const int s = c % GSTAGES;
-      const uint32_t ph = (uint32_t)((c / GSTAGES) & 1);
+    for (int c = 0; c < nchunks; ++c, ++cg) {
+      const int s = (int)(cg % GSTAGES);
+      const uint32_t ph = (uint32_t)((cg / GSTAGES) & 1);
       mbar_wait(&empty[s], ph ^ 1u);
       unsigned char* sa = stage_base + s * C_::STAGE_BYTES;
       unsigned char* sb = sa + C_::A_BYTES;
@@ -125,21 +131,26 @@ __global__ void __launch_bounds__(GemmCfg<TM, TN, WM, WN>::THREADS, 1) gemm_dmma
         }
       }
     }
+    }
     return;
   }
 
   // -------------------------------------------------------------- consumers
   const int wm = warp % WM, wn = warp / WM;
   const int lr = lane >> 2, lk = lane & 3;
+  long long cg = 0;
+  for (long long t = blockIdx.x; t < g.ntiles; t += gridDim.x) {
+  int ti, tj, nchunks;
+  decode(t, ti, tj, nchunks);
   double acc[FM][FN][2];
 #pragma unroll
   for (int a = 0; a < FM; ++a)
 #pragma unroll
     for (int b = 0; b < FN; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
 
-  for (int c = 0; c < nchunks; ++c) {
-    const int s = c % GSTAGES;
-    const uint32_t ph = (uint32_t)((c / GSTAGES) & 1);
+  for (int c = 0; c < nchunks; ++c, ++cg) {
+    const int s = (int)(cg % GSTAGES);
+    const uint32_t ph = (uint32_t)((cg / GSTAGES) & 1);
     mbar_wait(&full[s], ph);
     const double* sa = reinterpret_cast<const double*>(stage_base + s * C_::STAGE_BYTES);
     const double* sb = reinterpret_cast<const double*>(stage_base + s * C_::STAGE_BYTES + C_::A_BYTES);
@@ -190,10 +201,12 @@ __global__ void __launch_bounds__(GemmCfg<TM, TN, WM, WN>::THREADS, 1) gemm_dmma
       }
     }
   }
+  }
 }
 
 template <int MODE, bool BK, int TM, int TN, int WM, int WN>
-inline cudaError_t launch_gemm_cfg(cudaStream_t st, const GemmArgs& g) {
+inline cudaError_t launch_gemm_cfg(cudaStream_t st, const GemmArgs& g0) {
+  GemmArgs g = g0;
   using C_ = GemmCfg<TM, TN, WM, WN>;
   auto kfn = gemm_dmma_kernel<MODE, BK, TM, TN, WM, WN>;
   // per-device attribute, cheap host-side call: set it on every launch (multi-device contexts)
@@ -201,8 +214,16 @@ inline cudaError_t launch_gemm_cfg(cudaStream_t st, const GemmArgs& g) {
   if (e != cudaSuccess) return e;
   long long tiles = g.tri ? (long long)g.mt * (g.mt + 1) / 2 : (long long)g.mt * g.nt;
   if (tiles <= 0 || g.K <= 0) return cudaSuccess;
+  g.ntiles = tiles;
+  static int force_ctas = -1;  // GSP_GEMM_MAX_CTAS (tests): every GEMM runs as a persistent grid of at most this many CTAs
+  if (force_ctas < 0) {
+    const char* env = getenv("GSP_GEMM_MAX_CTAS");
+    force_ctas = env ? atoi(env) : 0;
+  }
+  if (force_ctas > 0) g.max_ctas = force_ctas;
+  const long long grid = (g.max_ctas > 0 && g.max_ctas < tiles) ? g.max_ctas : tiles;
   ProfScope prof_(MODE == GEMM_SAMPLE ? "gemm_dmma_sample" : (MODE == GEMM_SET ? "gemm_dmma_trsm" : "gemm_dmma_update"), st);
-  GSP_LAUNCH(kfn, dim3((unsigned)tiles), dim3(C_::THREADS), (size_t)C_::SMEM_BYTES, st, g);
+  GSP_LAUNCH(kfn, dim3((unsigned)grid), dim3(C_::THREADS), (size_t)C_::SMEM_BYTES, st, g);
   g_launches++;
   return cudaGetLastError();
 }

@@ -67,7 +67,7 @@ struct mbar_t {
 };
 GSP_DEV void mbar_init(mbar_t* b, int count) { b->expected = count; b->pending = count; b->tx = 0; b->phase = 0; }
 GSP_DEV void mbar_check_(mbar_t* b) {
-  if (b->pending == 0 && b->tx == 0) { b->phase ^= 1; b->pending = b->expected; }
+  if (b->pending == 0 && b->tx == 0) { b->phase ^= 1; b->pending = b->expected; emu::note_event(); }
 }
 GSP_DEV void mbar_arrive(mbar_t* b) { b->pending--; mbar_check_(b); }
 GSP_DEV void mbar_arrive_expect_tx(mbar_t* b, uint32_t bytes) { b->tx += (int)bytes; b->pending--; mbar_check_(b); }
@@ -192,6 +192,7 @@ GSP_DEV int ld_acquire_gpu(const int* p) {
 GSP_DEV void red_release_gpu_add(int* p, int v) {
 #ifdef GSP_EMU
   *p += v;
+  emu::note_event();
 #else
   asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 #endif

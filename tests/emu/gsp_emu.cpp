@@ -36,7 +36,7 @@ void named_bar_sync(int id, int count) {
   BlockState& bs = g->blocks[f.block];
   int gen = bs.named_gen[id];
   bs.named_count[id]++;
-  if (bs.named_count[id] >= count) { bs.named_count[id] = 0; bs.named_gen[id]++; return; }
+  if (bs.named_count[id] >= count) { bs.named_count[id] = 0; bs.named_gen[id]++; g->event = true; return; }
   while (bs.named_gen[id] == gen) { f.wait_kind = 4; yield_to_sched(); }
   f.wait_kind = 0;
 }
@@ -67,7 +67,7 @@ static void warp_rendezvous() {
   int w = warp_of(g->cur);
   int gen = g->warp_gen[w];
   g->warp_arrived[w]++;
-  if (g->warp_arrived[w] >= live_lanes_in_warp(g->cur)) { g->warp_arrived[w] = 0; g->warp_gen[w]++; return; }
+  if (g->warp_arrived[w] >= live_lanes_in_warp(g->cur)) { g->warp_arrived[w] = 0; g->warp_gen[w]++; g->event = true; return; }
   while (g->warp_gen[w] == gen) { f.wait_kind = 4; yield_to_sched(); }
   f.wait_kind = 0;
 }
@@ -123,7 +123,8 @@ static void run_blocks(State& st, dim3 grid, dim3 block, size_t smem, unsigned f
   st.live = st.nthreads;
   long idle_rounds = 0;
   while (st.live > 0) {
-    bool progressed = false;
+    bool progressed = st.event;
+    st.event = false;
     for (int t = 0; t < st.nthreads; ++t) {
       Fiber& f = st.fibers[t];
       if (f.done || f.wait_kind == 1) continue;

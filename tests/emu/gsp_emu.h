@@ -83,6 +83,8 @@ static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) {
   p->multiProcessorCount = 4; p->sharedMemPerBlockOptin = 227 * 1024; std::strcpy(p->name, "gsp-emu"); p->major = 10; p->minor = 0;
   return cudaSuccess;
 }
+enum { cudaDevAttrMultiProcessorCount = 16 };
+static inline cudaError_t cudaDeviceGetAttribute(int* v, int, int) { *v = 4; return cudaSuccess; }
 static inline cudaError_t cudaDeviceCanAccessPeer(int* can, int, int) { *can = 0; return cudaSuccess; }
 static inline cudaError_t cudaDeviceEnablePeerAccess(int, unsigned) { return cudaSuccess; }
 static inline cudaError_t cudaMemcpyPeerAsync(void* d, int, const void* s, int, size_t n, cudaStream_t = 0) { std::memmove(d, s, n); return cudaSuccess; }
@@ -124,6 +126,9 @@ struct State {
   // warp rendezvous
   std::vector<int> warp_arrived, warp_gen;
   std::vector<uint64_t> warp_buf;   // 32 slots per warp
+  // set whenever a wait condition is satisfied (warp rendezvous completes, mbarrier phase flips, a flag is released): kernels
+  // whose only yield points are spin-type waits (mbarrier pipelines) would otherwise look deadlocked to the scheduler
+  bool event = false;
 };
 
 extern State* g;
@@ -134,6 +139,7 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& bod
 void launch_coop(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body);  // all blocks co-resident
 inline unsigned char* dyn_smem() { return g->blocks[g->fibers[g->cur].block].dyn_smem; }
 void yield_to_sched();
+inline void note_event();
 void syncthreads();
 void named_bar_sync(int id, int count);
 void named_bar_arrive(int id, int count);
@@ -142,6 +148,7 @@ void warp_exchange(uint64_t v, uint64_t out[32]);
 void warp_sync();
 // cooperative spin: call inside a polling loop so other fibers can make progress
 inline void spin_yield() { g->fibers[g->cur].wait_kind = 4; yield_to_sched(); g->fibers[g->cur].wait_kind = 0; }
+inline void note_event() { g->event = true; }
 inline int lane() { return (int)(g_threadIdx.x + g_blockDim.x * (g_threadIdx.y + g_blockDim.y * g_threadIdx.z)) & 31; }
 
 }  // namespace emu

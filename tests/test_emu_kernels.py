@@ -269,6 +269,10 @@ def test_cholesky_big_tile_path(emu_lib):
     env = dict(os.environ, GSP_GEMM_SMALL_TILES="0", GSP_CHOL_LOOKAHEAD="1")
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
     assert out.returncode == 0 and "OK" in out.stdout, out.stderr[-1500:]
+    # persistent grids (look-ahead GEMMs that leave SMs free): 3 CTAs walk the 64x64 tiles, the ring runs on across tiles
+    env = dict(os.environ, GSP_GEMM_MAX_CTAS="3")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0 and "OK" in out.stdout, out.stderr[-1500:]
 
 
 def test_multi_device_block_cyclic_cholesky(emu_lib):

@@ -15,7 +15,17 @@
 
 namespace gsp {
 
-GSP_HD constexpr int p2_stages(int N) { return N <= 16 ? 1 : ((N == 512 || N >= 1024) ? 3 : 2); }
+// GSP_P2_R8 = 1 (experiment): extents 128 and 256 on 8 register slots per thread (radix 8 x 4 x 4 / 8 x 8 x 4, two exchanges) instead of
+// 16 (radix 16 x 8 / 16 x 16, one exchange): half the registers per thread, twice the threads per line.
+#ifndef GSP_P2_R8
+#define GSP_P2_R8 0
+#endif
+#ifndef GSP_P2_B256
+#define GSP_P2_B256 8  // kx per bundle of the strided passes for extents <= 512
+#endif
+GSP_HD constexpr int p2_stages(int N) {
+  return N <= 16 ? 1 : ((N == 512 || N >= 1024 || (GSP_P2_R8 && (N == 128 || N == 256))) ? 3 : 2);
+}
 GSP_HD constexpr int p2_radix_fwd(int N, int s) {
   switch (N) {
     case 2: return 2;
@@ -24,8 +34,8 @@ GSP_HD constexpr int p2_radix_fwd(int N, int s) {
     case 16: return 16;
     case 32: return s == 0 ? 16 : 2;
     case 64: return 8;
-    case 128: return s == 0 ? 16 : 8;
-    case 256: return 16;
+    case 128: return GSP_P2_R8 ? (s == 0 ? 8 : 4) : (s == 0 ? 16 : 8);
+    case 256: return GSP_P2_R8 ? (s < 2 ? 8 : 4) : 16;
     case 512: return 8;
     case 1024: return s < 2 ? 16 : 4;
     case 2048: return s < 2 ? 16 : 8;
@@ -145,7 +155,7 @@ struct RowLay {  // x passes: one padded row per line, one extra element every 2
 
 enum { P2_FWD = 1, P2_MUL = 2, P2_INV = 4 };
 
-GSP_HD constexpr int p2_bundle(int N) { return N <= 512 ? 8 : (N <= 2048 ? 4 : 2); }
+GSP_HD constexpr int p2_bundle(int N) { return N <= 512 ? GSP_P2_B256 : (N <= 2048 ? 4 : 2); }
 
 // All three pass kernels are PERSISTENT and software-pipelined: a CTA walks over its work items
 // (line bundles / row groups); while it transforms item i out of shared-memory stage i&1, the TMA
@@ -174,7 +184,9 @@ struct StridedCfg {
 #ifndef GSP_STRIDED_MINB
 #define GSP_STRIDED_MINB 4
 #endif
-  static constexpr int MINB = (STAGES == 1 && THREADS <= 128) ? GSP_STRIDED_MINB : 1;  // register cap for that many CTAs per SM
+  // register cap for that many CTAs per SM (8-slot experiment: 24 warps per SM)
+  static constexpr int MINB = (GSP_P2_R8 && SL == 8 && STAGES == 1 && THREADS <= 256) ? 768 / THREADS
+                                                                                      : ((STAGES == 1 && THREADS <= 128) ? GSP_STRIDED_MINB : 1);
 };
 
 template <int N, int B, int FLAGS, int STAGES>
@@ -327,7 +339,7 @@ struct XCfg {
 #ifndef GSP_X_MINB2
 #define GSP_X_MINB2 1  // CTAs per SM the register allocation of the 2-stage x kernels must allow
 #endif
-  static constexpr int MINB = (STAGES == 1 && THREADS <= 128) ? 4 : ((THREADS <= 128) ? GSP_X_MINB2 : 1);
+  static constexpr int MINB = (GSP_P2_R8 && SL == 8 && THREADS <= 128) ? 5 : ((STAGES == 1 && THREADS <= 128) ? 4 : ((THREADS <= 128) ? GSP_X_MINB2 : 1));
 };
 
 // noise source of the forward x pass when no array is injected: uniforms from the counter RNG (rng.cuh), generated straight into

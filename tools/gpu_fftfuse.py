@@ -20,7 +20,7 @@ for fuse in (0, 1):
     for lanes in lanes_list:
         os.environ["GSP_FFT_FUSE"] = str(fuse); os.environ["GSP_FFT_LANES"] = str(lanes)
         plan = gsp.FFTPlan(lib, st, dims, [0.0] * 3, [1.0] * 3)
-        for mode in ("inject", "rng"):
+        for mode in ("inject", "rng") if os.environ.get("FUSE_RNG", "0") == "1" else ("inject",):
             best = 1e9
             for _ in range(4):
                 torch.cuda.synchronize()

@@ -312,7 +312,9 @@ extern "C" int gsp_potrf(gsp_ctx* ctx, int64_t n, double* A) {
     else pad[(size_t)j * np + j] = 1.0;
   }
   GSP_CUDA_OK(ctx, cudaMemcpyAsync(dA.p, pad.data(), pad.size() * sizeof(double), cudaMemcpyHostToDevice, dc.stream));
-  GSP_CUDA_OK(ctx, chol_factor(dc.stream, dc.side, DevCtx::kSide, dA.as<double>(), np, nb, dinv.as<double>(), dinfo.as<int>()));
+  DevBuf work;
+  if (chol_work_doubles(nb) > 0) GSP_CUDA_OK(ctx, work.alloc(dc.dev, chol_work_doubles(nb) * sizeof(double)));
+  GSP_CUDA_OK(ctx, chol_factor(dc.stream, dc.side, DevCtx::kSide, dA.as<double>(), np, nb, dinv.as<double>(), dinfo.as<int>(), work.as<double>()));
   int info = 0;
   GSP_CUDA_OK(ctx, cudaMemcpyAsync(&info, dinfo.p, sizeof(int), cudaMemcpyDeviceToHost, dc.stream));
   GSP_CUDA_OK(ctx, cudaMemcpyAsync(pad.data(), dA.p, pad.size() * sizeof(double), cudaMemcpyDeviceToHost, dc.stream));

@@ -79,7 +79,8 @@ GSP_DEV double frag_b(const double* S, int k0, int c0, int lane) { return S[(c0 
 // (S) rows below = panel * inv(L16)^T.  The inverse of the whole block is then assembled from the eight 16x16 inverses by
 // X21 = -inv(C) * B * inv(A) over 16 -> 32 -> 64 wide halves, again on DMMA tiles (one 8-row block per warp and level).
 __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(double* __restrict__ A, long long lda, long long blk,
-                                                            double* __restrict__ invD, int* __restrict__ info) {
+                                                            double* __restrict__ invD, int* __restrict__ info,
+                                                            double* __restrict__ inv2, long long ld2) {
   GSP_DYN_SMEM(smem);
   double* S = reinterpret_cast<double*>(smem);   // [DB cols][DLD]
   double* Dv = S + DB * DLD;                     // [8 panels][16 k][DVL]: Dv[p][k * DVL + n] = inv(L16_p)[n][k]
@@ -253,7 +254,9 @@ __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(double* __restrict__
   double* Xo = invD + blk * DB * DB;
   for (int idx = tid; idx < DB * DB; idx += 256) {
     const int r = idx & (DB - 1), c = idx >> 7;
-    Xo[r + c * DB] = (r >= c) ? S[c * DLD + r] : 0.0;
+    const double v = (r >= c) ? S[c * DLD + r] : 0.0;
+    Xo[r + c * DB] = v;
+    if (inv2) inv2[r + c * ld2] = v;  // second copy on the diagonal of the panel-inverse workspace (chol_factor)
   }
 }
 
@@ -315,6 +318,44 @@ struct Chol {
   cudaError_t err = cudaSuccess;
   std::vector<cudaEvent_t> events;
   int side_ctas = 0;  // > 0: look-ahead GEMMs run as persistent grids of this many CTAs, the other SMs stay free for the main stream
+  // panel inverses (chol_factor with a workspace): group g = blocks [8g, 8g + 8) owns a dense 1024 x 1024 slot; the inverse of an
+  // aligned s-block panel (s = 1, 2, 4, 8) is the s*128-square sub-matrix on the slot's diagonal (ld = PIL).  built[k] marks the
+  // panels of size 2^k that are complete.
+  static constexpr int PIG = 8;
+  static constexpr long long PIL = (long long)PIG * DB;
+  double* linv = nullptr;
+  double* tmp = nullptr;   // (PIG/2 * 128)^2 scratch of the level builds
+  double* xbuf = nullptr;  // nb_total x PIG blocks: result of a panel solve before it is copied over the panel
+  int nb_total = 0;
+  std::vector<unsigned char> built[4];
+
+  double* linv_at(int blk_row, int blk_col) const {  // both inside the same 8-group
+    const int grp = blk_row / PIG;
+    return linv + (long long)grp * PIL * PIL + (long long)(blk_row % PIG) * DB + (long long)(blk_col % PIG) * DB * PIL;
+  }
+  static int lg2(int s) { return s == 1 ? 0 : (s == 2 ? 1 : (s == 4 ? 2 : (s == 8 ? 3 : -1))); }
+  bool panel_ready(int c0, int nc) const {
+    const int k = lg2(nc);
+    return linv && k >= 0 && c0 % nc == 0 && (size_t)(c0 / nc) < built[k].size() && built[k][c0 / nc];
+  }
+  // inverse of the aligned s-block panel at o from its two halves: X21 = -inv(C) * (B * inv(A))
+  void build_panel_inverse(int o, int s) {
+    const int k = lg2(s), h = s / 2;
+    if (!linv || k < 1 || o % s != 0 || !panel_ready(o, h) || !panel_ready(o + h, h)) return;
+    GemmArgs g{};
+    g.A = at(o + h, o); g.lda = ld;
+    g.B = linv_at(o, o); g.ldb = PIL;            // K x N: inv(A)[k][j]
+    g.C = tmp; g.ldc = (long long)h * DB;
+    g.mt = h; g.nt = h; g.K = h * DB;
+    check(launch_gemm<GEMM_SET, true>(st, g));
+    GemmArgs g2{};
+    g2.A = linv_at(o + h, o + h); g2.lda = PIL;  // inv(C)
+    g2.B = tmp; g2.ldb = (long long)h * DB;      // K x N: T
+    g2.C = linv_at(o + h, o); g2.ldc = PIL;      // zero on entry (workspace cleared by chol_factor)
+    g2.mt = h; g2.nt = h; g2.K = h * DB;
+    check(launch_gemm<GEMM_SUB, true>(st, g2));
+    built[k][o / s] = 1;
+  }
 
   double* at(int br, int bc) const { return A + (long long)br * DB + (long long)bc * DB * ld; }
 
@@ -356,6 +397,17 @@ struct Chol {
   // X * L[c0:c0+nc, c0:c0+nc]^T = A[r0:r0+nr, c0:c0+nc]   (in place)
   void trsm(int r0, int nr, int c0, int nc) {
     if (nr <= 0 || nc <= 0) return;
+    if (nc > 1 && panel_ready(c0, nc)) {
+      GemmArgs g{};
+      g.A = at(r0, c0); g.lda = ld;
+      g.B = linv_at(c0, c0); g.ldb = PIL;   // N x K: inv(L)[j][k], lower triangular
+      g.C = xbuf; g.ldc = (long long)nr * DB;
+      g.mt = nr; g.nt = nc; g.K = nc * DB; g.strip = 1;
+      check(launch_gemm<GEMM_SET, false>(st, g));
+      check(cudaMemcpy2DAsync(at(r0, c0), (size_t)ld * sizeof(double), xbuf, (size_t)nr * DB * sizeof(double), (size_t)nr * DB * sizeof(double),
+                              (size_t)nc * DB, cudaMemcpyDeviceToDevice, st));
+      return;
+    }
     if (nc == 1) {
       GemmArgs g{};
       g.A = at(r0, c0); g.lda = ld;
@@ -379,9 +431,11 @@ struct Chol {
       auto kfn = potrf_diag_kernel;
       check(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM));
       ProfScope prof_("potrf_diag", st);
-      GSP_LAUNCH(kfn, dim3(1), dim3(256), (size_t)DIAG_SMEM, st, A, ld, (long long)o, invD, info);
+      double* inv2 = linv ? linv_at(o, o) : nullptr;
+      GSP_LAUNCH(kfn, dim3(1), dim3(256), (size_t)DIAG_SMEM, st, A, ld, (long long)o, invD, info, inv2, PIL);
       g_launches++;
       check(cudaGetLastError());
+      if (linv) built[0][o] = 1;
       return;
     }
     const int n1 = n / 2, n2 = n - n1;
@@ -392,6 +446,7 @@ struct Chol {
     if (n2 == 1 || depth >= nside || n < 8) {
       update(st, false, p, p, n2, n2, p, o, p, o, n1, true);
       potrf(p, n2, nullptr, depth + 1);
+      if (n <= PIG) build_panel_inverse(o, n);
       return;
     }
     // look-ahead: the leading half of A22 (what the next level factors first) is updated on the main stream,
@@ -405,15 +460,48 @@ struct Chol {
     update(sd, true, p + m1, p + m1, m2, m2, p + m1, o, p + m1, o, n1, true);
     cudaEvent_t rest_done = record(sd);
     potrf(p, n2, rest_done, depth + 1);
+    if (n <= PIG) build_panel_inverse(o, n);
   }
 };
 
 }  // namespace
 
-cudaError_t chol_factor(cudaStream_t st, cudaStream_t* side, int nside, double* A, long long ld, int nblocks, double* invD, int* info) {
+// GSP_CHOL_PANELS=1 turns the panel-inverse solves on.  Measured on the B200 (session 3): C3 factorization 70.0 ms against 64.7 ms for
+// the recursive solves, 32k nodes 387 against 384 ms (an in-place variant, one CTA per 64-row strip walking the column tiles right to
+// left, was worse still: 73.9 ms) - the recursion's many small launches run back to back and spread over more CTAs than one
+// triangular-K GEMM per panel, so the saved launches buy nothing.  Off by default.
+static bool chol_panels_enabled() {
+  static int use_panels = -1;
+  if (use_panels < 0) {
+    const char* env = getenv("GSP_CHOL_PANELS");
+    use_panels = (env && env[0] == '1') ? 1 : 0;
+  }
+  return use_panels != 0;
+}
+
+size_t chol_work_doubles(int nblocks) {
+  if (!chol_panels_enabled()) return 0;
+  const size_t groups = (size_t)(nblocks + Chol::PIG - 1) / Chol::PIG;
+  return groups * (size_t)Chol::PIL * Chol::PIL + (size_t)(Chol::PIG / 2 * DB) * (Chol::PIG / 2 * DB) +
+         (size_t)nblocks * DB * Chol::PIL;
+}
+
+cudaError_t chol_factor(cudaStream_t st, cudaStream_t* side, int nside, double* A, long long ld, int nblocks, double* invD, int* info,
+                        double* work) {
   Chol c{st, side, nside, A, ld, invD, info};
   cudaError_t e = cudaMemsetAsync(info, 0, sizeof(int), st);
   if (e != cudaSuccess) return e;
+  if (work && chol_panels_enabled() && nblocks >= 4) {
+    const size_t groups = (size_t)(nblocks + Chol::PIG - 1) / Chol::PIG;
+    c.linv = work;
+    c.tmp = work + groups * (size_t)Chol::PIL * Chol::PIL;
+    c.xbuf = c.tmp + (size_t)(Chol::PIG / 2 * DB) * (Chol::PIG / 2 * DB);
+    c.nb_total = nblocks;
+    for (int k = 0; k < 4; ++k) c.built[k].assign((size_t)(nblocks >> k) + 1, 0);
+    // the level builds and the strip kernels read whole tiles of the (triangular) inverses: everything not written must be zero
+    e = cudaMemsetAsync(work, 0, groups * (size_t)Chol::PIL * Chol::PIL * sizeof(double), st);
+    if (e != cudaSuccess) return e;
+  }
   static int lookahead = -1;  // GSP_CHOL_LOOKAHEAD=0 disables the side streams (A/B measurements)
   if (lookahead < 0) {
     const char* env = getenv("GSP_CHOL_LOOKAHEAD");

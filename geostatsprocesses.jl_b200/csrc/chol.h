@@ -11,7 +11,11 @@ namespace gsp {
 // *info (device int): 0 or 1-based index of the first non-positive pivot.
 // `side[nside]`: low-priority streams used for look-ahead (the bulk of every trailing update runs there while
 // the next diagonal block / panel proceeds on `st`); everything is joined back into `st` before returning.
-cudaError_t chol_factor(cudaStream_t st, cudaStream_t* side, int nside, double* A, long long ld, int nblocks, double* invD, int* info);
+// `work` (optional, chol_work_doubles(nblocks) doubles - 0 unless GSP_CHOL_PANELS=1, an experiment measured slower): room for the inverses of the aligned 2-, 4- and 8-block diagonal panels; with it
+// every triangular solve against a panel of <= 8 blocks is ONE tile GEMM with the panel's inverse (+ a copy) instead of a recursion of 2 nc - 1 launches.
+size_t chol_work_doubles(int nblocks);
+cudaError_t chol_factor(cudaStream_t st, cudaStream_t* side, int nside, double* A, long long ld, int nblocks, double* invD, int* info,
+                        double* work = nullptr);
 // multi-GPU variant: every device holds a full (nblocks*128)^2 buffer `A` with the matrix assembled; panels of PB blocks are
 // owned cyclically, factored by their owner and pushed peer-to-peer into the same place on all devices (chol.cu).
 struct MgDev {

@@ -51,6 +51,8 @@ struct GemmArgs {
   const long long* sinds;
   double addmu;
   long long Ns, R;
+  int strip;         // 1: B (N x K) is lower triangular -> k < (tj+1)*TN only; column tiles heaviest first (triangular solve by an
+                     // explicit panel inverse, out of place: C must not alias A)
   long long ntiles;  // filled by launch_gemm_cfg
   int max_ctas;      // > 0: persistent grid of at most this many CTAs walking the tiles (look-ahead streams leave SMs free)
 };
@@ -86,6 +88,9 @@ __global__ void __launch_bounds__(GemmCfg<TM, TN, WM, WN>::THREADS, 1) gemm_dmma
       // lower-triangular A: row tile ti costs (ti+1) chunks -> heaviest rows first, columns fastest (LPT order)
       tj = (int)(t % g.nt);
       ti = g.mt - 1 - (int)(t / g.nt);
+    } else if (g.strip) {
+      ti = (int)(t % g.mt);
+      tj = g.nt - 1 - (int)(t / g.mt);
     } else {
       ti = (int)(t % g.mt);
       tj = (int)(t / g.mt);
@@ -93,6 +98,10 @@ __global__ void __launch_bounds__(GemmCfg<TM, TN, WM, WN>::THREADS, 1) gemm_dmma
     int kend = g.K;
     if (g.klimit) {
       long long lim = (long long)(ti + 1) * TM;
+      if (lim < kend) kend = (int)lim;
+    }
+    if (g.strip) {
+      long long lim = (long long)(tj + 1) * TN;
       if (lim < kend) kend = (int)lim;
     }
     nchunks = kend / GKC;

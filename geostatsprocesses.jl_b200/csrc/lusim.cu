@@ -276,6 +276,8 @@ extern "C" int gsp_lu_plan_create(gsp_ctx* ctx, const gsp_cov_model* cov, const 
   DevCtx& dc = *d0->dc;
   cudaSetDevice(dc.dev);
   cudaStream_t st = dc.stream;
+  DevBuf work;  // panel inverses of the single-device factorization: only needed while it runs, freed when this function returns
+  if (!mg && chol_work_doubles(nb) > 0) GSP_CUDA_OK(ctx, work.alloc(dc.dev, chol_work_doubles(nb) * sizeof(double)));
   GSP_CUDA_OK(ctx, cudaEventRecord(tev[1], st));
   // a2/a3: one joint Cholesky (lusim.jl:92 or 98-103)
   if (mg) {
@@ -285,7 +287,8 @@ extern "C" int gsp_lu_plan_create(gsp_ctx* ctx, const gsp_cov_model* cov, const 
     GSP_CUDA_OK(ctx, chol_factor_mg(mds, p->Np, nb, mg_pb));
     cudaSetDevice(dc.dev);
   } else {
-    GSP_CUDA_OK(ctx, chol_factor(st, dc.side, DevCtx::kSide, d0->A.as<double>(), p->Np, nb, d0->invD.as<double>(), d0->info.as<int>()));
+    GSP_CUDA_OK(ctx, chol_factor(st, dc.side, DevCtx::kSide, d0->A.as<double>(), p->Np, nb, d0->invD.as<double>(), d0->info.as<int>(),
+                                 work.as<double>()));
   }
   GSP_CUDA_OK(ctx, cudaEventRecord(tev[2], st));
   // d2 = A21 * (L11 \ z1)   (lusim.jl:102); zero when unconditional (lusim.jl:91)

@@ -275,6 +275,26 @@ def test_cholesky_big_tile_path(emu_lib):
     assert out.returncode == 0 and "OK" in out.stdout, out.stderr[-1500:]
 
 
+def test_cholesky_panel_inverse_solves(emu_lib):
+    """opt-in GSP_CHOL_PANELS=1 (measured slower on the B200, kept for A/B): inverses of aligned 2-block panels built from the diagonal
+    blocks' inverses, triangular solves as one triangular-K tile GEMM + copy.  5 blocks exercise the level-2 build and solve."""
+    import os, subprocess, sys, textwrap
+    code = textwrap.dedent("""
+        import sys, numpy as np, scipy.linalg
+        sys.path.insert(0, %r); sys.path.insert(0, %r)
+        import gsp_b200 as gsp
+        lib = gsp.Library(%r)
+        rng = np.random.default_rng(1)
+        M = rng.standard_normal((520, 520)); S = M @ M.T + 520 * np.eye(520)
+        L = lib.potrf(S)
+        err = np.abs(L - scipy.linalg.cholesky(S, lower=True)).max()
+        assert err < 1e-11, err
+        print("OK")
+    """) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)), emu_lib.path)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, GSP_CHOL_PANELS="1"), timeout=600)
+    assert out.returncode == 0 and "OK" in out.stdout, out.stderr[-1500:]
+
+
 def test_multi_device_block_cyclic_cholesky(emu_lib):
     """multi-GPU factorization (chol_factor_mg): panels owned cyclically, pushed in place to every device; exercised with the
     emulated device listed 3 times (separate buffers per listed device), PB = 1 block, in a subprocess (env is cached)."""

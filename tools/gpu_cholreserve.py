@@ -20,6 +20,6 @@ for (dims, nd) in (((128, 128), 1000), ((256, 128), 500)):
     print(dims, "factor ms", round(best, 2), flush=True)
 ''' % ROOT
 for r in sys.argv[1:] or ["0", "8", "16", "24", "32", "48"]:
-    env = dict(os.environ, GSP_CHOL_RESERVE=r)
+    env = dict(os.environ, GSP_CHOL_RESERVE=r)  # GSP_CHOL_PANELS etc. pass through from the caller's environment
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env)
     print("reserve", r, "|", " | ".join(out.stdout.strip().splitlines()), out.stderr[-300:] if out.returncode else "", flush=True)

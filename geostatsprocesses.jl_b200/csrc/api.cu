@@ -178,6 +178,19 @@ extern "C" int gsp_ctx_create(int32_t ndev, const int32_t* devs, gsp_ctx** out) 
   for (auto& dc : ctx->devs) {
     cudaError_t e = cudaSetDevice(dc.dev);
     int prio_lo = 0, prio_hi = 0;
+#ifndef GSP_EMU
+    if (e == cudaSuccess) {
+      // keep freed device memory in the default pool (DevBuf); GSP_MEMPOOL_KEEP=<bytes> lowers the threshold, 0 = return it at once
+      cudaMemPool_t pool = nullptr;
+      if (cudaDeviceGetDefaultMemPool(&pool, dc.dev) == cudaSuccess && pool) {
+        unsigned long long keep = ~0ull;
+        const char* env = getenv("GSP_MEMPOOL_KEEP");
+        if (env && env[0]) keep = strtoull(env, nullptr, 10);
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      }
+      cudaGetLastError();
+    }
+#endif
     if (e == cudaSuccess) e = cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&dc.stream, cudaStreamNonBlocking, prio_hi);
     for (int k = 0; k < DevCtx::kSide && e == cudaSuccess; ++k) e = cudaStreamCreateWithPriority(&dc.side[k], cudaStreamNonBlocking, prio_lo);
@@ -201,6 +214,18 @@ extern "C" int gsp_ctx_create(int32_t ndev, const int32_t* devs, gsp_ctx** out) 
         cudaSetDevice(a.dev);
         cudaDeviceEnablePeerAccess(b.dev, 0);
         cudaGetLastError();  // "already enabled" is fine
+#ifndef GSP_EMU
+        // stream-ordered pool memory is not covered by cudaDeviceEnablePeerAccess: device a may map what b's pool hands out
+        cudaMemPool_t pool = nullptr;
+        if (cudaDeviceGetDefaultMemPool(&pool, b.dev) == cudaSuccess && pool) {
+          cudaMemAccessDesc desc{};
+          desc.location.type = cudaMemLocationTypeDevice;
+          desc.location.id = a.dev;
+          desc.flags = cudaMemAccessFlagsProtReadWrite;
+          cudaMemPoolSetAccess(pool, &desc, 1);
+        }
+        cudaGetLastError();
+#endif
       }
     }
   *out = ctx;
@@ -216,6 +241,14 @@ extern "C" int gsp_ctx_destroy(gsp_ctx* ctx) {
       if (dc.side[k]) cudaStreamDestroy(dc.side[k]);
     if (dc.h2d) cudaStreamDestroy(dc.h2d);
     if (dc.d2h) cudaStreamDestroy(dc.d2h);
+#ifndef GSP_EMU
+    cudaMemPool_t pool = nullptr;  // hand the cached blocks back to the driver
+    if (cudaDeviceGetDefaultMemPool(&pool, dc.dev) == cudaSuccess && pool) {
+      cudaDeviceSynchronize();
+      cudaMemPoolTrimTo(pool, 0);
+    }
+    cudaGetLastError();
+#endif
   }
   delete ctx;
   return GSP_OK;

@@ -279,6 +279,7 @@ struct AxisPlan {
   int packed = 0;    // x axis only
   bool fast = false; // power-of-two register-resident kernels (fft_pow2.cuh)
   TensorMap tmH, tmF; // strided fast passes: TMA tiles of the work spectrum / of F along this axis
+  int bundle = 0;     // kx per work item of the fast strided passes along this axis (= inner extent of the TMA box / 2)
 };
 
 // One realization in flight: its own stream and half-spectrum work buffer (3-D grids run several lanes concurrently so that
@@ -434,12 +435,11 @@ cudaError_t launch_p2_xinv(cudaStream_t st, int sms, const cplx* H, double* out,
   return cudaGetLastError();
 }
 
-template <int N, int FLAGS>
+template <int N, int FLAGS, int B>
 cudaError_t launch_p2_strided_f(cudaStream_t st, int sms, const TensorMap& tmH, int axis, cplx* H, const cplx* twp, const cplx* tw, const cplx* twi,
                                 long long es, int hx,
                                 long long nother, long long other_stride, const double* Fh, long long esF, long long other_strideF, double s,
                                 const Sub& sub) {
-  constexpr int B = p2_bundle(N);
   constexpr int STAGES = GSP_STRIDED_STAGES;
   using C = StridedCfg<N, B, FLAGS, STAGES>;
   auto kfn = p2_strided_kernel<N, B, FLAGS, STAGES>;
@@ -459,14 +459,33 @@ cudaError_t launch_p2_strided_f(cudaStream_t st, int sms, const TensorMap& tmH, 
   return cudaGetLastError();
 }
 
+// wide bundles (16 kx = 256-byte runs) exist for the middle axis of 3-D grids with extents <= 256: measured on the B200 at 256^3 the
+// y passes gain (57.5 -> 53.4 us, 51.1 -> 50.4 us) although 9 x 16 kx cover hx = 129 less tightly than 17 x 8, the fused
+// forward-multiply-inverse pass of the last axis loses (77.4 -> 81.1 us) and keeps 8
+constexpr int P2_WIDE = 16;
+GSP_HD constexpr bool p2_wide_ok(int N) { return N >= 64 && N <= 256 && p2_bundle(N) < P2_WIDE; }
+
+template <int N, int B>
+cudaError_t launch_p2_strided_b(cudaStream_t st, int sms, int flags, const TensorMap& tmH, int axis, cplx* H, const cplx* twp, const cplx* tw,
+                                const cplx* twi, long long es,
+                                int hx, long long nother, long long other_stride, const double* Fh, long long esF, long long other_strideF,
+                                double s, const Sub& sub) {
+  if (flags == P2_FWD) return launch_p2_strided_f<N, P2_FWD, B>(st, sms, tmH, axis, H, twp, tw, twi, es, hx, nother, other_stride, Fh, esF, other_strideF, s, sub);
+  if (flags == P2_INV) return launch_p2_strided_f<N, P2_INV, B>(st, sms, tmH, axis, H, twp, tw, twi, es, hx, nother, other_stride, Fh, esF, other_strideF, s, sub);
+  return launch_p2_strided_f<N, P2_FWD | P2_MUL | P2_INV, B>(st, sms, tmH, axis, H, twp, tw, twi, es, hx, nother, other_stride, Fh, esF, other_strideF, s, sub);
+}
+
 template <int N>
-cudaError_t launch_p2_strided(cudaStream_t st, int sms, int flags, const TensorMap& tmH, int axis, cplx* H, const cplx* twp, const cplx* tw,
+cudaError_t launch_p2_strided(cudaStream_t st, int sms, int flags, int bundle, const TensorMap& tmH, int axis, cplx* H, const cplx* twp, const cplx* tw,
                               const cplx* twi, long long es,
                               int hx, long long nother, long long other_stride, const double* Fh, long long esF, long long other_strideF,
                               double s, const Sub& sub) {
-  if (flags == P2_FWD) return launch_p2_strided_f<N, P2_FWD>(st, sms, tmH, axis, H, twp, tw, twi, es, hx, nother, other_stride, Fh, esF, other_strideF, s, sub);
-  if (flags == P2_INV) return launch_p2_strided_f<N, P2_INV>(st, sms, tmH, axis, H, twp, tw, twi, es, hx, nother, other_stride, Fh, esF, other_strideF, s, sub);
-  return launch_p2_strided_f<N, P2_FWD | P2_MUL | P2_INV>(st, sms, tmH, axis, H, twp, tw, twi, es, hx, nother, other_stride, Fh, esF, other_strideF, s, sub);
+  if constexpr (p2_wide_ok(N)) {
+    if (bundle == P2_WIDE)
+      return launch_p2_strided_b<N, P2_WIDE>(st, sms, flags, tmH, axis, H, twp, tw, twi, es, hx, nother, other_stride, Fh, esF, other_strideF, s, sub);
+  }
+  if (bundle != p2_bundle(N)) return cudaErrorInvalidValue;
+  return launch_p2_strided_b<N, p2_bundle(N)>(st, sms, flags, tmH, axis, H, twp, tw, twi, es, hx, nother, other_stride, Fh, esF, other_strideF, s, sub);
 }
 
 template <int HN, int NY, bool INV, bool RNG>
@@ -658,7 +677,7 @@ cudaError_t run_strided(FftDev* d, gsp_fft_plan* p, const Lane& L, int axis, int
   }
   if (a.fast) {
 #define GSP_CALL(NN) \
-  launch_p2_strided<NN>(L.st, d->dc->sms, flags, L.tmH[axis], axis, H, a.lp.tw, d->stw_ax_fwd[axis].as<cplx>(), d->stw_ax_inv[axis].as<cplx>(), es, \
+  launch_p2_strided<NN>(L.st, d->dc->sms, flags, a.bundle, L.tmH[axis], axis, H, a.lp.tw, d->stw_ax_fwd[axis].as<cplx>(), d->stw_ax_inv[axis].as<cplx>(), es, \
                         (int)hx, \
                         nother, other_stride, Fh, esF, other_strideF, s, sub)
     GSP_P2_SWITCH(a.len, GSP_CALL)
@@ -759,7 +778,7 @@ cudaError_t realization(FftDev* d, gsp_fft_plan* p, const Lane& L, const double*
   } else if (p->ndim == 3 && d->slab_mode == 2) {
     // kx-bundle groups: y forward, z (forward, multiply, inverse) and y inverse of one group of bundles back to back;
     // the group's slab (group x ny x nz) stays in L2 between the three kernels
-    const int B = p2_bundle(d->ax[1].len);
+    const int B = d->ax[1].bundle;
     const int nball = (p->hx + B - 1) / B;
     for (int bx0 = 0; bx0 < nball && e == cudaSuccess; bx0 += d->slab_bundles) {
       Sub sub;
@@ -863,7 +882,13 @@ int build_device(gsp_ctx* ctx, gsp_fft_plan* p, FftDev* d, const CovDev& cov, co
   for (int axis = 1; axis < p->ndim; ++axis) {
     AxisPlan& a = d->ax[axis];
     if (!a.fast) continue;
-    const unsigned B = (unsigned)p2_bundle(a.len);
+    // GSP_FFT_WIDE=0 keeps 8 kx everywhere (A/B runs); the fused plane kernels and the bundle-group slabs are built for 8
+    const char* wenv = getenv("GSP_FFT_WIDE");
+    const char* fenv = getenv("GSP_FFT_FUSE");
+    const bool fuse_req = fenv && fenv[0] ? fenv[0] == '1' : GSP_FFT_FUSE_DEFAULT != 0;
+    const bool wide = p->ndim == 3 && axis == 1 && p2_wide_ok(a.len) && !(wenv && wenv[0] == '0') && !fuse_req && d->slab_mode != 2;
+    a.bundle = wide ? P2_WIDE : p2_bundle(a.len);
+    const unsigned B = (unsigned)a.bundle;
     const unsigned long long dH[3] = {2ull * p->hx, (unsigned long long)p->dims[1],
                                       (unsigned long long)(p->ndim == 2 ? p->rb : p->dims[2])};  // 2-D: 3rd extent = batch
     const unsigned long long dF[3] = {(unsigned long long)p->hxF, (unsigned long long)p->dims[1], (unsigned long long)p->dims[2]};

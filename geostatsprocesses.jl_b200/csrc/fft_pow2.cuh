@@ -126,21 +126,28 @@ GSP_DEV void p2_exchange(cplx* v, int t, cplx* buf, Lay lay) {
     for (int r = 0; r < R2; ++r) v[q * R2 + r] = buf[lay(p2_in_pos<N, INV, S_ + 1>(t, q, r))];
 }
 
-template <int N, bool INV, int S_, int TWS, class Lay>
-GSP_DEV void p2_run_from(cplx* v, int t, cplx* buf, Lay lay, const cplx* tw) {
+struct P2NoHook {
+  GSP_DEV void operator()() const {}
+};
+
+// `after_last_exchange` runs once every thread's slots are back in registers for the final stage: from there on the transform no
+// longer touches `buf` (single-stage passes start the next item's load at that point)
+template <int N, bool INV, int S_, int TWS, class Lay, class Hook>
+GSP_DEV void p2_run_from(cplx* v, int t, cplx* buf, Lay lay, const cplx* tw, Hook after_last_exchange) {
   p2_stage<N, INV, S_, TWS>(v, t, tw);
   if constexpr (S_ + 1 < p2_stages(N)) {
     p2_exchange<N, INV, S_>(v, t, buf, lay);
-    p2_run_from<N, INV, S_ + 1, TWS>(v, t, buf, lay, tw);
+    if constexpr (S_ + 2 == p2_stages(N)) after_last_exchange();
+    p2_run_from<N, INV, S_ + 1, TWS>(v, t, buf, lay, tw, after_last_exchange);
   }
 }
 
 // Full transform of one line held in registers.
 //   in : slot (q, r) = x[p2_in_pos<N,INV,0>(t,q,r)]
 //   out: slot (q, r) = X[p2_in_pos<N,!INV,0>(t,q,r)]  (natural order; same mapping as the opposite direction's input)
-template <int N, bool INV, int TWS, class Lay>
-GSP_DEV void p2_fft(cplx* v, int t, cplx* buf, Lay lay, const cplx* tw) {
-  p2_run_from<N, INV, 0, TWS>(v, t, buf, lay, tw);
+template <int N, bool INV, int TWS, class Lay, class Hook = P2NoHook>
+GSP_DEV void p2_fft(cplx* v, int t, cplx* buf, Lay lay, const cplx* tw, Hook after_last_exchange = Hook()) {
+  p2_run_from<N, INV, 0, TWS>(v, t, buf, lay, tw, after_last_exchange);
 }
 
 struct BundleLay {  // strided passes: [position][b], b fastest
@@ -186,7 +193,8 @@ struct StridedCfg {
 #endif
   // register cap for that many CTAs per SM (8-slot experiment: 24 warps per SM)
   static constexpr int MINB = (GSP_P2_R8 && SL == 8 && STAGES == 1 && THREADS <= 256) ? 768 / THREADS
-                                                                                      : ((STAGES == 1 && THREADS <= 128) ? GSP_STRIDED_MINB : 1);
+                                                                                      : ((STAGES == 1 && THREADS <= 128) ? GSP_STRIDED_MINB
+                                                                                         : ((STAGES == 1 && THREADS == 256) ? 2 : 1));
 };
 
 template <int N, int B, int FLAGS, int STAGES>
@@ -245,15 +253,30 @@ __global__ void __launch_bounds__(StridedCfg<N, B, FLAGS, STAGES>::THREADS, Stri
     }
   };
 
+  // STAGES == 1 and GSP_STRIDED_EARLY: the one stage is refilled as soon as the LAST exchange of the item has been read back into
+  // registers - the final radix stage and the stores of item i then overlap the load of item i + 1 (the exposed load wait is
+  // 22 % of the warp samples of these kernels, profiles/r01_s3_ncu_full_summary.csv).  Measured on the B200 at 256^3: no change
+  // (279.7 vs 279.8 us per realization, every pass within 1 us) - the other 3 CTAs of the SM already fill that wait.  Off.
+#ifndef GSP_STRIDED_EARLY
+#define GSP_STRIDED_EARLY 0
+#endif
+  constexpr bool EARLY = STAGES == 1 && GSP_STRIDED_EARLY != 0;
+  constexpr bool HAS_EX = p2_stages(N) > 1;
   long long unit = ubeg + blockIdx.x;
-  if (STAGES == 2 && unit < nunits) issue(unit, 0);
+  if ((STAGES == 2 || EARLY) && unit < nunits) issue(unit, 0);
   for (int it = 0; unit < nunits; unit += gridDim.x, ++it) {
     const int cur = STAGES == 2 ? (it & 1) : 0;
     if (STAGES == 2) {
       if (unit + gridDim.x < nunits) issue(unit + gridDim.x, cur ^ 1);
-    } else {
+    } else if (!EARLY) {
       issue(unit, 0);
     }
+    auto refill = [&]() {
+      if constexpr (EARLY) {
+        __syncthreads();  // every thread has read its slots out of the stage
+        if (unit + gridDim.x < nunits) issue(unit + gridDim.x, 0);
+      }
+    };
     const long long o = unit / nbundles;
     const int bx = bx0 + (int)(unit - o * nbundles);
     const bool valid = bx * B + b < hx;
@@ -278,7 +301,14 @@ __global__ void __launch_bounds__(StridedCfg<N, B, FLAGS, STAGES>::THREADS, Stri
     for (int q = 0; q < SL / R0; ++q)
 #pragma unroll
       for (int r = 0; r < R0; ++r) v[q * R0 + r] = buf[lay(p2_in_pos<N, FIRST_INV, 0>(t, q, r))];
-    if constexpr ((FLAGS & P2_FWD) != 0) p2_fft<N, false, TWS>(v, t, buf, lay, stwf);
+    if constexpr (!HAS_EX) refill();
+    constexpr bool LAST_IS_FWD = (FLAGS & P2_INV) == 0;
+    if constexpr ((FLAGS & P2_FWD) != 0) {
+      if constexpr (LAST_IS_FWD && HAS_EX)
+        p2_fft<N, false, TWS>(v, t, buf, lay, stwf, refill);
+      else
+        p2_fft<N, false, TWS>(v, t, buf, lay, stwf);
+    }
     if constexpr (MUL) {
       // slot (q, r) holds frequency f = p2_in_pos<N, true, 0>(t, q, r): P = s*F*W/|W|, angle(0) = 0 (fftsim.jl:125)
       constexpr int RI = p2_radix(N, true, 0);
@@ -297,7 +327,12 @@ __global__ void __launch_bounds__(StridedCfg<N, B, FLAGS, STAGES>::THREADS, Stri
           }
         }
     }
-    if constexpr ((FLAGS & P2_INV) != 0) p2_fft<N, true, TWS>(v, t, buf, lay, stwi);
+    if constexpr ((FLAGS & P2_INV) != 0) {
+      if constexpr (HAS_EX)
+        p2_fft<N, true, TWS>(v, t, buf, lay, stwi, refill);
+      else
+        p2_fft<N, true, TWS>(v, t, buf, lay, stwi);
+    }
     constexpr bool LAST_INV = (FLAGS & P2_INV) != 0;
     constexpr int RO = p2_radix(N, !LAST_INV, 0);
     if (valid) {
@@ -309,7 +344,7 @@ __global__ void __launch_bounds__(StridedCfg<N, B, FLAGS, STAGES>::THREADS, Stri
           st_stream2(reinterpret_cast<double*>(H + base + (long long)m * es), make_double2(v[q * RO + r].re, v[q * RO + r].im));
         }
     }
-    __syncthreads();
+    if constexpr (!EARLY) __syncthreads();
   }
 }
 

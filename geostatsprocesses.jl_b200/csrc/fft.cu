@@ -242,6 +242,15 @@ bool choose_radices(int n, LinePlan* lp) {
       m /= c;
     }
   }
+  // what is left is a product of primes > 13: one generic stage per prime (fft_stage_generic)
+  for (int q = 17; m > 1; q += 2) {
+    if ((long long)q * q > m) q = m;
+    while (m % q == 0) {
+      if (lp->nst >= FFT_MAX_STAGES) return false;
+      lp->radix[lp->nst++] = q;
+      m /= q;
+    }
+  }
   return m == 1;
 }
 
@@ -548,7 +557,7 @@ int setup_axes(gsp_ctx* ctx, gsp_fft_plan* p, FftDev* d) {
     a.len = nx;
     a.packed = (nx % 2 == 0) ? 1 : 0;
     const int n = a.packed ? nx / 2 : nx;
-    if (!choose_radices(n, &a.lp)) return set_err(ctx, GSP_E_UNSUPPORTED, "grid extent has a prime factor > 13");
+    if (!choose_radices(n, &a.lp)) return set_err(ctx, GSP_E_UNSUPPORTED, "x extent needs more than 16 FFT stages");
     std::vector<cplx> tw = make_twiddles(nx);
     GSP_CUDA_OK(ctx, d->tw[0].alloc(d->dc->dev, tw.size() * sizeof(cplx)));
     GSP_CUDA_OK(ctx, cudaMemcpyAsync(d->tw[0].p, tw.data(), tw.size() * sizeof(cplx), cudaMemcpyHostToDevice, d->dc->stream));
@@ -581,7 +590,7 @@ int setup_axes(gsp_ctx* ctx, gsp_fft_plan* p, FftDev* d) {
     AxisPlan& a = d->ax[axis];
     const int n = (int)p->dims[axis];
     a.len = n;
-    if (!choose_radices(n, &a.lp)) return set_err(ctx, GSP_E_UNSUPPORTED, "grid extent has a prime factor > 13");
+    if (!choose_radices(n, &a.lp)) return set_err(ctx, GSP_E_UNSUPPORTED, "grid extent needs more than 16 FFT stages");
     std::vector<cplx> tw = make_twiddles(n);
     GSP_CUDA_OK(ctx, d->tw[axis].alloc(d->dc->dev, tw.size() * sizeof(cplx)));
     GSP_CUDA_OK(ctx, cudaMemcpyAsync(d->tw[axis].p, tw.data(), tw.size() * sizeof(cplx), cudaMemcpyHostToDevice, d->dc->stream));

@@ -4,7 +4,8 @@
 // A "line bundle" is B lines of length n held in shared memory as buf[j*B + b] (j = position on
 // the line, b = line within the bundle).  Stages are Stockham autosort (ping-pong between two
 // buffers), radix 16/8/4/2 done entirely in registers (recursive DIT with literal twiddles) and
-// radix 3/5/7/11/13 by a small O(R^2) DFT, so every extent 2^a 3^b 5^c 7^d 11^e 13^f is supported.
+// radix 3/5/7/11/13 by a small O(R^2) DFT; any other prime factor p of the extent becomes a stage of radix p evaluated one output at
+// a time (O(p) each, fft_stage_generic) - slower, but every extent FFTW accepts in the reference works here too.
 // Inter-stage twiddles come from a table exp(-2*pi*i*t/n) computed on the host in long double.
 // Lanes run fastest over b, so every shared-memory access of a stage is a contiguous run of 16-byte
 // elements; x-axis passes use an odd B which also makes the global<->shared transposition
@@ -149,6 +150,36 @@ GSP_DEV void fft_stage(const cplx* __restrict__ in, cplx* __restrict__ out, int 
   }
 }
 
+// Stockham stage of ANY radix R (prime factors > 13): one output per work item.  With m = k + r*Ns (k = j mod Ns) the twiddled
+// butterfly collapses to y[(j-k)*R + m] = sum_q x[j + q*n/R] * w_M^(q*m), M = Ns*R, and w_M = tw[(n/M) * tw_stride]; the exponent
+// q*m mod M is carried incrementally in integers, so the accuracy is that of the table.
+template <bool INV>
+GSP_DEV void fft_stage_generic(const cplx* __restrict__ in, cplx* __restrict__ out, int n, int R, int Ns, int B, const cplx* __restrict__ tw,
+                               int tw_stride) {
+  const int T = n / R;
+  const int M = Ns * R;
+  const int twm = (n / M) * tw_stride;
+  const int items = n * B;
+  for (int it = threadIdx.x; it < items; it += blockDim.x) {
+    const int o = it / B, b = it - o * B;
+    const int r = o / T, j = o - r * T;
+    const int k = j % Ns;
+    const int m = k + r * Ns;
+    double are = 0.0, aim = 0.0;
+    int idx = 0;
+    for (int q = 0; q < R; ++q) {
+      cplx w = tw[idx * twm];
+      if (INV) w.im = -w.im;
+      const cplx x = in[(j + q * T) * B + b];
+      are += x.re * w.re - x.im * w.im;
+      aim += x.re * w.im + x.im * w.re;
+      idx += m;
+      if (idx >= M) idx -= M;
+    }
+    out[((j - k) * R + m) * B + b] = cplx{are, aim};
+  }
+}
+
 // full transform of a bundle; returns the buffer holding the result (a or b).  Ends synchronised.
 template <bool INV>
 GSP_DEV cplx* fft_bundle(const LinePlan& lp, cplx* a, cplx* b, int B) {
@@ -166,7 +197,8 @@ GSP_DEV cplx* fft_bundle(const LinePlan& lp, cplx* a, cplx* b, int B) {
       case 5: fft_stage<5, INV>(in, out, lp.n, Ns, B, lp.tw, lp.tw_stride); break;
       case 7: fft_stage<7, INV>(in, out, lp.n, Ns, B, lp.tw, lp.tw_stride); break;
       case 11: fft_stage<11, INV>(in, out, lp.n, Ns, B, lp.tw, lp.tw_stride); break;
-      default: fft_stage<13, INV>(in, out, lp.n, Ns, B, lp.tw, lp.tw_stride); break;
+      case 13: fft_stage<13, INV>(in, out, lp.n, Ns, B, lp.tw, lp.tw_stride); break;
+      default: fft_stage_generic<INV>(in, out, lp.n, R, Ns, B, lp.tw, lp.tw_stride); break;
     }
     Ns *= R;
     __syncthreads();

@@ -29,7 +29,7 @@ extern "C" {
 
 #define GSP_OK 0
 #define GSP_E_CUDA (-1001)        /* CUDA runtime failure; text in gsp_last_error */
-#define GSP_E_UNSUPPORTED (-1002) /* e.g. grid extent with a prime factor > 13, dim > 3 */
+#define GSP_E_UNSUPPORTED (-1002) /* e.g. dim > 3, a grid line that does not fit shared memory (extent > ~6000 off the fast path) */
 #define GSP_E_NOMEM (-1003)
 #define GSP_E_STATE (-1004)       /* plan not usable (failed factorization) */
 

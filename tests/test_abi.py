@@ -71,8 +71,8 @@ def test_argument_errors_emulated(emu_lib):
         gsp.LUPlan(emu_lib, st, dom, np.array([65]), np.array([0.0]), 0.0)
     with pytest.raises(ValueError):  # unknown model kind
         gsp.LUPlan(emu_lib, [(17, 1.0, np.eye(3))], dom, None, None, 0.0)
-    with pytest.raises(gsp.GspError):  # prime factor 17 > 13 unsupported, reported not faked
-        gsp.FFTPlan(emu_lib, st, (34, 8), (0, 0), (1, 1))
+    with pytest.raises(gsp.GspError):  # a prime extent whose line does not fit shared memory: unsupported, reported not faked
+        gsp.FFTPlan(emu_lib, st, (20011, 2), (0, 0), (1, 1))
     plan = gsp.FFTPlan(emu_lib, st, (8, 8), (0, 0), (1, 1))
     with pytest.raises(ValueError):
         plan.sample(1, np.zeros((1, 64)) + 0.5, sill=-1.0)

@@ -114,6 +114,23 @@ def test_fftsim(emu_lib, dims, kind):
     plan.close()
 
 
+def test_fftsim_large_prime_extents(emu_lib):
+    """extents with prime factors > 13 (FFTW takes any size in the reference): generic-radix Stockham stages, packed (even nx) and
+    plain (odd nx) x transforms, strided axes, 1-D to 3-D."""
+    rng = np.random.default_rng(17)
+    for dims in ((34,), (101,), (34, 19), (37, 46), (17, 6, 23), (58, 10, 17)):
+        nd = len(dims)
+        st = iso(O.SPHERICAL, 1.3, 5.0, nd)
+        plan = gsp.FFTPlan(emu_lib, st, dims, [0.0] * nd, [1.0] * nd)
+        Fo = O.fftsim_preprocess(ostructs(st), dims, [0.0] * nd, [1.0] * nd)
+        assert relerr(plan.spectrum(), Fo) < 1e-12, dims
+        w = rng.random((2, int(np.prod(dims))))
+        Z = plan.sample(2, w, sill=1.3, mu=-0.2)
+        Zo = np.stack([O.fftsim_sample(Fo, w[r], 1.3, -0.2) for r in range(2)])
+        assert relerr(Z, Zo) < TOL, dims
+        plan.close()
+
+
 def test_fftsim_view_subset_and_rng(emu_lib):
     dims = (16, 8)
     st = iso(O.SPHERICAL, 1.0, 3.0, 2)

@@ -251,6 +251,22 @@ def test_fftsim_parity(gpu_lib, dims, kind, rang):
     plan.close()
 
 
+def test_fftsim_large_prime_extents(gpu_lib):
+    """prime factors > 13 in the grid extents (101 x 101 as in a reference user's grid, 2 * 211, 3-D with 17 / 29 / 31)."""
+    rng = np.random.default_rng(23)
+    for dims in ((101, 101), (422, 37), (34, 29, 31), (1009,)):
+        nd = len(dims)
+        st = iso(O.EXPONENTIAL, 1.0, 7.0, nd)
+        plan = gsp.FFTPlan(gpu_lib, st, dims, [0.0] * nd, [1.0] * nd)
+        Fo = O.fftsim_preprocess(ostructs(st), dims, [0.0] * nd, [1.0] * nd)
+        assert relerr(plan.spectrum(), Fo) < 1e-11, dims
+        w = rng.random((3, int(np.prod(dims))))
+        Z = plan.sample(3, w, sill=1.0, mu=0.1)
+        Zo = np.stack([O.fftsim_sample(Fo, w[r], 1.0, 0.1) for r in range(3)])
+        assert relerr(Z, Zo) < 1e-9, dims
+        plan.close()
+
+
 def test_fftsim_anisotropic_3d_and_view(gpu_lib):
     dims = (64, 64, 32)
     st = aniso3(O.SPHERICAL, 1.0, (20.0, 10.0, 5.0), 30.0)

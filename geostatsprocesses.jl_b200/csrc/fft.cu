@@ -1408,21 +1408,37 @@ extern "C" int gsp_fft_plan_condition(gsp_fft_plan* p, double mu, int32_t minnei
     GSP_CUDA_OK(ctx, c.nbr.alloc(d->dc->dev, nslots * sizeof(int)));
     GSP_CUDA_OK(ctx, c.knodes.alloc(d->dc->dev, (size_t)nk * sizeof(long long)));
     GSP_CUDA_OK(ctx, cudaMemcpyAsync(c.knodes.p, k0.data(), (size_t)nk * sizeof(long long), cudaMemcpyHostToDevice, st));
-    const unsigned blocks = (unsigned)((n + 127) / 128);
+    const unsigned blocks = (unsigned)((n + KW_THREADS - 1) / KW_THREADS);
     const long long* dinds = n_inds > 0 ? di.as<long long>() : nullptr;
+    // sample-to-sample covariances of a Kriging, assembled once (up to 4,096 samples = 128 MB; beyond that the kernel evaluates them)
+    DevBuf ktab;
+    auto sample_table = [&](const double* coords, long long ns) -> const double* {
+      if (ns > 4096) return nullptr;
+      if (ktab.bytes < (size_t)ns * ns * sizeof(double) && ktab.alloc(d->dc->dev, (size_t)ns * ns * sizeof(double)) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+      }
+      DomDev sd{};
+      sd.kind = 0; sd.dim = p->ndim; sd.nelems = ns; sd.coords = coords;
+      launch_assemble(st, p->cov, sd, sd, nullptr, nullptr, ns, ns, ktab.as<double>(), ns, false);
+      return ktab.as<double>();
+    };
     {
+      const double* kt = sample_table(dx.as<double>(), nd);
       ProfScope prof_("krige_weights", st);
       // first Kriging: the data where they are -> zbar (fftsim.jl:99); nothing else of it is needed later
-      GSP_LAUNCH(krige_weights_kernel, dim3(blocks), dim3(128), 0, st, p->cov, p->dom, dinds, n, (int)kmax_d, (long long)nd,
+      GSP_LAUNCH(krige_weights_kernel, dim3(blocks), dim3(KW_THREADS), 0, st, p->cov, p->dom, dinds, n, (int)kmax_d, (long long)nd,
                  (const double*)dx.as<double>(), (const double*)dv.as<double>(), mu, c.zbar.as<double>(), (double*)nullptr, (int*)nullptr,
-                 info.as<int>());
+                 info.as<int>(), kt);
       g_launches++;
     }
     {
+      const double* kt = sample_table(kx.as<double>(), nk);
       ProfScope prof_("krige_weights", st);
       // second Kriging: samples at the centroids of the data nodes -> weight table, applied to every realization
-      GSP_LAUNCH(krige_weights_kernel, dim3(blocks), dim3(128), 0, st, p->cov, p->dom, dinds, n, (int)kmax_k, (long long)nk,
-                 (const double*)kx.as<double>(), (const double*)nullptr, mu, (double*)nullptr, c.lam.as<double>(), c.nbr.as<int>(), info.as<int>());
+      GSP_LAUNCH(krige_weights_kernel, dim3(blocks), dim3(KW_THREADS), 0, st, p->cov, p->dom, dinds, n, (int)kmax_k, (long long)nk,
+                 (const double*)kx.as<double>(), (const double*)nullptr, mu, (double*)nullptr, c.lam.as<double>(), c.nbr.as<int>(), info.as<int>(),
+                 kt);
       g_launches++;
     }
     GSP_CUDA_OK(ctx, cudaGetLastError());

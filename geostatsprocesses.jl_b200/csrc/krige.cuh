@@ -14,102 +14,267 @@ namespace gsp {
 
 constexpr int KRIGE_MAXK = 32;  // neighbours per node (the reference's default maxneighbors is 26)
 
-// One thread per element of sdom.  Samples: coordinates sx (dim x ns, column-major) and, when zbar != nullptr, values sv.
+// Samples: coordinates sx (dim x ns, column-major) and, when zbar != nullptr, values sv.
 //   zbar != nullptr : zbar[i] = mu + sum lambda_a (sv[nbr_a] - mu)            (fftsim.jl:99)
 //   lam  != nullptr : slot (i, a) = lambda_a and the sample index (a < kk; unused slots: lambda 0, index 0), stored TILE-major
 //                     at (i / 32) * kk * 32 + a * 32 + i % 32: the weight rows of 32 consecutive nodes are one contiguous block
 // Ties in distance keep the sample with the lower index (stable insertion while scanning in index order).
 // info: 1-based index of the first element whose Kriging matrix is not positive definite (0 = ok).
-__global__ void __launch_bounds__(128) krige_weights_kernel(CovDev cov, DomDev dom, const long long* __restrict__ inds, long long n, int kk,
-                                                            long long ns, const double* __restrict__ sx, const double* __restrict__ sv, double mu,
-                                                            double* __restrict__ zbar, double* __restrict__ lam, int* __restrict__ nbr,
-                                                            int* __restrict__ info) {
-  __shared__ double tile[3 * 128];
+//
+// Two phases per warp of 32 consecutive elements:
+//  A. one thread per element: brute-force scan of the samples (staged in shared memory) for its kk nearest;
+//  B. the WARP solves the elements' Kriging systems one after the other, lane a = neighbour a: the neighbour list is sorted by sample
+//     index across the lanes (bitonic network; the order of the neighbours only permutes the system), the covariance matrix lives in
+//     shared memory one row per lane (ld 33: conflict-free rows AND columns), Cholesky / forward / backward substitution are short
+//     ROLLED loops over it with one broadcast per step.  Consecutive elements mostly have the SAME neighbour set (an order-26 Voronoi
+//     cell of 1,000 data in 256^3 is ~7 elements across): then the factor is simply reused and only the right-hand side and the two
+//     substitutions remain.
+// History (256^3, 1,000 data, per Kriging): everything per thread in 4.9 KB of local memory each: 276 ms; rows in registers with fully
+// unrolled shuffle recursions: 655 ms - 8k warp instructions per element of straight-line code, stalled on instruction fetch
+// (ncu: no_instruction 12.6 per issue); this version: see profiles/r01_s3_notes.md.
+constexpr int KW_THREADS = 64;
+constexpr int KW_LD = KRIGE_MAXK + 1;
+constexpr int KW_PRUNE = KRIGE_MAXK * KW_LD;  // samples whose centre distances fit the (still unused) matrix storage of a warp
+
+__global__ void __launch_bounds__(KW_THREADS) krige_weights_kernel(CovDev cov, DomDev dom, const long long* __restrict__ inds, long long n, int kk,
+                                                                   long long ns, const double* __restrict__ sx, const double* __restrict__ sv,
+                                                                   double mu, double* __restrict__ zbar, double* __restrict__ lam,
+                                                                   int* __restrict__ nbr, int* __restrict__ info,
+                                                                   const double* __restrict__ ktab) {
+  // ktab (optional): ns x ns covariances between the samples, assembled once per Kriging (8 MB for 1,000 samples: L2-resident) - a
+  // matrix entry is then one load instead of a covariance evaluation
+  __shared__ double tile[3 * KW_THREADS];
+  __shared__ int nbrS[KW_THREADS / 32][32][KW_LD];
+  __shared__ double Ls[KW_THREADS / 32][KRIGE_MAXK][KW_LD];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = i < n;
   double tx = 0.0, ty = 0.0, tz = 0.0;
   if (live) centroid(dom, inds ? inds[i] - 1 : i, tx, ty, tz);
-  double bd[KRIGE_MAXK];
-  int bi[KRIGE_MAXK];
-  int cnt = 0;
   const int dim = dom.dim;
-  for (long long s0 = 0; s0 < ns; s0 += 128) {
-    const int m = (int)((ns - s0 < 128) ? ns - s0 : 128);
-    __syncthreads();
-    if ((int)threadIdx.x < m) {
-      const double* p = sx + (s0 + threadIdx.x) * dim;
-      tile[threadIdx.x] = p[0];
-      tile[128 + threadIdx.x] = dim > 1 ? p[1] : 0.0;
-      tile[256 + threadIdx.x] = dim > 2 ? p[2] : 0.0;
-    }
-    __syncthreads();
-    if (!live) continue;
-    for (int j = 0; j < m; ++j) {
-      const double dx = tile[j] - tx, dy = tile[128 + j] - ty, dz = tile[256 + j] - tz;
-      const double d2 = dx * dx + dy * dy + dz * dz;
-      if (cnt == kk && !(d2 < bd[kk - 1])) continue;
-      int pos = cnt < kk ? cnt : kk - 1;  // slot that is freed (or appended)
-      while (pos > 0 && d2 < bd[pos - 1]) {
-        bd[pos] = bd[pos - 1];
-        bi[pos] = bi[pos - 1];
-        --pos;
+  // ---- A: the kk nearest samples of this thread's element.  The list is kept UNSORTED (phase B orders it by sample index anyway):
+  // a candidate replaces the current worst entry - largest distance, ties: highest sample index, which is what a stable sorted
+  // insertion would push out - and the new worst is found by one pass over the list (independent local loads; the sorted insertion
+  // of the first version was a chain of dependent local-memory loads and took most of the kernel's time).  The worst distance
+  // lives in a register, so a sample that does not enter costs no local-memory access.
+  // The warp first PRUNES the samples together (ns <= KW_PRUNE): with c, rho the centre and half-diagonal of the box around its 32
+  // elements and U >= the kk-th smallest distance from c (bisection on the cached distances), every element's kk nearest samples lie
+  // within U + 2 rho of c (triangle inequality), typically ~120 of 1,000.  The candidates keep their index order (ballot compaction),
+  // so the tie rule is unchanged.
+  {
+    double bd[KRIGE_MAXK];
+    int bi[KRIGE_MAXK];
+    int cntA = 0, wpos = 0;
+    double worst = -1.0;
+    auto offer = [&](double d2, int sidx) {
+      if (cntA < kk) {
+        bd[cntA] = d2;
+        bi[cntA] = sidx;
+        if (d2 >= worst) {  // later index wins the tie for "worst"
+          worst = d2;
+          wpos = cntA;
+        }
+        ++cntA;
+        return;
       }
-      bd[pos] = d2;
-      bi[pos] = (int)(s0 + j);
-      if (cnt < kk) ++cnt;
+      if (!(d2 < worst)) return;
+      bd[wpos] = d2;
+      bi[wpos] = sidx;
+      worst = -1.0;
+      int wi = -1;
+      for (int a = 0; a < kk; ++a) {
+        const double da = bd[a];
+        const int ia = bi[a];
+        if (da > worst || (da == worst && ia > wi)) {
+          worst = da;
+          wi = ia;
+          wpos = a;
+        }
+      }
+    };
+    if (ns <= KW_PRUNE) {
+      double* dc = &Ls[warp][0][0];          // phase B's matrix is not in use yet: squared distances from the box centre
+      int* cand = &nbrS[warp][0][0];         // ... and its neighbour table: the candidate list
+      // box of the warp's elements (lanes past the end copy lane 0)
+      const unsigned livemask = __ballot_sync(0xffffffffu, live);
+      int ncand = 0;
+      if (livemask != 0u) {
+        const int src = __ffs((int)livemask) - 1;
+        const double fx = __shfl_sync(0xffffffffu, tx, src), fy = __shfl_sync(0xffffffffu, ty, src), fz = __shfl_sync(0xffffffffu, tz, src);
+        double lx = live ? tx : fx, ly = live ? ty : fy, lz = live ? tz : fz;
+        double hx2 = lx, hy2 = ly, hz2 = lz;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          lx = fmin(lx, __shfl_xor_sync(0xffffffffu, lx, o)); hx2 = fmax(hx2, __shfl_xor_sync(0xffffffffu, hx2, o));
+          ly = fmin(ly, __shfl_xor_sync(0xffffffffu, ly, o)); hy2 = fmax(hy2, __shfl_xor_sync(0xffffffffu, hy2, o));
+          lz = fmin(lz, __shfl_xor_sync(0xffffffffu, lz, o)); hz2 = fmax(hz2, __shfl_xor_sync(0xffffffffu, hz2, o));
+        }
+        const double cx = 0.5 * (lx + hx2), cy = 0.5 * (ly + hy2), cz = 0.5 * (lz + hz2);
+        const double rho = 0.5 * sqrt((hx2 - lx) * (hx2 - lx) + (hy2 - ly) * (hy2 - ly) + (hz2 - lz) * (hz2 - lz));
+        double dmax = 0.0;
+        for (int sidx = lane; sidx < (int)ns; sidx += 32) {
+          const double* p = sx + (long long)sidx * dim;
+          const double dx = p[0] - cx, dy = (dim > 1 ? p[1] : 0.0) - cy, dz = (dim > 2 ? p[2] : 0.0) - cz;
+          const double d2 = dx * dx + dy * dy + dz * dz;
+          dc[sidx] = d2;
+          dmax = fmax(dmax, d2);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) dmax = fmax(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+        __syncwarp();
+        // U^2: smallest bisection point with at least kk samples inside (any upper bound of the kk-th distance is valid)
+        double lo = 0.0, hi = dmax;
+        const int need = (int)(ns < kk ? ns : kk);
+        for (int itb = 0; itb < 14; ++itb) {
+          const double mid = 0.5 * (lo + hi);
+          int c = 0;
+          for (int sidx = lane; sidx < (int)ns; sidx += 32) c += dc[sidx] <= mid ? 1 : 0;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+          if (c >= need) hi = mid;
+          else lo = mid;
+        }
+        const double rr = sqrt(hi) + 2.0 * rho;
+        const double T = rr * rr * (1.0 + 1e-9);  // slack for the rounding of the three distances in the triangle inequality
+        // candidates in index order
+        for (int s0 = 0; s0 < (int)ns; s0 += 32) {
+          const int sidx = s0 + lane;
+          const bool in = sidx < (int)ns && dc[sidx] <= T;
+          const unsigned mk = __ballot_sync(0xffffffffu, in);
+          __syncwarp();
+          if (in) cand[ncand + __popc(mk & ((1u << lane) - 1u))] = sidx;
+          ncand += __popc(mk);
+        }
+        __syncwarp();
+        if (live) {
+          for (int t = 0; t < ncand; ++t) {
+            const int sidx = cand[t];
+            const double* p = sx + (long long)sidx * dim;
+            const double dx = p[0] - tx, dy = (dim > 1 ? p[1] : 0.0) - ty, dz = (dim > 2 ? p[2] : 0.0) - tz;
+            offer(dx * dx + dy * dy + dz * dz, sidx);
+          }
+        }
+        __syncwarp();   // the candidate list is dead: its storage becomes the neighbour table
+      }
+    } else {
+      for (long long s0 = 0; s0 < ns; s0 += KW_THREADS) {
+        const int m = (int)((ns - s0 < KW_THREADS) ? ns - s0 : KW_THREADS);
+        __syncthreads();
+        if ((int)threadIdx.x < m) {
+          const double* p = sx + (s0 + threadIdx.x) * dim;
+          tile[threadIdx.x] = p[0];
+          tile[KW_THREADS + threadIdx.x] = dim > 1 ? p[1] : 0.0;
+          tile[2 * KW_THREADS + threadIdx.x] = dim > 2 ? p[2] : 0.0;
+        }
+        __syncthreads();
+        if (!live) continue;
+        for (int j = 0; j < m; ++j) {
+          const double dx = tile[j] - tx, dy = tile[KW_THREADS + j] - ty, dz = tile[2 * KW_THREADS + j] - tz;
+          offer(dx * dx + dy * dy + dz * dz, (int)(s0 + j));
+        }
+      }
     }
+    for (int a = 0; a < KRIGE_MAXK; ++a) nbrS[warp][lane][a] = (live && a < cntA) ? bi[a] : 0x7fffffff;
   }
-  if (!live) return;
-  // simple-Kriging system of the cnt neighbours: packed lower C, right-hand side c0 = cov(sample, target)
-  double C[KRIGE_MAXK * (KRIGE_MAXK + 1) / 2];
-  double x[KRIGE_MAXK];
-  for (int a = 0; a < cnt; ++a) {
-    const double* pa = sx + (long long)bi[a] * dim;
-    const double ax = pa[0], ay = dim > 1 ? pa[1] : 0.0, az = dim > 2 ? pa[2] : 0.0;
-    for (int b = 0; b <= a; ++b) {
-      const double* pb = sx + (long long)bi[b] * dim;
-      C[a * (a + 1) / 2 + b] = cov_eval(cov, ax - pb[0], dim > 1 ? ay - pb[1] : 0.0, dim > 2 ? az - pb[2] : 0.0);
+  __syncwarp();
+  // ---- B: the warp's 32 elements one after the other, lane = neighbour
+  const int cnt = (int)(ns < kk ? ns : kk);      // every element finds the same number of neighbours
+  const long long wbase = i - lane;              // first element of this warp
+  double (*L)[KW_LD] = Ls[warp];
+  double rd_own = 1.0;                           // 1 / L[lane][lane]
+  double ax = 0.0, ay = 0.0, az = 0.0;
+  int prev = -1;
+  bool have = false;
+  const bool act = lane < cnt;
+  for (int nn = 0; nn < 32; ++nn) {
+    const long long inode = wbase + nn;
+    if (inode >= n) break;                       // uniform: elements of a warp are consecutive
+    // neighbour list sorted by sample index (sentinels last)
+    int my = nbrS[warp][nn][lane];
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        const int other = __shfl_xor_sync(0xffffffffu, my, j);
+        const bool up = (lane & k) == 0, lower = (lane & j) == 0;
+        my = (lower == up) ? (my < other ? my : other) : (my > other ? my : other);
+      }
     }
-    x[a] = cov_eval(cov, ax - tx, ay - ty, az - tz);
-  }
-  // Cholesky (row by row), then L y = c0 and L' lambda = y
-  bool bad = false;
-  for (int a = 0; a < cnt; ++a) {
-    for (int b = 0; b <= a; ++b) {
-      double s = C[a * (a + 1) / 2 + b];
-      for (int k = 0; k < b; ++k) s -= C[a * (a + 1) / 2 + k] * C[b * (b + 1) / 2 + k];
-      if (b < a) {
-        C[a * (a + 1) / 2 + b] = s / C[b * (b + 1) / 2 + b];
+    const bool same = have && (__ballot_sync(0xffffffffu, my != prev) == 0u);
+    if (!same) {
+      if (act) {
+        const double* pa = sx + (long long)my * dim;
+        ax = pa[0];
+        ay = dim > 1 ? pa[1] : 0.0;
+        az = dim > 2 ? pa[2] : 0.0;
+      }
+      // row `lane` of the covariance matrix of the neighbours (lower part)
+      if (ktab) {
+        const double* krow = ktab + (long long)(act ? my : 0) * ns;
+        for (int b = 0; b < cnt; ++b) {
+          const int mb = __shfl_sync(0xffffffffu, my, b);
+          if (act && b <= lane) L[lane][b] = krow[mb];
+        }
       } else {
-        if (!(s > 0.0)) bad = true;
-        C[a * (a + 1) / 2 + a] = sqrt(s);
+        for (int b = 0; b < cnt; ++b) {
+          const double bx = __shfl_sync(0xffffffffu, ax, b), by = __shfl_sync(0xffffffffu, ay, b), bz = __shfl_sync(0xffffffffu, az, b);
+          if (act && b <= lane) L[lane][b] = cov_eval(cov, ax - bx, ay - by, az - bz);
+        }
       }
+      __syncwarp();
+      // left-looking Cholesky, one column per step: lane r forms L[r][J] from its own row and row J (a broadcast) - two loads and
+      // one FMA per term, the sum in registers (the right-looking form read-modify-wrote the whole trailing block in shared memory)
+      bool bad = false;
+      for (int J = 0; J < cnt; ++J) {
+        const double* rl = L[lane];
+        const double* rj = L[J];
+        double s0 = 0.0, s1 = 0.0;
+        int k = 0;
+        for (; k + 1 < J; k += 2) {
+          s0 += rl[k] * rj[k];
+          s1 += rl[k + 1] * rj[k + 1];
+        }
+        if (k < J) s0 += rl[k] * rj[k];
+        const double v = rl[J] - (s0 + s1);
+        const double piv = __shfl_sync(0xffffffffu, v, J);
+        if (!(piv > 0.0)) bad = true;
+        const double rinv = rsqrt(piv);
+        if (lane == J) {
+          L[J][J] = piv * rinv;
+          rd_own = rinv;
+        } else if (lane > J && act) {
+          L[lane][J] = v * rinv;
+        }
+        __syncwarp();
+      }
+      if (bad && lane == 0) atomicCAS(info, 0, (int)(inode < 2147483646LL ? inode + 1 : 2147483647LL));
+      prev = my;
+      have = true;
     }
-  }
-  if (bad) {
-    atomicCAS(info, 0, (int)(i < 2147483646LL ? i + 1 : 2147483647LL));
-    return;
-  }
-  for (int a = 0; a < cnt; ++a) {
-    double s = x[a];
-    for (int k = 0; k < a; ++k) s -= C[a * (a + 1) / 2 + k] * x[k];
-    x[a] = s / C[a * (a + 1) / 2 + a];
-  }
-  for (int a = cnt - 1; a >= 0; --a) {
-    double s = x[a];
-    for (int k = a + 1; k < cnt; ++k) s -= C[k * (k + 1) / 2 + a] * x[k];
-    x[a] = s / C[a * (a + 1) / 2 + a];
-  }
-  if (zbar) {
-    double acc = 0.0;
-    for (int a = 0; a < cnt; ++a) acc += x[a] * (sv[bi[a]] - mu);
-    zbar[i] = mu + acc;
-  }
-  if (lam) {
-    const long long base = (i >> 5) * kk * 32 + (i & 31);
-    for (int a = 0; a < kk; ++a) {
-      lam[base + a * 32] = a < cnt ? x[a] : 0.0;
-      nbr[base + a * 32] = a < cnt ? bi[a] : 0;
+    // right-hand side: covariance between neighbour `lane` and the element, then L y = c0 and L' lambda = y, both column-oriented:
+    // one broadcast of the finished component per step, every other lane updates its own
+    const double ex = __shfl_sync(0xffffffffu, tx, nn), ey = __shfl_sync(0xffffffffu, ty, nn), ez = __shfl_sync(0xffffffffu, tz, nn);
+    double x = act ? cov_eval(cov, ax - ex, ay - ey, az - ez) : 0.0;
+    for (int J = 0; J < cnt; ++J) {
+      const double yj = __shfl_sync(0xffffffffu, x * rd_own, J);
+      if (lane == J) x = yj;
+      else if (lane > J && act) x -= L[lane][J] * yj;
+    }
+    for (int J = cnt - 1; J >= 0; --J) {
+      const double lj = __shfl_sync(0xffffffffu, x * rd_own, J);
+      if (lane == J) x = lj;
+      else if (lane < J) x -= L[J][lane] * lj;
+    }
+    if (zbar) {
+      double t = act ? x * (sv[my] - mu) : 0.0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      if (lane == 0) zbar[inode] = mu + t;
+    }
+    if (lam && lane < kk) {
+      const long long base = (inode >> 5) * kk * 32 + (inode & 31);
+      lam[base + lane * 32] = act ? x : 0.0;
+      nbr[base + lane * 32] = act ? my : 0;
     }
   }
 }

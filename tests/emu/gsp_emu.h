@@ -199,6 +199,8 @@ static inline unsigned __ballot_sync(unsigned, int pred) {
   return r;
 }
 
+static inline int __all_sync(unsigned m, int pred) { return __ballot_sync(m, !pred) == 0u; }
+static inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0u; }
 template <class T> static inline T atomicAdd(T* p, T v) { T o = *p; *p = o + v; return o; }
 static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { auto o = *p; *p = o + v; return o; }
 template <class T> static inline T atomicMin(T* p, T v) { T o = *p; if (v < o) *p = v; return o; }
@@ -208,6 +210,8 @@ template <class T> static inline T atomicExch(T* p, T v) { T o = *p; *p = v; ret
 
 static inline double __longlong_as_double(long long v) { double d; std::memcpy(&d, &v, 8); return d; }
 static inline long long __double_as_longlong(double d) { long long v; std::memcpy(&v, &d, 8); return v; }
+static inline int __popc(unsigned x) { return __builtin_popcount(x); }
+static inline int __ffs(int x) { return __builtin_ffs(x); }
 static inline int __clz(int x) { return x == 0 ? 32 : __builtin_clz((unsigned)x); }
 static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((uint64_t)a * b) >> 32); }
 static inline double sinpi(double x) { return std::sin(M_PI * x); }

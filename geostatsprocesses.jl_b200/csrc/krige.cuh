@@ -330,10 +330,16 @@ __global__ void __launch_bounds__(256) krige_apply_kernel(double* __restrict__ Z
       const double2 l01 = *reinterpret_cast<const double2*>(&lamS[a][c0]);
       const double2 l23 = *reinterpret_cast<const double2*>(&lamS[a][c0 + 2]);
       const int4 o = *reinterpret_cast<const int4*>(&nbrS[a][c0]);
-      acc0 += l01.x * resl[o.x];
-      acc1 += l01.y * resl[o.y];
-      acc2 += l23.x * resl[o.z];
-      acc3 += l23.y * resl[o.w];
+      // the weight table lists every element's neighbours in sample order (krige_weights_kernel sorts them), so adjacent elements
+      // mostly name the same sample at the same rank: one gather then serves several of the four (uniform branches: o is a broadcast)
+      const double r0 = resl[o.x];
+      const double r1 = (o.y == o.x) ? r0 : resl[o.y];
+      const double r2 = (o.z == o.y) ? r1 : resl[o.z];
+      const double r3 = (o.w == o.z) ? r2 : resl[o.w];
+      acc0 += l01.x * r0;
+      acc1 += l01.y * r1;
+      acc2 += l23.x * r2;
+      acc3 += l23.y * r3;
     }
     if (lane < nb) {
       if (i0 + c0 < n) Zs[lane][c0] = zbar[i0 + c0] + (Zs[lane][c0] - (mu + acc0));

@@ -14,7 +14,7 @@ st = aniso3(O.SPHERICAL, 1.0, (40.0, 20.0, 10.0), 30.0)
 w = torch.rand((R, N), dtype=torch.float64, device=dev)
 z = torch.empty((R, N), dtype=torch.float64, device=dev)
 ref = os.environ.get("FFTLIB_REF")
-for lanes in (1, 4):
+for lanes in [int(x) for x in os.environ.get("FFTLIB_LANES", "1,4").split(",")]:
     os.environ["GSP_FFT_LANES"] = str(lanes)
     plan = gsp.FFTPlan(lib, st, dims, [0.0] * 3, [1.0] * 3)
     for mode in ("inject", "rng"):

@@ -12,6 +12,9 @@
 
 namespace gsp {
 
+#ifndef GSP_CHOL_MG_RESERVE_DEFAULT
+#define GSP_CHOL_MG_RESERVE_DEFAULT 0
+#endif
 #ifndef GSP_CHOL_RESERVE_DEFAULT
 #define GSP_CHOL_RESERVE_DEFAULT 8  // measured on B200: C3 66.4 -> 64.6 ms, 32k nodes 394 -> 385 ms (tools/gpu_cholreserve.py); 16-24 the same, 48 worse
 #endif
@@ -543,11 +546,24 @@ cudaError_t chol_factor_mg(const std::vector<MgDev>& devs, long long ld, int nbl
   auto check = [&](cudaError_t e) {
     if (err == cudaSuccess && e != cudaSuccess) err = e;
   };
+  // GSP_CHOL_MG_RESERVE=r: the bulk updates on the update streams run as persistent grids that leave r SMs to the main stream, where the
+  // next panel is updated, factored and sent (see chol_factor's GSP_CHOL_RESERVE)
+  static int mg_reserve = -1;
+  if (mg_reserve < 0) {
+    const char* env = getenv("GSP_CHOL_MG_RESERVE");
+    mg_reserve = env ? atoi(env) : GSP_CHOL_MG_RESERVE_DEFAULT;
+    if (mg_reserve < 0) mg_reserve = 0;
+  }
   std::vector<Chol> ch;
   ch.reserve(G);
   for (int g = 0; g < G; ++g) {
     check(cudaSetDevice(devs[g].dev));
     ch.push_back(Chol{devs[g].main, nullptr, 0, devs[g].A, ld, devs[g].invD, devs[g].info});
+    if (mg_reserve > 0) {
+      int sms = 0;
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, devs[g].dev);
+      ch.back().side_ctas = sms - mg_reserve > 8 ? sms - mg_reserve : 8;
+    }
     check(cudaMemsetAsync(devs[g].info, 0, sizeof(int), devs[g].main));
   }
   std::vector<cudaEvent_t> evs;
@@ -609,7 +625,7 @@ cudaError_t chol_factor_mg(const std::vector<MgDev>& devs, long long ld, int nbl
           any_upd = true;
         }
         ch[g].st = s;  // Chol::update launches on the stream it is given; keep st consistent for error paths
-        ch[g].update(s, false, c0, c0, nblocks - c0, n2, c0, r0, c0, r0, nq, false);
+        ch[g].update(s, !lookahead, c0, c0, nblocks - c0, n2, c0, r0, c0, r0, nq, false);
         ch[g].st = devs[g].main;
         check(ch[g].err);
       }

@@ -95,6 +95,35 @@ def test_lusim_conditional(gpu_lib, kind, nd, mu):
     plan.close()
 
 
+def test_matern_lusim_and_fftsim(gpu_lib):
+    """Matern structures (order 1.5 and 0.7, nested with a nugget) through the whole LUSIM and FFTSIM paths, injected noise."""
+    rng = np.random.default_rng(41)
+    dims = (48, 40)
+    A = np.zeros((3, 3)); A[0, 0] = 1 / 14.0; A[1, 1] = 1 / 9.0
+    st = [(O.MATERN, 0.9, A, 1.5), (O.MATERN, 0.4, A * 2.0, 0.7), (O.NUGGET, 0.05, np.eye(3))]
+    coords = O.grid_centroids(dims, [0, 0], [1, 1])
+    dinds = np.sort(rng.choice(coords.shape[0], 150, replace=False))
+    z1 = rng.standard_normal(150)
+    plan = gsp.LUPlan(gpu_lib, st, grid_dom(dims), dinds + 1, z1, 0.0)
+    pre = O.lusim_preprocess(ostructs(st), coords, dinds, z1, 0.0)
+    W = rng.standard_normal((plan.Ns, 50))
+    Z = plan.sample(50, W)
+    Zo = O.lusim_sample(pre, W)
+    assert max(relerr(Z[:, r], Zo[:, r]) for r in range(50)) < TOL
+    assert np.array_equal(Z[dinds], np.repeat(z1[:, None], 50, 1))
+    plan.close()
+    fdims = (64, 64, 32)
+    A3 = np.diag([1 / 12.0, 1 / 8.0, 1 / 5.0])
+    fst = [(O.MATERN, 1.0, A3, 2.5)]
+    fplan = gsp.FFTPlan(gpu_lib, fst, fdims, [0.0] * 3, [1.0] * 3)
+    Fo = O.fftsim_preprocess(ostructs(fst), fdims, [0.0] * 3, [1.0] * 3)
+    w = rng.random((2, int(np.prod(fdims))))
+    Zf = fplan.sample(2, w, sill=1.0, mu=0.0)
+    for r in range(2):
+        assert relerr(Zf[r], O.fftsim_sample(Fo, w[r], 1.0, 0.0)) < TOL
+    fplan.close()
+
+
 def test_lusim_bivariate(gpu_lib):
     """cosimulation (lusim.jl:112-126,164): rho-mixing of the noises, each variable with its own marginal plan."""
     rng = np.random.default_rng(5)

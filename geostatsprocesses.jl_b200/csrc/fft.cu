@@ -331,6 +331,7 @@ struct FftDev {
   DevBuf stw_fwd, stw_inv;  // x axis: per-stage twiddle tables of the length-nx/2 transform (forward / inverse radix order)
   DevBuf stw_ax_fwd[3], stw_ax_inv[3];  // strided axes: the same for the full-length transforms
   DevBuf Fh;       // real half spectrum
+  DevBuf Fperm;    // 3-D fast grids: F in the item order of the last axis' fused pass (p2_permute_F_kernel)
   DevBuf H;        // complex half-spectrum work buffer
   DevBuf win[2], zout[2];  // staging for host-pointer sampling
   DevBuf inds;
@@ -448,7 +449,7 @@ template <int N, int FLAGS, int B>
 cudaError_t launch_p2_strided_f(cudaStream_t st, int sms, const TensorMap& tmH, int axis, cplx* H, const cplx* twp, const cplx* tw, const cplx* twi,
                                 long long es, int hx,
                                 long long nother, long long other_stride, const double* Fh, long long esF, long long other_strideF, double s,
-                                const Sub& sub) {
+                                const Sub& sub, const double* Fperm = nullptr) {
   constexpr int STAGES = GSP_STRIDED_STAGES;
   using C = StridedCfg<N, B, FLAGS, STAGES>;
   auto kfn = p2_strided_kernel<N, B, FLAGS, STAGES>;
@@ -463,7 +464,7 @@ cudaError_t launch_p2_strided_f(cudaStream_t st, int sms, const TensorMap& tmH, 
   const long long ubeg = o0 * nbundles, uend = o1 * nbundles;
   ProfScope prof_((FLAGS & P2_MUL) ? "fft_strided_fwd_mul_inv" : ((FLAGS & P2_FWD) ? "fft_strided_fwd" : "fft_strided_inv"), st);
   GSP_LAUNCH(kfn, dim3(persistent_grid(per_sm, sms, uend - ubeg)), dim3(C::THREADS), C::SMEM, st, tmH, axis, H, twp, tw, twi, es, hx, nbundles, uend,
-             other_stride, Fh, esF, other_strideF, s, bx0, ubeg);
+             other_stride, Fh, esF, other_strideF, s, bx0, ubeg, (FLAGS & P2_MUL) ? Fperm : (const double*)nullptr);
   g_launches++;
   return cudaGetLastError();
 }
@@ -478,23 +479,37 @@ template <int N, int B>
 cudaError_t launch_p2_strided_b(cudaStream_t st, int sms, int flags, const TensorMap& tmH, int axis, cplx* H, const cplx* twp, const cplx* tw,
                                 const cplx* twi, long long es,
                                 int hx, long long nother, long long other_stride, const double* Fh, long long esF, long long other_strideF,
-                                double s, const Sub& sub) {
+                                double s, const Sub& sub, const double* Fperm) {
   if (flags == P2_FWD) return launch_p2_strided_f<N, P2_FWD, B>(st, sms, tmH, axis, H, twp, tw, twi, es, hx, nother, other_stride, Fh, esF, other_strideF, s, sub);
   if (flags == P2_INV) return launch_p2_strided_f<N, P2_INV, B>(st, sms, tmH, axis, H, twp, tw, twi, es, hx, nother, other_stride, Fh, esF, other_strideF, s, sub);
-  return launch_p2_strided_f<N, P2_FWD | P2_MUL | P2_INV, B>(st, sms, tmH, axis, H, twp, tw, twi, es, hx, nother, other_stride, Fh, esF, other_strideF, s, sub);
+  return launch_p2_strided_f<N, P2_FWD | P2_MUL | P2_INV, B>(st, sms, tmH, axis, H, twp, tw, twi, es, hx, nother, other_stride, Fh, esF, other_strideF, s, sub,
+                                                             Fperm);
 }
 
 template <int N>
 cudaError_t launch_p2_strided(cudaStream_t st, int sms, int flags, int bundle, const TensorMap& tmH, int axis, cplx* H, const cplx* twp, const cplx* tw,
                               const cplx* twi, long long es,
                               int hx, long long nother, long long other_stride, const double* Fh, long long esF, long long other_strideF,
-                              double s, const Sub& sub) {
+                              double s, const Sub& sub, const double* Fperm) {
   if constexpr (p2_wide_ok(N)) {
     if (bundle == P2_WIDE)
-      return launch_p2_strided_b<N, P2_WIDE>(st, sms, flags, tmH, axis, H, twp, tw, twi, es, hx, nother, other_stride, Fh, esF, other_strideF, s, sub);
+      return launch_p2_strided_b<N, P2_WIDE>(st, sms, flags, tmH, axis, H, twp, tw, twi, es, hx, nother, other_stride, Fh, esF, other_strideF, s, sub,
+                                             nullptr);
   }
   if (bundle != p2_bundle(N)) return cudaErrorInvalidValue;
-  return launch_p2_strided_b<N, p2_bundle(N)>(st, sms, flags, tmH, axis, H, twp, tw, twi, es, hx, nother, other_stride, Fh, esF, other_strideF, s, sub);
+  return launch_p2_strided_b<N, p2_bundle(N)>(st, sms, flags, tmH, axis, H, twp, tw, twi, es, hx, nother, other_stride, Fh, esF, other_strideF, s, sub,
+                                              Fperm);
+}
+
+// item-major copy of F for the fused pass of the last axis of a 3-D grid (bundles of p2_bundle(N) kx)
+template <int N>
+cudaError_t launch_p2_permute(cudaStream_t st, const double* Fh, long long esF, long long other_strideF, int hx, long long nother, double* Fperm) {
+  constexpr int B = p2_bundle(N);
+  using C = StridedCfg<N, B, P2_FWD | P2_MUL | P2_INV, 1>;
+  const long long items = nother * ((hx + B - 1) / B);
+  GSP_LAUNCH((p2_permute_F_kernel<N, B>), dim3((unsigned)items), dim3(C::THREADS), 0, st, Fh, esF, other_strideF, hx, Fperm);
+  g_launches++;
+  return cudaGetLastError();
 }
 
 template <int HN, int NY, bool INV, bool RNG>
@@ -688,7 +703,8 @@ cudaError_t run_strided(FftDev* d, gsp_fft_plan* p, const Lane& L, int axis, int
 #define GSP_CALL(NN) \
   launch_p2_strided<NN>(L.st, d->dc->sms, flags, a.bundle, L.tmH[axis], axis, H, a.lp.tw, d->stw_ax_fwd[axis].as<cplx>(), d->stw_ax_inv[axis].as<cplx>(), es, \
                         (int)hx, \
-                        nother, other_stride, Fh, esF, other_strideF, s, sub)
+                        nother, other_stride, Fh, esF, other_strideF, s, sub, \
+                        (axis == 2 && sub.nb == 0 && a.bundle == p2_bundle(a.len)) ? d->Fperm.as<double>() : (const double*)nullptr)
     GSP_P2_SWITCH(a.len, GSP_CALL)
 #undef GSP_CALL
   }
@@ -940,6 +956,24 @@ int build_device(gsp_ctx* ctx, gsp_fft_plan* p, FftDev* d, const CovDev& cov, co
   GSP_CUDA_OK(ctx, cudaMemcpyAsync(&s2, total.p, sizeof(double), cudaMemcpyDeviceToHost, d->dc->stream));
   GSP_CUDA_OK(ctx, cudaStreamSynchronize(d->dc->stream));
   p->sumF2 = s2;
+  {
+    // item-major copy of F for the last axis' fused pass (3-D, register-resident kernels); GSP_FFT_FPERM=0 keeps the strided reads
+    const char* env = getenv("GSP_FFT_FPERM");
+    const AxisPlan& a = d->ax[2];
+    if (all_fast && !(env && env[0] == '0') && a.bundle == p2_bundle(a.len)) {
+      const long long nball = (p->hx + a.bundle - 1) / a.bundle;
+      const size_t count = (size_t)p->dims[1] * (size_t)nball * (size_t)a.len * (size_t)a.bundle;
+      GSP_CUDA_OK(ctx, d->Fperm.alloc(d->dc->dev, count * sizeof(double)));
+      auto build = [&]() -> cudaError_t {
+#define GSP_CALL(NN) \
+  launch_p2_permute<NN>(d->dc->stream, d->Fh.as<double>(), (long long)p->hxF * p->dims[1], (long long)p->hxF, p->hx, p->dims[1], d->Fperm.as<double>())
+        GSP_P2_SWITCH(a.len, GSP_CALL)
+#undef GSP_CALL
+      };
+      GSP_CUDA_OK(ctx, build());
+      GSP_CUDA_OK(ctx, cudaStreamSynchronize(d->dc->stream));
+    }
+  }
   return GSP_OK;
 }
 

@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(StridedCfg<N, B, FLAGS, STAGES>::THREADS, Stri
                                                                                      long long es, int hx, int nbundles, long long nunits,
                                                                                      long long other_stride, const double* __restrict__ Fh,
                                                                                      long long esF, long long other_strideF, double s, int bx0,
-                                                                                     long long ubeg) {
+                                                                                     long long ubeg, const double* __restrict__ Fperm) {
   // work units [ubeg, nunits): unit = o * nbundles + (bx - bx0), i.e. `nbundles` kx bundles starting at bundle bx0 for every
   // index o along the remaining axis.  Sub-ranges (slabs of planes or groups of kx bundles) keep a slab resident in L2.
   using C = StridedCfg<N, B, FLAGS, STAGES>;
@@ -287,11 +287,19 @@ __global__ void __launch_bounds__(StridedCfg<N, B, FLAGS, STAGES>::THREADS, Stri
     double fv[MUL ? SL : 1];
     if constexpr (MUL) {
       constexpr int RI = p2_radix(N, true, 0);
-      const double* fp = Fh + o * other_strideF + (long long)bx * B + b;
+      if (Fperm) {
+        // item-major copy of F (p2_permute_F_kernel): slot j of all the item's threads is one contiguous run
+        const long long item = o * ((hx + B - 1) / B) + bx;
+        const double* fp = Fperm + item * (long long)(SL * TPU) + tid;
 #pragma unroll
-      for (int q = 0; q < SL / RI; ++q)
+        for (int j = 0; j < SL; ++j) fv[j] = __ldg(fp + j * TPU);
+      } else {
+        const double* fp = Fh + o * other_strideF + (long long)bx * B + b;
 #pragma unroll
-        for (int r = 0; r < RI; ++r) fv[q * RI + r] = valid ? __ldg(fp + (long long)p2_in_pos<N, true, 0>(t, q, r) * esF) : 0.0;
+        for (int q = 0; q < SL / RI; ++q)
+#pragma unroll
+          for (int r = 0; r < RI; ++r) fv[q * RI + r] = valid ? __ldg(fp + (long long)p2_in_pos<N, true, 0>(t, q, r) * esF) : 0.0;
+      }
     }
     mbar_wait(&full[cur], (uint32_t)(STAGES == 2 ? ((it >> 1) & 1) : (it & 1)));
     constexpr bool FIRST_INV = (FLAGS & P2_FWD) == 0;
@@ -346,6 +354,28 @@ __global__ void __launch_bounds__(StridedCfg<N, B, FLAGS, STAGES>::THREADS, Stri
     }
     if constexpr (!EARLY) __syncthreads();
   }
+}
+
+// F in the order the fused forward-multiply-inverse pass consumes it: Fperm[(item * SL + j) * TPU + tid] = F of slot j of thread tid
+// of item = o * nball + bx (zero past hx).  One CTA of TPU threads per item, built once per plan: the pass then reads SL contiguous
+// runs of TPU doubles per item instead of N strided 64-byte runs.
+template <int N, int B>
+__global__ void __launch_bounds__(StridedCfg<N, B, P2_FWD | P2_MUL | P2_INV, 1>::THREADS)
+    p2_permute_F_kernel(const double* __restrict__ Fh, long long esF, long long other_strideF, int hx, double* __restrict__ Fperm) {
+  using C = StridedCfg<N, B, P2_FWD | P2_MUL | P2_INV, 1>;
+  constexpr int SL = C::SL, TPU = C::THREADS, RI = p2_radix(N, true, 0);
+  const int nball = (hx + B - 1) / B;
+  const long long item = blockIdx.x;
+  const long long o = item / nball;
+  const int bx = (int)(item - o * nball);
+  const int tid = threadIdx.x, b = tid % B, t = tid / B;
+  const bool valid = bx * B + b < hx;
+  const double* fp = Fh + o * other_strideF + (long long)bx * B + b;
+  double* out = Fperm + item * (long long)(SL * TPU) + tid;
+#pragma unroll
+  for (int q = 0; q < SL / RI; ++q)
+#pragma unroll
+    for (int r = 0; r < RI; ++r) out[(q * RI + r) * TPU] = valid ? fp[(long long)p2_in_pos<N, true, 0>(t, q, r) * esF] : 0.0;
 }
 
 // ------------------------------------------------------------------------------------------------

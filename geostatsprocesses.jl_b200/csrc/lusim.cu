@@ -69,8 +69,10 @@ struct LuDev {
   DevBuf info;
   // sampling scratch (per chunk)
   DevBuf Wp, W1p, Zc, Wraw, W1raw;
+  DevBuf Zc2, Wraw2, W1raw2;   // second slot of the host-pointer pipeline (H2D / compute / D2H of consecutive chunks overlap)
   long long chunk_cols = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
 };
 
 inline unsigned grid_for(long long n, int sms) {
@@ -97,7 +99,7 @@ struct gsp_lu_plan {
 namespace gsp {
 namespace {
 
-int ensure_chunk(gsp_ctx* ctx, gsp_lu_plan* p, LuDev* d, long long cols, bool need_w1) {
+int ensure_chunk(gsp_ctx* ctx, gsp_lu_plan* p, LuDev* d, long long cols, bool need_w1, bool two_slots = false) {
   const long long cpad = round_up(cols, 128);
   if (d->chunk_cols < cpad) {
     GSP_CUDA_OK(ctx, d->Wp.alloc(d->dc->dev, (size_t)p->Nsp * cpad * sizeof(double)));
@@ -105,11 +107,24 @@ int ensure_chunk(gsp_ctx* ctx, gsp_lu_plan* p, LuDev* d, long long cols, bool ne
     GSP_CUDA_OK(ctx, d->Wraw.alloc(d->dc->dev, (size_t)p->Ns * cpad * sizeof(double)));
     d->W1p.release();
     d->W1raw.release();
+    d->Zc2.release();
+    d->Wraw2.release();
+    d->W1raw2.release();
     d->chunk_cols = cpad;
   }
   if (need_w1 && !d->W1p.p) {
     GSP_CUDA_OK(ctx, d->W1p.alloc(d->dc->dev, (size_t)p->Nsp * d->chunk_cols * sizeof(double)));
     GSP_CUDA_OK(ctx, d->W1raw.alloc(d->dc->dev, (size_t)p->Ns * d->chunk_cols * sizeof(double)));
+  }
+  if (two_slots) {
+    if (!d->Zc2.p) GSP_CUDA_OK(ctx, d->Zc2.alloc(d->dc->dev, (size_t)p->N * d->chunk_cols * sizeof(double)));
+    if (!d->Wraw2.p) GSP_CUDA_OK(ctx, d->Wraw2.alloc(d->dc->dev, (size_t)p->Ns * d->chunk_cols * sizeof(double)));
+    if (need_w1 && !d->W1raw2.p) GSP_CUDA_OK(ctx, d->W1raw2.alloc(d->dc->dev, (size_t)p->Ns * d->chunk_cols * sizeof(double)));
+    for (int k = 0; k < 2; ++k) {
+      if (!d->ev_in[k]) GSP_CUDA_OK(ctx, cudaEventCreateWithFlags(&d->ev_in[k], cudaEventDisableTiming));
+      if (!d->ev_comp[k]) GSP_CUDA_OK(ctx, cudaEventCreateWithFlags(&d->ev_comp[k], cudaEventDisableTiming));
+      if (!d->ev_out[k]) GSP_CUDA_OK(ctx, cudaEventCreateWithFlags(&d->ev_out[k], cudaEventDisableTiming));
+    }
   }
   return GSP_OK;
 }
@@ -345,6 +360,11 @@ extern "C" int gsp_lu_plan_destroy(gsp_lu_plan* p) {
     cudaStreamSynchronize(d->dc->stream);
     if (d->ev0) cudaEventDestroy(d->ev0);
     if (d->ev1) cudaEventDestroy(d->ev1);
+    for (int k = 0; k < 2; ++k) {
+      if (d->ev_in[k]) cudaEventDestroy(d->ev_in[k]);
+      if (d->ev_comp[k]) cudaEventDestroy(d->ev_comp[k]);
+      if (d->ev_out[k]) cudaEventDestroy(d->ev_out[k]);
+    }
   }
   delete p;
   return GSP_OK;
@@ -437,9 +457,17 @@ int lu_sample_impl(gsp_lu_plan* p, int64_t R, const double* W, uint64_t seed, in
   long long maxshard = 0;
   for (int i = 0; i < ndev; ++i) maxshard = std::max(maxshard, r0[i + 1] - r0[i]);
   const long long chunk = std::min<long long>(std::max<long long>(maxshard, 1), 512);
+  // host-pointer calls with more than one chunk per device run a two-slot pipeline: the H2D copy of chunk c+1 (copy-in stream) and the
+  // D2H copy of chunk c-1 (copy-out stream) overlap the GEMM of chunk c (compute stream).  GSP_LU_PIPELINE=0: everything in stream order.
+  static int pipe_on = -1;
+  if (pipe_on < 0) {
+    const char* env = getenv("GSP_LU_PIPELINE");
+    pipe_on = (env && env[0] == '0') ? 0 : 1;
+  }
+  const bool piped = pipe_on && !ens && maxshard > chunk;
   for (int i = 0; i < ndev; ++i) {
     cudaSetDevice(p->dev[i]->dc->dev);
-    GSP_TRY(ensure_chunk(ctx, p, p->dev[i].get(), chunk, mix));
+    GSP_TRY(ensure_chunk(ctx, p, p->dev[i].get(), chunk, mix, piped));
   }
   {
     LuDev* d0 = p->dev[0].get();
@@ -447,31 +475,47 @@ int lu_sample_impl(gsp_lu_plan* p, int64_t R, const double* W, uint64_t seed, in
     cudaEventRecord(d0->ev0, d0->dc->stream);
   }
   int rc = GSP_OK;
-  // chunks are issued round-robin over the devices; each device runs H2D -> compute -> D2H in stream order.  The D2H copies
-  // are issued in a second sweep so that a (host-blocking) copy into pageable memory overlaps the other devices' compute.
-  for (long long c0 = 0; c0 < maxshard && rc == GSP_OK; c0 += chunk) {
+  auto cuda_ok = [&](cudaError_t e) {
+    if (e != cudaSuccess && rc == GSP_OK) rc = set_err(ctx, GSP_E_CUDA, cudaGetErrorString(e));
+    return e == cudaSuccess;
+  };
+  // chunks are issued round-robin over the devices; each device runs H2D -> compute -> D2H in stream order (or pipelined, see above).
+  // The D2H copies are issued in a second sweep so that a (host-blocking) copy into pageable memory overlaps the other devices' compute.
+  long long ci = 0;
+  for (long long c0 = 0; c0 < maxshard && rc == GSP_OK; c0 += chunk, ++ci) {
+    const int slot = piped ? (int)(ci & 1) : 0;
     for (int i = 0; i < ndev && rc == GSP_OK; ++i) {
       const long long nloc = r0[i + 1] - r0[i];
       if (c0 >= nloc) continue;
       LuDev* d = p->dev[i].get();
       cudaSetDevice(d->dc->dev);
       cudaStream_t st = d->dc->stream;
+      cudaStream_t sin = piped ? d->dc->h2d : st;
       const long long cols = std::min(chunk, nloc - c0);
       const long long ra = r0[i] + c0;  // absolute first realization of this chunk
       const double* Wd = nullptr;
       const double* W1d = nullptr;
-      cudaError_t e = cudaSuccess;
+      DevBuf& wraw = slot ? d->Wraw2 : d->Wraw;
+      DevBuf& w1raw = slot ? d->W1raw2 : d->W1raw;
       if (W) {
-        e = cudaMemcpyAsync(d->Wraw.p, W + ra * p->Ns, (size_t)p->Ns * cols * sizeof(double), cudaMemcpyHostToDevice, st);
-        Wd = d->Wraw.as<double>();
-        if (e == cudaSuccess && mix) {
-          e = cudaMemcpyAsync(d->W1raw.p, W1 + ra * p->Ns, (size_t)p->Ns * cols * sizeof(double), cudaMemcpyHostToDevice, st);
-          W1d = d->W1raw.as<double>();
+        // the slot's noise buffer is free once the compute of the chunk that used it two steps ago has run
+        if (piped && ci >= 2 && !cuda_ok(cudaStreamWaitEvent(sin, d->ev_comp[slot], 0))) break;
+        if (!cuda_ok(cudaMemcpyAsync(wraw.p, W + ra * p->Ns, (size_t)p->Ns * cols * sizeof(double), cudaMemcpyHostToDevice, sin))) break;
+        Wd = wraw.as<double>();
+        if (mix) {
+          if (!cuda_ok(cudaMemcpyAsync(w1raw.p, W1 + ra * p->Ns, (size_t)p->Ns * cols * sizeof(double), cudaMemcpyHostToDevice, sin))) break;
+          W1d = w1raw.as<double>();
+        }
+        if (piped) {
+          if (!cuda_ok(cudaEventRecord(d->ev_in[slot], sin))) break;
+          if (!cuda_ok(cudaStreamWaitEvent(st, d->ev_in[slot], 0))) break;
         }
       }
-      if (e != cudaSuccess) { rc = set_err(ctx, GSP_E_CUDA, cudaGetErrorString(e)); break; }
-      double* Zt = ens ? ens->dev[i]->Z.as<double>() + c0 * p->N : d->Zc.as<double>();
+      // ... and its field buffer once that chunk's copy-out has finished
+      if (piped && ci >= 2 && !cuda_ok(cudaStreamWaitEvent(st, d->ev_out[slot], 0))) break;
+      double* Zt = ens ? ens->dev[i]->Z.as<double>() + c0 * p->N : (slot ? d->Zc2.as<double>() : d->Zc.as<double>());
       rc = sample_core(ctx, p, d, cols, Wd, p->Ns, seed, stream, first_real + ra, rho, W1d, Zt, p->N);
+      if (rc == GSP_OK && piped) cuda_ok(cudaEventRecord(d->ev_comp[slot], st));
     }
     for (int i = 0; i < ndev && rc == GSP_OK && !ens; ++i) {
       const long long nloc = r0[i + 1] - r0[i];
@@ -480,8 +524,22 @@ int lu_sample_impl(gsp_lu_plan* p, int64_t R, const double* W, uint64_t seed, in
       cudaSetDevice(d->dc->dev);
       const long long cols = std::min(chunk, nloc - c0);
       const long long ra = r0[i] + c0;
-      cudaError_t e = cudaMemcpyAsync(Z + ra * p->N, d->Zc.p, (size_t)p->N * cols * sizeof(double), cudaMemcpyDeviceToHost, d->dc->stream);
-      if (e != cudaSuccess) { rc = set_err(ctx, GSP_E_CUDA, cudaGetErrorString(e)); break; }
+      cudaStream_t sout = piped ? d->dc->d2h : d->dc->stream;
+      if (piped && !cuda_ok(cudaStreamWaitEvent(sout, d->ev_comp[slot], 0))) break;
+      const double* Zs = slot ? d->Zc2.as<double>() : d->Zc.as<double>();
+      if (!cuda_ok(cudaMemcpyAsync(Z + ra * p->N, Zs, (size_t)p->N * cols * sizeof(double), cudaMemcpyDeviceToHost, sout))) break;
+      if (piped) cuda_ok(cudaEventRecord(d->ev_out[slot], sout));
+    }
+  }
+  if (piped) {
+    // the compute streams (timed, and synchronised below) wait for the copy streams
+    for (int i = 0; i < ndev; ++i) {
+      LuDev* d = p->dev[i].get();
+      cudaSetDevice(d->dc->dev);
+      for (int k = 0; k < 2; ++k) {
+        cudaStreamWaitEvent(d->dc->stream, d->ev_out[k], 0);   // never-recorded events are complete: no-op
+        cudaStreamWaitEvent(d->dc->stream, d->ev_in[k], 0);
+      }
     }
   }
   {

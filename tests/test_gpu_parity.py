@@ -204,6 +204,32 @@ def test_lusim_c3_size_properties(gpu_lib):
     plan.close()
 
 
+def test_lusim_host_pipeline_matches_device_path(gpu_lib):
+    """host-pointer sampling with several chunks per device (H2D / GEMM / D2H of consecutive chunks overlap on three streams,
+    two buffer slots) returns exactly what the device-pointer path returns for the same injected noise, bivariate mixing included."""
+    import torch
+    rng = np.random.default_rng(9)
+    dims = (48, 40)
+    N, nd, R = 1920, 60, 1300          # 3 chunks of 512 columns
+    st = iso(O.SPHERICAL, 1.0, 9.0, 2)
+    dinds = np.sort(rng.choice(N, nd, replace=False))
+    z1 = rng.standard_normal(nd)
+    plan = gsp.LUPlan(gpu_lib, st, grid_dom(dims), dinds + 1, z1, 0.0)
+    W = rng.standard_normal((plan.Ns, R))
+    W1 = rng.standard_normal((plan.Ns, R))
+    dev = torch.device("cuda:0")
+    for rho, w1 in ((math.nan, None), (0.7, W1)):
+        Zh = plan.sample(R, W, rho=rho, W1=w1)
+        dW = torch.from_numpy(np.ascontiguousarray(W.T)).to(dev)
+        dW1 = torch.from_numpy(np.ascontiguousarray(W1.T)).to(dev) if w1 is not None else None
+        dZ = torch.empty((R, N), dtype=torch.float64, device=dev)
+        plan.sample_dev(R, dW.data_ptr(), plan.Ns, 0, 0, 0, rho, dW1.data_ptr() if dW1 is not None else None, dZ.data_ptr(), N)
+        torch.cuda.synchronize()
+        assert np.array_equal(Zh, dZ.cpu().numpy().T)
+        assert np.array_equal(Zh[dinds], np.repeat(z1[:, None], R, 1))
+    plan.close()
+
+
 def test_lusim_c5_size_properties(gpu_lib):
     """BASELINE configs[4] at full size: bivariate (rho = 0.7) LUSIM on 32,768 nodes with 500 shared data nodes.
     The oracle would need ~100 s per variable here, so check properties: data honoured bit-exactly for both variables,

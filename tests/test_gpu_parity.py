@@ -478,7 +478,9 @@ def test_ensemble_resident_simulation_gpu(gpu_lib):
 
 # ------------------------------------------------------------------ §8f rank 2: conditional FFTSIM (fftsim.jl:94-101,140-153)
 @pytest.mark.parametrize("dims,nd,kind,maxn,view", [((64, 64), 100, O.EXPONENTIAL, 26, False), ((32, 32, 16), 80, O.SPHERICAL, 26, False),
-                                                    ((48, 40), 60, O.CUBIC, 8, True), ((40, 40), 12, O.SPHERICAL, 26, False)])
+                                                    ((48, 40), 60, O.CUBIC, 8, True), ((40, 40), 12, O.SPHERICAL, 26, False),
+                                                    # more data than the warp-level pruning caches (1,056): full-scan path of the weights kernel
+                                                    ((32, 32, 12), 1200, O.EXPONENTIAL, 26, False)])
 def test_fftsim_conditional_parity(gpu_lib, dims, nd, kind, maxn, view):
     # (no GaussianCovariance here: its Kriging matrices are numerically singular, kappa ~ 1e12+, so the weights of two correct
     #  implementations agree to ~1e-6 only - the same caveat SURVEY §7 records for LUSIM + Gaussian)

@@ -1447,7 +1447,8 @@ extern "C" int gsp_fft_plan_condition(gsp_fft_plan* p, double mu, int32_t minnei
     // sample-to-sample covariances of a Kriging, assembled once (up to 4,096 samples = 128 MB; beyond that the kernel evaluates them)
     DevBuf ktab;
     auto sample_table = [&](const double* coords, long long ns) -> const double* {
-      if (ns > 4096) return nullptr;
+      const char* tenv = getenv("GSP_KRIGE_TABLE");  // =0: evaluate the covariances inside the kernel (the path of > 4,096 samples)
+      if (ns > 4096 || (tenv && tenv[0] == '0')) return nullptr;
       if (ktab.bytes < (size_t)ns * ns * sizeof(double) && ktab.alloc(d->dc->dev, (size_t)ns * ns * sizeof(double)) != cudaSuccess) {
         cudaGetLastError();
         return nullptr;

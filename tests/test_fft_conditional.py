@@ -80,6 +80,12 @@ def test_conditional_fftsim_vs_oracle(emu_lib, dims, nd, kind, maxn, view, snapp
     _case(emu_lib, dims, nd, 2, kind, 4.0, 0.7, maxn, seed=len(dims) * 100 + nd, view=view, snapped=snapped)
 
 
+def test_conditional_without_covariance_table(emu_lib, monkeypatch):
+    """GSP_KRIGE_TABLE=0: the weights kernel evaluates the sample-to-sample covariances itself (what it does beyond 4,096 samples)."""
+    monkeypatch.setenv("GSP_KRIGE_TABLE", "0")
+    _case(emu_lib, (16, 12), 40, 2, O.EXPONENTIAL, 5.0, 0.3, 26, 5)
+
+
 def test_conditional_two_devices_and_errors(emu_lib):
     lib2 = gsp.Library(emu_lib.path, devices=[0, 0])
     _case(lib2, (12, 8), 20, 3, O.SPHERICAL, 3.0, -0.2, 8, seed=77)

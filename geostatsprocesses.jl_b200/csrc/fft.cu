@@ -469,9 +469,9 @@ cudaError_t launch_p2_strided_f(cudaStream_t st, int sms, const TensorMap& tmH, 
   return cudaGetLastError();
 }
 
-// wide bundles (16 kx = 256-byte runs) exist for the middle axis of 3-D grids with extents <= 256: measured on the B200 at 256^3 the
-// y passes gain (57.5 -> 53.4 us, 51.1 -> 50.4 us) although 9 x 16 kx cover hx = 129 less tightly than 17 x 8, the fused
-// forward-multiply-inverse pass of the last axis loses (77.4 -> 81.1 us) and keeps 8
+// wide bundles (16 kx = 256-byte runs) exist for the middle axis of 3-D grids with extents <= 256 (opt-in, GSP_FFT_WIDE=1): the first
+// measurements on the B200 at 256^3 favoured them for the y passes (57.5 -> 53.4 us, 51.1 -> 50.4 us; the fused pass of the last axis
+// lost, 77.4 -> 81.1 us, and never used them), a repeated same-box A/B of the final tree did not (y inverse 52 -> 56 us)
 constexpr int P2_WIDE = 16;
 GSP_HD constexpr bool p2_wide_ok(int N) { return N >= 64 && N <= 256 && p2_bundle(N) < P2_WIDE; }
 
@@ -907,11 +907,12 @@ int build_device(gsp_ctx* ctx, gsp_fft_plan* p, FftDev* d, const CovDev& cov, co
   for (int axis = 1; axis < p->ndim; ++axis) {
     AxisPlan& a = d->ax[axis];
     if (!a.fast) continue;
-    // GSP_FFT_WIDE=0 keeps 8 kx everywhere (A/B runs); the fused plane kernels and the bundle-group slabs are built for 8
+    // GSP_FFT_WIDE=1 turns the 16-kx bundles on (off by default: a repeated same-box A/B of the final tree showed 280 vs 274 us per
+    // realization on one lane and no difference with 4 lanes); the fused plane kernels and the bundle-group slabs are built for 8
     const char* wenv = getenv("GSP_FFT_WIDE");
     const char* fenv = getenv("GSP_FFT_FUSE");
     const bool fuse_req = fenv && fenv[0] ? fenv[0] == '1' : GSP_FFT_FUSE_DEFAULT != 0;
-    const bool wide = p->ndim == 3 && axis == 1 && p2_wide_ok(a.len) && !(wenv && wenv[0] == '0') && !fuse_req && d->slab_mode != 2;
+    const bool wide = p->ndim == 3 && axis == 1 && p2_wide_ok(a.len) && (wenv && wenv[0] == '1') && !fuse_req && d->slab_mode != 2;
     a.bundle = wide ? P2_WIDE : p2_bundle(a.len);
     const unsigned B = (unsigned)a.bundle;
     const unsigned long long dH[3] = {2ull * p->hx, (unsigned long long)p->dims[1],

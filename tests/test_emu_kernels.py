@@ -194,10 +194,11 @@ def test_philox_matches_restatement(emu_lib):
     plan.close()
 
 
-def test_fftsim_pow2_fast_path(emu_lib):
+def test_fftsim_pow2_fast_path(emu_lib, monkeypatch):
     """register-resident power-of-two passes (fft_pow2.cuh): 2- and 3-stage plans, TMA tiles, persistent pipelining."""
     rng = np.random.default_rng(11)
-    # (32, 64, 16) and (32, 128, 8): middle axis of a 3-D grid with extent 64..256 -> 16-kx bundles (256-byte runs)
+    # (32, 64, 16) and (32, 128, 8): middle axis of a 3-D grid with extent 64..256 -> 16-kx bundles (256-byte runs, opt-in)
+    monkeypatch.setenv("GSP_FFT_WIDE", "1")
     for dims in ((64, 32), (32, 16, 16), (256, 16), (1024, 16), (32, 512), (32, 1024), (64, 16, 32), (32, 64, 16), (32, 128, 8)):
         nd = len(dims)
         st = iso(O.SPHERICAL, 1.7, 4.0, nd)

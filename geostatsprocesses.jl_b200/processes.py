@@ -328,18 +328,27 @@ def merge_moments(parts):
     return cnt, mean, m2 / (cnt - 1)
 
 
+def _fresh_seed() -> int:
+    """64 fresh bits per unseeded call (os entropy through numpy's SeedSequence)."""
+    return int(np.random.SeedSequence().generate_state(1, dtype=np.uint64)[0])
+
+
 def rand(process: GaussianProcess, domain, nreals: Optional[int] = None, *, rng: Union[None, int, np.random.Generator] = None,
          data: Optional[GeoTable] = None, method: Optional[FieldSimulationMethod] = None, init=None, resident: bool = False):
     """rand([rng], process, domain, [n]; data, method, init) - field.jl:47-124.
 
     rng: a numpy Generator -> noise is drawn on the host in the reference's order and injected
-    (parity mode); None or an int seed -> on-device counter RNG (throughput mode).
+    (parity mode); an int seed -> on-device counter RNG, reproducible; None -> on-device counter RNG with a FRESH
+    64-bit seed per call (the reference draws from Random.default_rng(): successive calls are independent).
     Without `nreals` a single GeoTable is returned, with it an Ensemble.  resident=True keeps the realizations on the
     GPUs (Ensemble with the `fetch` hook, ensembles.jl:16): statistics run in HBM, `e[i]` downloads one realization."""
     init = init or NearestInit()
     smethod = method if method is not None else defaultsimulation(process, domain, data)
     gen = rng if isinstance(rng, np.random.Generator) else None
-    seed = int(rng) if isinstance(rng, (int, np.integer)) else 0
+    if isinstance(rng, (int, np.integer)):
+        seed = int(rng) & 0xFFFFFFFFFFFFFFFF
+    else:
+        seed = _fresh_seed()  # unused when a Generator injects the noise
     n = 1 if nreals is None else int(nreals)
     if isinstance(smethod, LUSIM):
         pre = preprocess_lusim(process, smethod, init, domain, data)

@@ -1,6 +1,7 @@
 # GeoStatsProcessesB200.jl - reference-side glue for libgspb200 (see INTEGRATION.md).
 #
-# NOT EXECUTED IN THIS REPOSITORY'S CI: the build image has no Julia.  The file is the binding a
+# NOT EXECUTED IN THIS REPOSITORY'S CI: the build image has no Julia, so boundary item (b) is UNTESTED on the Julia side
+# (the same entry points with the same marshalling are what the Python ctypes tests drive).  The file is the binding a
 # maintainer of GeoStatsProcesses.jl would add (as a package extension, exactly like
 # ext/GeoStatsProcessesTuringPatternsExt.jl adds a method from outside): two method structs that plug
 # into the unchanged `rand(process, domain, n; method=...)` (src/simulation/field.jl:47-124) through
@@ -9,14 +10,18 @@
 module GeoStatsProcessesB200
 
 using GeoStatsProcesses
-using GeoStatsProcesses: FieldSimulationMethod, GaussianProcess, initialize
+using GeoStatsProcesses: FieldSimulationMethod, GaussianProcess, Ensemble, NearestInit, initialize
 using GeoStatsFunctions
+using GeoTables: georef
 using Meshes
 using LinearAlgebra
 using Random
 using Unitful: ustrip, unit
 
 import GeoStatsProcesses: preprocess, randsingle
+# the statistics of src/ensembles.jl:42-52 are Distributions' generic functions (GeoStatsProcesses.jl:28-30 imports them);
+# importing the bindings from GeoStatsProcesses extends exactly the functions `mean(e::Ensemble)` etc. dispatch on
+import GeoStatsProcesses: mean, var, cdf, ccdf, quantile
 
 const LIB = get(ENV, "GSP_B200_LIB", "libgspb200")
 
@@ -321,30 +326,35 @@ function rand_resident(process::GaussianProcess, domain, nreals::Int; method=FFT
     check(ctx, ccall((:gsp_lu_sample_ensemble, LIB), Cint,
                      (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, UInt64, Int32, Int64, Float64, Ptr{Float64}),
                      pre.plans[1], ref[], C_NULL, seed, 0, 0, NaN, C_NULL))
-    var = pre.names[1]
+    var = pre.vars[1]
   end
   reals = DeviceReals(ref[], var, n, nreals)
   Ensemble(domain, reals; fetch=fetchreal)
 end
 
-function devstat(e::Ensemble{<:Any,DeviceReals}, f::Symbol, args...)
+# one explicit ccall per statistic: ccall needs a literal (symbol, library) pair and a literal argument-type tuple
+function devvec(e::Ensemble{<:Any,DeviceReals}, call)
   z = Vector{Float64}(undef, e.reals.n)
-  argt = (Ptr{Cvoid}, map(_ -> Float64, args)..., Ptr{Float64})
-  check(context(), ccall((f, LIB), Cint, argt, e.reals.ptr, map(Float64, args)..., z))
+  check(context(), call(e.reals.ptr, z))
   georef((; e.reals.var => z), e.domain)
 end
-Statistics.mean(e::Ensemble{<:Any,DeviceReals}) = devstat(e, :gsp_ensemble_mean)            # ensembles.jl:42
-Statistics.var(e::Ensemble{<:Any,DeviceReals}) = devstat(e, :gsp_ensemble_var)              # ensembles.jl:44
-cdf(e::Ensemble{<:Any,DeviceReals}, x::Number) = devstat(e, :gsp_ensemble_cdf, x)           # ensembles.jl:46
-ccdf(e::Ensemble{<:Any,DeviceReals}, x::Number) = devstat(e, :gsp_ensemble_ccdf, x)         # ensembles.jl:48
-function Statistics.quantile(e::Ensemble{<:Any,DeviceReals}, ps::AbstractVector)            # ensembles.jl:50-52
+mean(e::Ensemble{<:Any,DeviceReals}) =                                                      # ensembles.jl:42
+  devvec(e, (h, z) -> ccall((:gsp_ensemble_mean, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), h, z))
+var(e::Ensemble{<:Any,DeviceReals}) =                                                       # ensembles.jl:44
+  devvec(e, (h, z) -> ccall((:gsp_ensemble_var, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), h, z))
+cdf(e::Ensemble{<:Any,DeviceReals}, x::Number) =                                            # ensembles.jl:46
+  devvec(e, (h, z) -> ccall((:gsp_ensemble_cdf, LIB), Cint, (Ptr{Cvoid}, Float64, Ptr{Float64}), h, Float64(x), z))
+ccdf(e::Ensemble{<:Any,DeviceReals}, x::Number) =                                           # ensembles.jl:48
+  devvec(e, (h, z) -> ccall((:gsp_ensemble_ccdf, LIB), Cint, (Ptr{Cvoid}, Float64, Ptr{Float64}), h, Float64(x), z))
+function quantile(e::Ensemble{<:Any,DeviceReals}, ps::AbstractVector)                       # ensembles.jl:50-52
   n = e.reals.n
   q = Matrix{Float64}(undef, n, length(ps))
+  pv = Float64.(ps)
   check(context(), ccall((:gsp_ensemble_quantile, LIB), Cint, (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}),
-                         e.reals.ptr, length(ps), Float64.(ps), q))
-  [georef((; e.reals.var => q[:, k]), e.domain) for k in eachindex(ps)]
+                         e.reals.ptr, length(pv), pv, q))
+  [georef((; e.reals.var => q[:, k]), e.domain) for k in eachindex(pv)]
 end
-Statistics.quantile(e::Ensemble{<:Any,DeviceReals}, p::Number) = first(quantile(e, [p]))
+quantile(e::Ensemble{<:Any,DeviceReals}, p::Number) = first(quantile(e, [p]))
 release!(e::Ensemble{<:Any,DeviceReals}) = ccall((:gsp_ensemble_destroy, LIB), Cint, (Ptr{Cvoid},), e.reals.ptr)
 
 export LUSIM_B200, FFTSIM_B200, rand_resident, release!

@@ -131,3 +131,16 @@ def test_ensemble():  # test/ensembles.jl
     assert ens.quantile(0.5).z.tolist() == [2.0] * 9
     assert "2D Ensemble" in repr(ens) and "N° reals:  3" in repr(ens)
     assert [r.z[0] for r in ens] == [1.0, 2.0, 3.0]
+
+
+def test_unseeded_rand_calls_are_independent(emu_lib):
+    """rng=None draws a fresh seed per call (the reference uses Random.default_rng(), field.jl:47-48); an int seed reproduces."""
+    proc = gsp.GaussianProcess(gsp.SphericalCovariance(range=5.0))
+    grid = gsp.CartesianGrid(12, 10)
+    for method in (gsp.LUSIM(library=emu_lib), gsp.FFTSIM(library=emu_lib)):
+        a = gsp.rand(proc, grid, 2, method=method)
+        b = gsp.rand(proc, grid, 2, method=method)
+        assert not np.array_equal(a[0].field, b[0].field)
+        c = gsp.rand(proc, grid, 2, rng=11, method=method)
+        d = gsp.rand(proc, grid, 2, rng=11, method=method)
+        assert np.array_equal(c[0].field, d[0].field) and np.array_equal(c[1].field, d[1].field)

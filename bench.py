@@ -19,6 +19,12 @@ import sys
 import tempfile
 import time
 
+if "reference" in sys.argv:
+    # the CPU arm uses every host core whatever the launcher exported (torchrun sets OMP_NUM_THREADS=1, which silently turned
+    # OpenBLAS single-threaded in round 1's N>1 reference runs); must happen before numpy / scipy load their BLAS
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_v] = str(os.cpu_count() or 1)
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -29,10 +35,15 @@ RANGES = (40.0, 20.0, 10.0)
 ANGLE = 30.0
 REALS_PER_GPU = 64
 E2E_REALS = 8          # realizations per e2e step (host pinned buffers, PCIe inside the timed region)
-LUSIM_GRID = (128, 128)
-LUSIM_ND = 1000
-LUSIM_R = 1000
 SPHERICAL, EXPONENTIAL = 1, 2
+# LUSIM halves of the metric (BASELINE.json configs[2] and configs[4]); C1 / C2 are one-line extras
+LUSIM_C3 = {"name": "c3", "dims": (128, 128), "nd": 1000, "kind": EXPONENTIAL, "range": 20.0, "R": 1000, "nvars": 1, "rho": None, "seed": 3,
+            "workload": "LUSIM conditional 128x128 grid (16,384 nodes) + 1,000 data, ExponentialCovariance(range=20), 1,000 realizations"}
+LUSIM_C5 = {"name": "c5", "dims": (256, 128), "nd": 500, "kind": SPHERICAL, "range": 20.0, "R": 4096, "nvars": 2, "rho": 0.7, "seed": 5,
+            "workload": "bivariate LUSIM (rho = 0.7) 256x128 grid (32,768 nodes) + 500 shared data nodes, SphericalCovariance(range=20), "
+                        "4,096 realizations of both variables"}
+LUSIM_C1 = {"name": "c1", "dims": (50, 50), "nd": 0, "kind": SPHERICAL, "range": 20.0, "R": 100, "nvars": 1, "rho": None, "seed": 1,
+            "workload": "LUSIM unconditional 50x50 grid, SphericalCovariance(range=20), 100 realizations"}
 
 
 def shard_range(R: int, rank: int, world: int):
@@ -48,10 +59,18 @@ def fft_structs():
     return [(SPHERICAL, 1.0, np.diag(1.0 / np.asarray(RANGES)) @ R.T)]
 
 
-def lusim_structs():
+def lusim_structs(cfg):
     A = np.zeros((3, 3))
-    A[0, 0] = A[1, 1] = 1.0 / 20.0
-    return [(EXPONENTIAL, 1.0, A)]
+    A[0, 0] = A[1, 1] = 1.0 / cfg["range"]
+    return [(cfg["kind"], 1.0, A)]   # C5: both marginals of [1 .7; .7 1] * Spherical are this structure (lusim.jl:132-137)
+
+
+def lusim_data(cfg):
+    N = cfg["dims"][0] * cfg["dims"][1]
+    rng = np.random.default_rng(cfg["seed"])
+    dinds = np.sort(rng.choice(N, cfg["nd"], replace=False)) if cfg["nd"] else np.zeros(0, dtype=np.int64)
+    z = [rng.standard_normal(cfg["nd"]) * 0.5 for _ in range(cfg["nvars"])]
+    return N, dinds, z
 
 
 def peaks():
@@ -151,6 +170,13 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
+    threads = {"scipy_fft_workers": cores, "OMP_NUM_THREADS": os.environ.get("OMP_NUM_THREADS")}
+    try:
+        import threadpoolctl
+        threadpoolctl.threadpool_limits(cores)
+        threads["blas"] = [f"{i.get('internal_api')} {i.get('num_threads')}" for i in threadpoolctl.threadpool_info() if i.get("user_api") == "blas"]
+    except Exception:
+        pass
     per_step = 1  # bounded sample: each step = 1 realization of the same 256^3 workload
     one = cpu_fft_sampler()
     for k in range(max(args.warmup, 1)):
@@ -168,7 +194,11 @@ def run_reference(args):
                          "sample": f"{args.steps * per_step} realization(s) of the 256^3 workload, scipy.fft workers={cores}; "
                                    "Julia is absent from the image, so the oracle restatement stands in for the reference"},
         "e2e": {"value": val, "unit": "realizations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "threads": threads,
     }
+    if not args.skip_lusim:
+        # LUSIM half of the metric on the same host cores (outside the timed FFTSIM steps): C3 in full, C5 reduced + extrapolated
+        line["lusim"] = {"cpu_baseline": cpu_lusim_baseline()}
     print(json.dumps(line))
 
 
@@ -246,6 +276,7 @@ def run_gpu(args):
     mean0 = float(z0.mean())
     var0 = float((z0 * z0).sum() / (N - 1))
     ok_invariants = abs(mean0) < 1e-10 and abs(var0 - 1.0) < 1e-10
+    del z0
 
     # ---- per-kernel device times (instrumented pass right after the timed region, CUDA events per launch)
     # The timed region runs 4 realizations concurrently (lanes), which makes per-launch event times overlap; the per-kernel
@@ -303,15 +334,72 @@ def run_gpu(args):
         dist.all_reduce(tr, op=dist.ReduceOp.MAX)
     e2e_rng_value = Re * world * e2e_steps / float(tr[0])
 
+    # ---- what bounds e2e: pinned host<->device copy bandwidth of this box, all ranks copying at once (both directions concurrently,
+    # the same 2 x 8N bytes per realization the e2e step moves).  e2e cannot exceed aggregate / (16 N) whatever the kernels do.
+    s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    dwb = w[:Re]
+    dzb = z[:Re]
+    barrier()
+    t0 = time.perf_counter()
+    creps = 2
+    for _ in range(creps):
+        with torch.cuda.stream(s_in):
+            dwb.copy_(hw, non_blocking=True)
+        with torch.cuda.stream(s_out):
+            hz.copy_(dzb, non_blocking=True)
+    barrier()
+    tc = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+    host_copy_gbs = 2.0 * 8 * N * Re * creps * world / float(tc[0]) / 1e9
+    hw.copy_(w[:Re].cpu())  # restore (dwb aliases w)
+    del dwb, dzb
+
+    # ---- the resident path of the same metric on every rank: Rg realizations simulated into a device-resident ensemble (on-device
+    # noise), only the per-node mean and variance maps (2 x 8N bytes) return to pinned host memory - Ensemble's `fetch` hook design
+    res_value = None
+    if not args.skip_ensemble:
+        hst = torch.empty((2, N), dtype=torch.float64).pin_memory()
+        ens_r = plan.sample_ensemble(Rg, None, seed=11, first_real=r0)
+
+        def resident_step():
+            plan.sample_ensemble(Rg, None, seed=12, first_real=r0, ens=ens_r)
+            lib.check(lib.lib.gsp_ensemble_mean(ens_r.h, hst[0].data_ptr()))
+            lib.check(lib.lib.gsp_ensemble_var(ens_r.h, hst[1].data_ptr()))
+
+        resident_step()
+        barrier()
+        t0 = time.perf_counter()
+        resident_step()
+        barrier()
+        trs = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(trs, op=dist.ReduceOp.MAX)
+        res_value = Rg * world / float(trs[0])
+        ens_r.close()
+        del hst
+
     # ---- resident ensemble + statistics in HBM: what a user who wants mean / variance / quantile maps pays
     ens_line = None
     if rank == 0 and not args.skip_ensemble:
         ens_line = bench_ensemble(lib, plan, Rg, N, r0)
 
-    # ---- LUSIM 16k nodes (configs[2]) on rank 0's GPU, reported beside the headline
+    # ---- LUSIM half of the metric (configs[2] and configs[4]): rank 0 drives ONE context over all `world` GPUs (the library's
+    # multi-device model: one process, peer access over NVLink); the other ranks release their buffers and wait on the CPU
+    # (gloo barrier - an NCCL barrier would spin a kernel on the GPUs being measured)
     lus = None
-    if rank == 0 and not args.skip_lusim:
-        lus = bench_lusim(lib, gsp, torch, dev)
+    if not args.skip_lusim:
+        plan.close()
+        plan = None
+        del w, z, hw, hz
+        torch.cuda.empty_cache()
+        import datetime
+        cpu_group = dist.new_group(backend="gloo", timeout=datetime.timedelta(minutes=30)) if world > 1 else None
+        barrier()
+        if rank == 0:
+            lus = bench_lusim_all(gsp, torch, world, args.skip_cpu)
+        if cpu_group is not None:
+            dist.barrier(group=cpu_group)
 
     if rank == 0:
         pk = peaks()
@@ -362,7 +450,15 @@ def run_gpu(args):
                     "api": "gsp_fft_sample (host pointers, pinned), 3-stream H2D/compute/D2H pipeline",
                     "device_rng_variant": {"value": e2e_rng_value, "unit": "realizations/s", "h2d_bytes_per_step": 0,
                                            "d2h_bytes_per_step": 8 * N * Re,
-                                           "note": "same call with w = NULL (on-device Philox noise); PCIe carries only the fields"}},
+                                           "note": "same call with w = NULL (on-device Philox noise); PCIe carries only the fields"},
+                    "host_copy_ceiling": {"pinned_h2d_plus_d2h_GBps_all_ranks": host_copy_gbs,
+                                          "realizations_per_s_at_that_bandwidth": host_copy_gbs * 1e9 / (16.0 * N),
+                                          "note": "all ranks copy 8N bytes in and 8N bytes out per realization concurrently (torch copy_, pinned); "
+                                                  "the e2e value cannot exceed this whatever the kernels do"},
+                    "resident_statistics_variant": None if res_value is None else {
+                        "value": res_value, "unit": "realizations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 16 * N,
+                        "note": "realizations stay in HBM (gsp_fft_sample_ensemble, on-device noise); only the mean and variance maps "
+                                "return to pinned host memory (gsp_ensemble_mean / _var) - the Ensemble `fetch` design of ensembles.jl:16"}},
             "gpu_launches": int(launches), "roofline": roof, "clocks": clocks,
             "invariants_ok": ok_invariants, "field_mean": mean0, "field_var": var0,
         }
@@ -375,7 +471,8 @@ def run_gpu(args):
         if ens_line is not None:
             line["ensemble_statistics"] = ens_line
         emit(line)
-    plan.close()
+    if plan is not None:
+        plan.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -435,60 +532,244 @@ def plan_nh(dims):
     return (dims[0] // 2 + 1) * dims[1] * dims[2]
 
 
-def bench_lusim(lib, gsp, torch, dev):
-    """LUSIM conditional, 128x128 grid (16,384 nodes) + 1,000 hard data, ExponentialCovariance range 20, 1,000 realizations."""
-    N = LUSIM_GRID[0] * LUSIM_GRID[1]
-    rng = np.random.default_rng(3)
-    dinds = np.sort(rng.choice(N, LUSIM_ND, replace=False))
-    z1 = rng.standard_normal(LUSIM_ND) * 0.5
-    dom = (gsp._lib.make_grid_domain(LUSIM_GRID, [0.0, 0.0], [1.0, 1.0]), None)
-    gsp.LUPlan(lib, lusim_structs(), dom, dinds + 1, z1, 0.0).close()  # warm-up (allocator, module load)
-    t0 = time.perf_counter()
-    plan = gsp.LUPlan(lib, lusim_structs(), dom, dinds + 1, z1, 0.0)
-    plan_s = time.perf_counter() - t0
-    asm_ms, fac_ms, solve_ms = plan.times()  # CUDA-event stage timers of the un-profiled plan (look-ahead streams concurrent)
-    lib.profile_enable(True)
-    p2 = gsp.LUPlan(lib, lusim_structs(), dom, dinds + 1, z1, 0.0)
-    prof_plan = lib.profile_read()
-    p2.close()
-    R = LUSIM_R
-    W = torch.randn((R, plan.Ns), dtype=torch.float64, device=dev)
-    Z = torch.empty((R, N), dtype=torch.float64, device=dev)
+def measure_fp64_peak(torch, dev):
+    """FP64 tensor-core denominator measured IN THIS RUN: cuBLAS Dgemm 8192^3 through torch.matmul (library call, not ours):
+    best single call (burst) and ~2 s back to back (sustained).  Nominal B200 FP64 tensor peak: 40 TF/s."""
+    n = 8192
+    a = torch.randn((n, n), dtype=torch.float64, device=dev)
+    b = torch.randn((n, n), dtype=torch.float64, device=dev)
+    c = torch.empty_like(a)
+    fl = 2.0 * n ** 3
     for _ in range(2):
-        plan.sample_dev(R, W.data_ptr(), plan.Ns, 0, 0, 0, math.nan, None, Z.data_ptr(), N)
-    lib.profile_enable(True)
-    ms = []
+        torch.matmul(a, b, out=c)
+    torch.cuda.synchronize(dev)
+    best = 1e30
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, b, out=c)
+        e1.record()
+        e1.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    reps = max(4, int(2000.0 / best))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        torch.matmul(a, b, out=c)
+    e1.record()
+    e1.synchronize()
+    sus = e0.elapsed_time(e1) / reps
+    del a, b, c
+    return {"burst_tflops": fl / best / 1e9, "sustained_tflops": fl / sus / 1e9, "nominal_tflops": 40.0,
+            "how": f"torch.matmul f64 {n}^3 (cuBLAS Dgemm): best of 5 single calls; {reps} calls back to back"}
+
+
+def bench_lusim_config(gsp, torch, lib, cfg, ndev, peak_tf, detailed=False, e2e=True):
+    """one LUSIM configuration through the C ABI on the context `lib` (ndev devices driven by this process):
+    plan (assembly + Cholesky + d2; the factorization is distributed over the devices), resident sampling with the on-device
+    RNG (realizations sharded over the devices), and the end-to-end run with host noise / host fields in pinned memory."""
+    N, dinds, z = lusim_data(cfg)
+    nv, R, rho = cfg["nvars"], cfg["R"], cfg["rho"]
+    dom = (gsp._lib.make_grid_domain(cfg["dims"], [0.0, 0.0], [1.0, 1.0]), None)
+    st = lusim_structs(cfg)
+    nd = len(dinds)
+
+    def make_plans():
+        return [gsp.LUPlan(lib, st, dom, dinds + 1 if nd else None, z[j] if nd else None, 0.0) for j in range(nv)]
+
+    def sync():
+        for d in range(ndev):
+            torch.cuda.synchronize(d)
+
+    for p in make_plans():  # warm-up (allocator pools, module load on every device)
+        p.close()
+    sync()
+    best = None
+    for _ in range(2):      # the plan is built once per ensemble: best of two timed builds
+        t0 = time.perf_counter()
+        plans = make_plans()
+        plan_s = time.perf_counter() - t0
+        tm = [p.times() for p in plans]
+        if best is None or plan_s < best[0]:
+            if best is not None:
+                for p in best[2]:
+                    p.close()
+            best = (plan_s, tm, plans)
+        else:
+            for p in plans:
+                p.close()
+    plan_s, tm, plans = best
+    asm_ms, fac_ms, solve_ms = (sum(t[k] for t in tm) for k in range(3))
+    Ns = plans[0].Ns
+    Np = (nd + 127) // 128 * 128 + (Ns + 127) // 128 * 128
+    f_chol = nv * Np ** 3 / 3.0
+    f_lz = nv * float(Ns) ** 2 * R
+
+    # ---- resident sampling (device RNG, fields stay in HBM, sharded over the devices)
+    ens = [gsp.DeviceEnsemble(lib, N, R) for _ in range(nv)]
+
+    def sample_resident():
+        plans[0].sample_ensemble(R, None, seed=7, stream=0, ens=ens[0])
+        if nv == 2:
+            plans[1].sample_ensemble(R, None, seed=7, stream=1, rho=rho, ens=ens[1])
+
+    sample_resident()
+    sync()
+    ts = []
     for _ in range(3):
-        plan.sample_dev(R, W.data_ptr(), plan.Ns, 0, 0, 0, math.nan, None, Z.data_ptr(), N)
-        ms.append(lib.last_sample_ms())
-    prof_samp = lib.profile_read()
-    lib.profile_enable(False)
-    sample_ms = min(ms)
-    Np = (LUSIM_ND + 127) // 128 * 128 + (plan.Ns + 127) // 128 * 128
-    f_chol = Np ** 3 / 3.0
-    f_lz = float(plan.Ns) ** 2 * R
-    chol_ms = sum(v["ms"] for k, v in prof_plan.items() if k.startswith("gemm_dmma") or k == "potrf_diag")
-    # end to end through the host API with pinned buffers
-    hW = torch.randn((R, plan.Ns), dtype=torch.float64).pin_memory()
-    hZ = torch.empty((R, N), dtype=torch.float64).pin_memory()
-    t0 = time.perf_counter()
-    lib.check(lib.lib.gsp_lu_sample(plan.h, R, hW.data_ptr(), 0, 0, 0, math.nan, None, hZ.data_ptr()))
-    e2e_s = time.perf_counter() - t0
-    exact = bool(np.array_equal(hZ.numpy()[:, dinds], np.repeat(z1[None, :], R, 0)))
-    plan.close()
-    return {"workload": "LUSIM conditional 128x128 grid (16,384 nodes) + 1,000 data, ExponentialCovariance(range=20), 1,000 realizations",
-            "plan_wall_s": plan_s, "assemble_device_ms": asm_ms, "factor_device_ms": fac_ms, "solve_d2_device_ms": solve_ms,
-            "factor_tflops": f_chol / fac_ms / 1e9 if fac_ms else None,
-            "factor_plus_sample_tflops": (f_chol + f_lz) / (fac_ms + sample_ms) / 1e9 if fac_ms else None,
-            "fp64_peak_tflops": 35.5,
-            "factor_plus_sample_frac_of_peak": (f_chol + f_lz) / (fac_ms + sample_ms) / 1e9 / 35.5 if fac_ms else None,
-            "factor_kernel_ms_sum_serialised": chol_ms,
-            "sample_device_ms": sample_ms, "sample_tflops": f_lz / sample_ms / 1e9,
-            "realizations_per_s_sampling": R / sample_ms * 1e3, "realizations_per_s_end_to_end": R / (plan_s + e2e_s),
-            "e2e_sample_wall_s": e2e_s, "data_honoured_exactly": exact,
-            "kernel_ms_plan": {k: round(v["ms"], 3) for k, v in prof_plan.items()},
-            "kernel_ms_sample_x3": {k: round(v["ms"], 3) for k, v in prof_samp.items()},
-            "fp64_peak_note": "cuBLAS Dgemm 8192^3 measured 35.5 TF/s on this pool (tools/gpu_check.py); fractions are of that"}
+        t0 = time.perf_counter()
+        sample_resident()
+        ts.append(time.perf_counter() - t0)
+    sample_s = min(ts)
+    mean_err = None
+    if nd:
+        m = ens[0].mean()
+        mean_err = float(np.abs(m[dinds] - z[0]).max())   # data nodes: every realization carries z1
+    for e in ens:
+        e.close()
+    out = {"workload": cfg["workload"], "n_devices": ndev, "plan_wall_s": plan_s, "assemble_device_ms": asm_ms, "factor_device_ms": fac_ms,
+           "solve_d2_device_ms": solve_ms, "factor_tflops": f_chol / fac_ms / 1e9,
+           "sample_resident_wall_ms": sample_s * 1e3, "sample_tflops": f_lz / sample_s / 1e12,
+           "factor_plus_sample_tflops": (f_chol + f_lz) / (fac_ms / 1e3 + sample_s) / 1e12,
+           "realizations_per_s_sampling_resident": R / sample_s,
+           "realizations_per_s_plan_plus_resident_sampling": R / (plan_s + sample_s),
+           "flops": {"cholesky": f_chol, "L_times_W": f_lz, "note": "Np^3/3 per variable (padded joint matrix) and Ns^2 R per variable (SURVEY 8d)"},
+           "data_mean_abs_err_resident": mean_err}
+    if peak_tf:
+        out["factor_plus_sample_frac_of_peak"] = out["factor_plus_sample_tflops"] / (peak_tf * ndev)
+        out["factor_frac_of_peak"] = out["factor_tflops"] / (peak_tf * ndev)
+        out["peak_tflops_used"] = peak_tf * ndev
+
+    # ---- end to end: plan + host-pointer sampling, injected host noise and host fields in pinned memory (H2D + D2H inside)
+    if e2e:
+        hW = [torch.empty((R, Ns), dtype=torch.float64, pin_memory=True).normal_() for _ in range(nv)]
+        hZ = [torch.empty((R, N), dtype=torch.float64, pin_memory=True) for _ in range(nv)]
+
+        def sample_host():
+            lib.check(lib.lib.gsp_lu_sample(plans[0].h, R, hW[0].data_ptr(), 0, 0, 0, math.nan, None, hZ[0].data_ptr()))
+            if nv == 2:
+                lib.check(lib.lib.gsp_lu_sample(plans[1].h, R, hW[1].data_ptr(), 0, 1, 0, rho, hW[0].data_ptr(), hZ[1].data_ptr()))
+
+        sample_host()
+        te = []
+        for _ in range(2):
+            t0 = time.perf_counter()
+            sample_host()
+            te.append(time.perf_counter() - t0)
+        e2e_s = min(te)
+        exact = all(bool(np.array_equal(hZ[j].numpy()[:, dinds], np.repeat(z[j][None, :], R, 0))) for j in range(nv)) if nd else None
+        out.update({"e2e_sample_wall_s": e2e_s, "realizations_per_s_end_to_end": R / (plan_s + e2e_s),
+                    "e2e_h2d_bytes": 8 * Ns * R * nv, "e2e_d2h_bytes": 8 * N * R * nv, "data_honoured_exactly": exact})
+        del hW, hZ
+
+    # ---- per-kernel device times of one profiled plan + sampling (1-device contexts only: events serialise the launches)
+    if detailed and ndev == 1:
+        lib.profile_enable(True)
+        for p in make_plans():
+            p.close()
+        prof_plan = lib.profile_read()
+        dev = torch.device("cuda", lib.devices[0])
+        W = torch.randn((R, Ns), dtype=torch.float64, device=dev)
+        Z = torch.empty((R, N), dtype=torch.float64, device=dev)
+        plans[0].sample_dev(R, W.data_ptr(), Ns, 0, 0, 0, math.nan, None, Z.data_ptr(), N)
+        lib.profile_enable(True)
+        ms = []
+        for _ in range(3):
+            plans[0].sample_dev(R, W.data_ptr(), Ns, 0, 0, 0, math.nan, None, Z.data_ptr(), N)
+            ms.append(lib.last_sample_ms())
+        prof_samp = lib.profile_read()
+        lib.profile_enable(False)
+        del W, Z
+        out.update({"sample_device_ms_injected_noise": min(ms), "sample_device_tflops": float(Ns) ** 2 * R / min(ms) / 1e9,
+                    "factor_kernel_ms_sum_serialised": sum(v["ms"] for k, v in prof_plan.items() if k.startswith("gemm_dmma") or k.startswith("potrf")),
+                    "kernel_ms_plan": {k: round(v["ms"], 3) for k, v in prof_plan.items()},
+                    "kernel_launches_plan": {k: v["launches"] for k, v in prof_plan.items()},
+                    "kernel_ms_sample_x3": {k: round(v["ms"], 3) for k, v in prof_samp.items()}})
+    for p in plans:
+        p.close()
+    return out
+
+
+def bench_lusim_all(gsp, torch, world, skip_cpu):
+    """LUSIM half of the metric on rank 0: C3 and C5 (+ C1) on a context over ALL `world` GPUs of the job (the other ranks idle in
+    a CPU-side barrier meanwhile), the same on one GPU when world > 1 (speed-up inside one line), the in-run FP64 peak and, at
+    N = 1, the oracle's CPU time for the same configurations."""
+    dev0 = torch.device("cuda", 0)
+    peak = measure_fp64_peak(torch, dev0)
+    ptf = peak["burst_tflops"]
+    out = {"fp64_peak": peak, "peak_note": "fractions are of the in-run cuBLAS Dgemm burst figure x number of devices"}
+    libN = gsp.Library(devices=list(range(world)))
+    out["c3"] = bench_lusim_config(gsp, torch, libN, LUSIM_C3, world, ptf, detailed=True)
+    out["c5"] = bench_lusim_config(gsp, torch, libN, LUSIM_C5, world, ptf)
+    out["c1"] = bench_lusim_config(gsp, torch, libN, LUSIM_C1, world, ptf, e2e=False)
+    libN.close()
+    if world > 1:
+        lib1 = gsp.Library(devices=[0])
+        for key, cfg in (("c3", LUSIM_C3), ("c5", LUSIM_C5)):
+            one = bench_lusim_config(gsp, torch, lib1, cfg, 1, ptf)
+            out[key]["one_gpu_same_run"] = {k: one[k] for k in ("plan_wall_s", "factor_device_ms", "sample_resident_wall_ms",
+                                                                "realizations_per_s_end_to_end", "realizations_per_s_plan_plus_resident_sampling")}
+            out[key]["speedup_vs_n1"] = {"factor": one["factor_device_ms"] / out[key]["factor_device_ms"],
+                                         "sample_resident": one["sample_resident_wall_ms"] / out[key]["sample_resident_wall_ms"],
+                                         "realizations_per_s_end_to_end": out[key]["realizations_per_s_end_to_end"] / one["realizations_per_s_end_to_end"],
+                                         "realizations_per_s_plan_plus_resident_sampling":
+                                             out[key]["realizations_per_s_plan_plus_resident_sampling"] / one["realizations_per_s_plan_plus_resident_sampling"]}
+        lib1.close()
+    if world == 1 and not skip_cpu:
+        out["cpu_baseline"] = cpu_lusim_baseline()
+    return out
+
+
+def cpu_lusim_baseline(full_c3=True):
+    """the oracle restatement of lusim.jl:38-175 on the host cores (SciPy / OpenBLAS potrf, trsm, gemm), timed beside the GPU numbers:
+    C3 in full; C5 at 1/4 of the nodes (8,192 + 125 data, 256 realizations) with the stated N^3 / N^2 R extrapolation."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import gsp_oracle as O
+    try:
+        import threadpoolctl
+        blas = [f"{i.get('internal_api')} {i.get('num_threads')} threads" for i in threadpoolctl.threadpool_info() if i.get("user_api") == "blas"]
+    except Exception:
+        blas = ["unknown"]
+
+    def run(cfg, dims, nd, R):
+        N = dims[0] * dims[1]
+        rng = np.random.default_rng(cfg["seed"])
+        dinds = np.sort(rng.choice(N, nd, replace=False))
+        z1 = rng.standard_normal(nd) * 0.5
+        A = np.zeros((3, 3))
+        A[0, 0] = A[1, 1] = 1.0 / cfg["range"]
+        st = [O.Structure(cfg["kind"], 1.0, A)]
+        coords = O.grid_centroids(dims, [0, 0], [1, 1])
+        t0 = time.perf_counter()
+        pre = O.lusim_preprocess(st, coords, dinds, z1, 0.0)
+        t_pre = time.perf_counter() - t0
+        W = rng.standard_normal((N - nd, R))
+        t0 = time.perf_counter()
+        O.lusim_sample(pre, W)
+        t_s = time.perf_counter() - t0
+        # the O(N^2) covariance assembly inside the preprocess, timed on its own so that the extrapolation scales it by N^2, not N^3
+        t0 = time.perf_counter()
+        O.pairwise(st, coords[pre.sinds])
+        O.pairwise(st, coords[dinds], coords[pre.sinds])
+        O.pairwise(st, coords[dinds])
+        t_asm = min(time.perf_counter() - t0, t_pre)
+        return t_pre, t_s, t_asm
+
+    out = {"kind": "port", "cores": os.cpu_count(), "blas": blas,
+           "note": "Julia is absent from the image: the oracle restatement (SciPy/OpenBLAS) stands in for the reference's LAPACK path"}
+    if full_c3:
+        tp, ts, ta = run(LUSIM_C3, LUSIM_C3["dims"], LUSIM_C3["nd"], LUSIM_C3["R"])
+        out["c3"] = {"preprocess_s": tp, "of_which_assembly_s": ta, "sample_s": ts, "realizations_per_s_end_to_end": LUSIM_C3["R"] / (tp + ts),
+                     "realizations_per_s_sampling": LUSIM_C3["R"] / ts, "sample": "the full configuration (one variable, 1,000 realizations)"}
+    tp, ts, ta = run(LUSIM_C5, (128, 64), 125, 256)
+    pre_x = 2 * ((tp - ta) * 4.0 ** 3 + ta * 4.0 ** 2)
+    s_x = ts * 2 * 4.0 ** 2 * (LUSIM_C5["R"] / 256.0)
+    out["c5"] = {"preprocess_s_measured_reduced": tp, "of_which_assembly_s": ta, "sample_s_measured_reduced": ts,
+                 "preprocess_s_extrapolated": pre_x, "sample_s_extrapolated": s_x,
+                 "realizations_per_s_end_to_end": LUSIM_C5["R"] / (pre_x + s_x),
+                 "sample": "8,192 nodes + 125 data, 256 realizations, one variable; extrapolated x2 variables, factorization part x4^3 (N^3), "
+                           "assembly part x4^2 (N^2), L*W x4^2 x16 (N^2 R) to the full configuration"}
+    return out
 
 
 def main():

@@ -266,13 +266,14 @@ class LUPlan:
         return Z
 
     def sample_ensemble(self, R: int, W: Optional[np.ndarray] = None, seed: int = 0, stream: int = 0, first_real: int = 0,
-                        rho: float = math.nan, W1: Optional[np.ndarray] = None) -> "DeviceEnsemble":
-        """like `sample`, but the realizations stay on the devices"""
+                        rho: float = math.nan, W1: Optional[np.ndarray] = None, ens: Optional["DeviceEnsemble"] = None) -> "DeviceEnsemble":
+        """like `sample`, but the realizations stay on the devices (`ens`: refill an existing ensemble of the same shape)"""
         if W is not None:
             W = np.asfortranarray(W, dtype=np.float64).reshape(self.Ns, R, order="F")
         if W1 is not None:
             W1 = np.asfortranarray(W1, dtype=np.float64).reshape(self.Ns, R, order="F")
-        ens = DeviceEnsemble(self.lib, self.N, R)
+        if ens is None:
+            ens = DeviceEnsemble(self.lib, self.N, R)
         rc = self.lib.lib.gsp_lu_sample_ensemble(self.h, ens.h, _ptr(W), seed, stream, first_real, float(rho), _ptr(W1))
         self.lib.check(rc)
         return ens

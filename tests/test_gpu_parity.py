@@ -174,8 +174,9 @@ def test_lusim_golden(gpu_lib):
 
 
 def test_lusim_c3_size_properties(gpu_lib):
-    """BASELINE configs[2] at full size (16,384 nodes + 1,000 data, 1,000 realizations): the oracle needs minutes here,
-    so check properties: data honoured bit-exactly, L L' == K on sampled entries, d2 == K21 K11^-1 z1, ensemble moments."""
+    """BASELINE configs[2] at full size (16,384 nodes + 1,000 data, 1,000 realizations),
+    1,000 device-RNG realizations: data honoured bit-exactly, d2 == K21 K11^-1 z1 on probes, ensemble moments
+    (the factor itself is compared entry by entry in test_lusim_c3_full_size_oracle_parity)."""
     rng = np.random.default_rng(3)
     dims = (128, 128)
     st = iso(O.EXPONENTIAL, 1.0, 20.0, 2)
@@ -202,6 +203,92 @@ def test_lusim_c3_size_properties(gpu_lib):
     v = Z[sinds].var(axis=1, ddof=1)
     assert v.max() < 1.35 and v.min() > 0.0
     plan.close()
+
+
+def _c3_setup():
+    rng = np.random.default_rng(3)
+    dims = (128, 128)
+    st = iso(O.EXPONENTIAL, 1.0, 20.0, 2)
+    coords = O.grid_centroids(dims, [0, 0], [1, 1])
+    N, nd = 16384, 1000
+    dinds = np.sort(rng.choice(N, nd, replace=False))
+    pre0 = O.lusim_preprocess(ostructs(st), coords[dinds], np.zeros(0, dtype=np.int64), np.zeros(0), 0.0)
+    z1 = O.lusim_sample(pre0, rng.standard_normal((nd, 1)))[:, 0]
+    return rng, dims, st, coords, N, nd, dinds, z1
+
+
+def test_lusim_c3_full_size_oracle_parity(gpu_lib):
+    """BASELINE configs[2] at FULL size against the full oracle (lusim.jl:95-103,160-169): the whole L22 (15,384^2, every
+    recursion level, look-ahead stream and tile shape of the factorization), d2, and 8 injected-noise realizations at 1e-9."""
+    rng, dims, st, coords, N, nd, dinds, z1 = _c3_setup()
+    pre = O.lusim_preprocess(ostructs(st), coords, dinds, z1, 0.0)   # SciPy potrf/trsm at 16k: tens of seconds
+    plan = gsp.LUPlan(gpu_lib, st, grid_dom(dims), dinds + 1, z1, 0.0)
+    d2, L22 = plan.get()
+    assert np.all(np.triu(L22, 1) == 0.0) and L22.diagonal().min() > 0.0
+    assert relerr(d2, pre.d2) < 1e-10
+    assert relerr(L22, pre.L22) < 1e-10
+    # probe form of the same statement, independent of the oracle's own factorization:
+    # L22 (L22' v) == (C22 - C21 C11^-1 C12) v for random v
+    sinds = pre.sinds
+    C11 = O.pairwise(ostructs(st), coords[dinds])
+    C21 = O.pairwise(ostructs(st), coords[sinds], coords[dinds])
+    C22 = O.pairwise(ostructs(st), coords[sinds])
+    V = rng.standard_normal((len(sinds), 8))
+    rhs = C22 @ V - C21 @ scipy.linalg.cho_solve(scipy.linalg.cho_factor(C11), C21.T @ V)
+    lhs = L22 @ (L22.T @ V)
+    assert np.abs(lhs - rhs).max() / np.abs(rhs).max() < 1e-10
+    del C22, C21, lhs, rhs
+    R = 8
+    W = rng.standard_normal((plan.Ns, R))
+    Z = plan.sample(R, W)
+    Zo = O.lusim_sample(pre, W)
+    assert max(relerr(Z[:, r], Zo[:, r]) for r in range(R)) < TOL
+    assert np.array_equal(Z[dinds], np.repeat(z1[:, None], R, 1))
+    plan.close()
+
+
+def test_lusim_c5_full_size_oracle_parity(gpu_lib):
+    """BASELINE configs[4] at FULL size (bivariate rho = 0.7, 32,768 nodes, 500 shared data nodes) against the full oracle:
+    4 injected-noise realizations of both variables at 1e-9 (oracle.lusim_sample(pre, W2, rho, W1)), d2 and the whole L22.
+    Both marginals are the same SphericalCovariance, so the oracle factorises once and only d2 differs per variable."""
+    import dataclasses
+    rng = np.random.default_rng(5)
+    dims = (256, 128)
+    N, nd, R = 32768, 500, 4
+    C = np.array([[1.0, 0.7], [0.7, 1.0]])
+    mv = [(O.SPHERICAL, C, np.eye(3) / 20.0)]
+    coords = O.grid_centroids(dims, [0, 0], [1, 1])
+    dinds = np.sort(rng.choice(N, nd, replace=False))
+    z = [rng.standard_normal(nd) * 0.3, rng.standard_normal(nd) * 0.3]
+    rho = O.rho_mv(mv)
+    m0, m1 = O.marginalize(mv, 0), O.marginalize(mv, 1)
+    assert [(a.kind, a.sill) for a in m0] == [(a.kind, a.sill) for a in m1] and all(np.array_equal(a.A, b.A) for a, b in zip(m0, m1))
+    pre1 = O.lusim_preprocess(m0, coords, dinds, z[0], 0.0)
+    C11 = O.pairwise(m0, coords[dinds])
+    C21 = O.pairwise(m0, coords[pre1.sinds], coords[dinds])
+    pre2 = dataclasses.replace(pre1, z1=z[1], d2=C21 @ scipy.linalg.cho_solve(scipy.linalg.cho_factor(C11), z[1]))
+    del C21
+    plans = [gsp.LUPlan(gpu_lib, [(s_.kind, s_.sill, s_.A) for s_ in m], grid_dom(dims), dinds + 1, z[j], 0.0) for j, m in enumerate((m0, m1))]
+    W1, W2 = rng.standard_normal((plans[0].Ns, R)), rng.standard_normal((plans[0].Ns, R))
+    Z1 = plans[0].sample(R, W1)
+    Z2 = plans[1].sample(R, W2, rho=rho, W1=W1)
+    Zo1 = O.lusim_sample(pre1, W1)
+    Zo2 = O.lusim_sample(pre2, W2, rho, W1)
+    assert max(relerr(Z1[:, r], Zo1[:, r]) for r in range(R)) < TOL
+    assert max(relerr(Z2[:, r], Zo2[:, r]) for r in range(R)) < TOL
+    assert np.array_equal(Z1[dinds], np.repeat(z[0][:, None], R, 1)) and np.array_equal(Z2[dinds], np.repeat(z[1][:, None], R, 1))
+    d2a = np.empty(plans[1].Ns)
+    plans[1].lib.check(plans[1].lib.lib.gsp_lu_plan_get(plans[1].h, d2a.ctypes.data, None))
+    assert relerr(d2a, pre2.d2) < 1e-9
+    plans[1].close()
+    d2, L22 = plans[0].get()
+    assert relerr(d2, pre1.d2) < 1e-9
+    assert np.all(np.triu(L22, 1) == 0.0)
+    err = 0.0
+    for c0 in range(0, L22.shape[1], 2048):   # blockwise: no second 8 GB temporary
+        err = max(err, float(np.abs(L22[:, c0:c0 + 2048] - pre1.L22[:, c0:c0 + 2048]).max()))
+    assert err / np.abs(pre1.L22).max() < 1e-10
+    plans[0].close()
 
 
 def test_lusim_host_pipeline_matches_device_path(gpu_lib):

@@ -2,6 +2,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 
 #include "chol.h"
@@ -193,6 +194,7 @@ extern "C" int gsp_ctx_create(int32_t ndev, const int32_t* devs, gsp_ctx** out) 
 #endif
     if (e == cudaSuccess) e = cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&dc.stream, cudaStreamNonBlocking, prio_hi);
+    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&dc.aux, cudaStreamNonBlocking, prio_hi);
     for (int k = 0; k < DevCtx::kSide && e == cudaSuccess; ++k) e = cudaStreamCreateWithPriority(&dc.side[k], cudaStreamNonBlocking, prio_lo);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&dc.h2d, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&dc.d2h, cudaStreamNonBlocking);
@@ -345,9 +347,16 @@ extern "C" int gsp_potrf(gsp_ctx* ctx, int64_t n, double* A) {
     else pad[(size_t)j * np + j] = 1.0;
   }
   GSP_CUDA_OK(ctx, cudaMemcpyAsync(dA.p, pad.data(), pad.size() * sizeof(double), cudaMemcpyHostToDevice, dc.stream));
-  DevBuf work;
-  if (chol_work_doubles(nb) > 0) GSP_CUDA_OK(ctx, work.alloc(dc.dev, chol_work_doubles(nb) * sizeof(double)));
-  GSP_CUDA_OK(ctx, chol_factor(dc.stream, dc.side, DevCtx::kSide, dA.as<double>(), np, nb, dinv.as<double>(), dinfo.as<int>(), work.as<double>()));
+  const char* algo = getenv("GSP_CHOL_ALGO");
+  if (algo && algo[0] == 'p') {  // the panel algorithm of the distributed factorization, on this one device
+    DevBuf rows;
+    GSP_CUDA_OK(ctx, rows.alloc(dc.dev, (size_t)nb * sizeof(int)));
+    const int pb_env = getenv("GSP_CHOL_PB") ? atoi(getenv("GSP_CHOL_PB")) : 0;
+    std::vector<DistDev> dv{DistDev{dc.dev, dc.stream, dc.aux, dc.side[0], dA.as<double>(), dinv.as<double>(), dinfo.as<int>(), rows.as<int>()}};
+    GSP_CUDA_OK(ctx, chol_factor_dist(dv, np, nb, std::min(nb, pb_env > 0 ? pb_env : 4)));
+  } else {
+    GSP_CUDA_OK(ctx, chol_factor(dc.stream, dc.side, DevCtx::kSide, dA.as<double>(), np, nb, dinv.as<double>(), dinfo.as<int>()));
+  }
   int info = 0;
   GSP_CUDA_OK(ctx, cudaMemcpyAsync(&info, dinfo.p, sizeof(int), cudaMemcpyDeviceToHost, dc.stream));
   GSP_CUDA_OK(ctx, cudaMemcpyAsync(pad.data(), dA.p, pad.size() * sizeof(double), cudaMemcpyDeviceToHost, dc.stream));

@@ -13,9 +13,12 @@ constexpr int AT = 64;  // tile edge
 // nullptr = identity map.  lower_only: skip tiles strictly above the diagonal.
 __global__ void __launch_bounds__(256) assemble_kernel(CovDev m, DomDev drow, DomDev dcol, const long long* __restrict__ rowmap,
                                                        const long long* __restrict__ colmap, long long nrow, long long ncol,
-                                                       double* __restrict__ out, long long ld, int lower_only, int vec_ok) {
+                                                       double* __restrict__ out, long long ld, int lower_only, int vec_ok,
+                                                       long long row_base) {
+  // row_base: global index of matrix row 0 of this launch (a device assembling only a band of rows passes rowmap / out already
+  // offset to the band); it only enters the "is this the diagonal" decisions
   const long long r0 = (long long)blockIdx.x * AT, c0 = (long long)blockIdx.y * AT;
-  if (lower_only && r0 + AT <= c0) return;
+  if (lower_only && row_base + r0 + AT <= c0) return;
   __shared__ double xr[3][AT], xc[3][AT];
   __shared__ int padr[AT], padc[AT];
   const int tid = threadIdx.x;
@@ -48,7 +51,7 @@ __global__ void __launch_bounds__(256) assemble_kernel(CovDev m, DomDev drow, Do
     for (int i = 0; i < 4; ++i) {
       const long long p = r0 + lr + i;
       if (padr[lr + i] || padc[lc])
-        v[i] = (p == q) ? 1.0 : 0.0;
+        v[i] = (row_base + p == q) ? 1.0 : 0.0;
       else
         v[i] = cov_eval(m, xr[0][lr + i] - xc[0][lc], xr[1][lr + i] - xc[1][lc], xr[2][lr + i] - xc[2][lc]);
     }
@@ -65,12 +68,12 @@ __global__ void __launch_bounds__(256) assemble_kernel(CovDev m, DomDev drow, Do
 }
 
 void launch_assemble(cudaStream_t st, const CovDev& m, const DomDev& drow, const DomDev& dcol, const long long* rowmap,
-                     const long long* colmap, long long nrow, long long ncol, double* out, long long ld, bool lower_only) {
+                     const long long* colmap, long long nrow, long long ncol, double* out, long long ld, bool lower_only, long long row_base) {
   dim3 grid((unsigned)((nrow + AT - 1) / AT), (unsigned)((ncol + AT - 1) / AT));
   int vec_ok = (ld % 2 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
   ProfScope prof_("assemble", st);
   GSP_LAUNCH(assemble_kernel, grid, dim3(256), 0, st, m, drow, dcol, rowmap, colmap, nrow, ncol, out, ld, lower_only ? 1 : 0,
-             vec_ok);
+             vec_ok, row_base);
   g_launches++;
 }
 

@@ -5,6 +5,7 @@
 // triangular solve becomes a tile GEMM with the explicit inverse.
 #include "chol.h"
 
+#include <algorithm>
 #include <cstdlib>
 #include <vector>
 
@@ -82,8 +83,7 @@ GSP_DEV double frag_b(const double* S, int k0, int c0, int lane) { return S[(c0 
 // (S) rows below = panel * inv(L16)^T.  The inverse of the whole block is then assembled from the eight 16x16 inverses by
 // X21 = -inv(C) * B * inv(A) over 16 -> 32 -> 64 wide halves, again on DMMA tiles (one 8-row block per warp and level).
 __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(double* __restrict__ A, long long lda, long long blk,
-                                                            double* __restrict__ invD, int* __restrict__ info,
-                                                            double* __restrict__ inv2, long long ld2) {
+                                                            double* __restrict__ invD, int* __restrict__ info, const GSP_GRID_CONSTANT DiagPeers peers) {
   GSP_DYN_SMEM(smem);
   double* S = reinterpret_cast<double*>(smem);   // [DB cols][DLD]
   double* Dv = S + DB * DLD;                     // [8 panels][16 k][DVL]: Dv[p][k * DVL + n] = inv(L16_p)[n][k]
@@ -187,10 +187,12 @@ __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(double* __restrict__
     __syncthreads();
   }
 
-  // write L (upper triangle explicitly zero)
+  // write L (upper triangle explicitly zero), also into the other devices' matrices (distributed factorization)
   for (int idx = tid; idx < DB * DB; idx += 256) {
     const int r = idx & (DB - 1), c = idx >> 7;
-    Ab[r + (long long)c * lda] = (r >= c) ? S[c * DLD + r] : 0.0;
+    const double v = (r >= c) ? S[c * DLD + r] : 0.0;
+    Ab[r + (long long)c * lda] = v;
+    for (int p = 0; p < peers.n; ++p) peers.A[p][blk * DB * (lda + 1) + r + (long long)c * lda] = v;
   }
   __syncthreads();
 
@@ -259,7 +261,7 @@ __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(double* __restrict__
     const int r = idx & (DB - 1), c = idx >> 7;
     const double v = (r >= c) ? S[c * DLD + r] : 0.0;
     Xo[r + c * DB] = v;
-    if (inv2) inv2[r + c * ld2] = v;  // second copy on the diagonal of the panel-inverse workspace (chol_factor)
+    for (int p = 0; p < peers.n; ++p) peers.invD[p][blk * DB * DB + r + c * DB] = v;
   }
 }
 
@@ -312,7 +314,7 @@ namespace {
 
 struct Chol {
   cudaStream_t st;       // main (high priority): diagonal blocks, panels, leading part of every update
-  cudaStream_t* side;    // look-ahead streams, one per recursion depth
+  cudaStream_t* side;    // look-ahead streams, one per recursion depth (recursive single-device algorithm)
   int nside;
   double* A;
   long long ld;
@@ -321,44 +323,7 @@ struct Chol {
   cudaError_t err = cudaSuccess;
   std::vector<cudaEvent_t> events;
   int side_ctas = 0;  // > 0: look-ahead GEMMs run as persistent grids of this many CTAs, the other SMs stay free for the main stream
-  // panel inverses (chol_factor with a workspace): group g = blocks [8g, 8g + 8) owns a dense 1024 x 1024 slot; the inverse of an
-  // aligned s-block panel (s = 1, 2, 4, 8) is the s*128-square sub-matrix on the slot's diagonal (ld = PIL).  built[k] marks the
-  // panels of size 2^k that are complete.
-  static constexpr int PIG = 8;
-  static constexpr long long PIL = (long long)PIG * DB;
-  double* linv = nullptr;
-  double* tmp = nullptr;   // (PIG/2 * 128)^2 scratch of the level builds
-  double* xbuf = nullptr;  // nb_total x PIG blocks: result of a panel solve before it is copied over the panel
-  int nb_total = 0;
-  std::vector<unsigned char> built[4];
-
-  double* linv_at(int blk_row, int blk_col) const {  // both inside the same 8-group
-    const int grp = blk_row / PIG;
-    return linv + (long long)grp * PIL * PIL + (long long)(blk_row % PIG) * DB + (long long)(blk_col % PIG) * DB * PIL;
-  }
-  static int lg2(int s) { return s == 1 ? 0 : (s == 2 ? 1 : (s == 4 ? 2 : (s == 8 ? 3 : -1))); }
-  bool panel_ready(int c0, int nc) const {
-    const int k = lg2(nc);
-    return linv && k >= 0 && c0 % nc == 0 && (size_t)(c0 / nc) < built[k].size() && built[k][c0 / nc];
-  }
-  // inverse of the aligned s-block panel at o from its two halves: X21 = -inv(C) * (B * inv(A))
-  void build_panel_inverse(int o, int s) {
-    const int k = lg2(s), h = s / 2;
-    if (!linv || k < 1 || o % s != 0 || !panel_ready(o, h) || !panel_ready(o + h, h)) return;
-    GemmArgs g{};
-    g.A = at(o + h, o); g.lda = ld;
-    g.B = linv_at(o, o); g.ldb = PIL;            // K x N: inv(A)[k][j]
-    g.C = tmp; g.ldc = (long long)h * DB;
-    g.mt = h; g.nt = h; g.K = h * DB;
-    check(launch_gemm<GEMM_SET, true>(st, g));
-    GemmArgs g2{};
-    g2.A = linv_at(o + h, o + h); g2.lda = PIL;  // inv(C)
-    g2.B = tmp; g2.ldb = (long long)h * DB;      // K x N: T
-    g2.C = linv_at(o + h, o); g2.ldc = PIL;      // zero on entry (workspace cleared by chol_factor)
-    g2.mt = h; g2.nt = h; g2.K = h * DB;
-    check(launch_gemm<GEMM_SUB, true>(st, g2));
-    built[k][o / s] = 1;
-  }
+  DiagPeers peers{};  // distributed factorization: the other devices' matrices / inverse arrays (final blocks are multicast there)
 
   double* at(int br, int bc) const { return A + (long long)br * DB + (long long)bc * DB * ld; }
 
@@ -372,51 +337,33 @@ struct Chol {
     events.push_back(ev);
     return ev;
   }
-
-  // C[mt x nt blocks at (cr, cc)] -= A[(ar, ac), K blocks] * B[(br, bc), K blocks]^T   (lower tiles only if tri)
-  // On a look-ahead stream the K range is cut into slices so that no CTA holds an SM for long:
-  // pending high-priority CTAs of the main stream then get an SM within one slice.
-  void update(cudaStream_t s, bool sliced, int cr, int cc, int mt, int nt, int ar, int ac, int br, int bc, int kb, bool tri) {
-    if (mt <= 0 || nt <= 0 || kb <= 0) return;
-    static int slice = -1;  // GSP_CHOL_SLICE: K blocks per launch on look-ahead streams
-    if (slice < 0) {
-      const char* env = getenv("GSP_CHOL_SLICE");
-      slice = env ? atoi(env) : 0;  // default: no slicing (measured best on B200: 70.4 ms vs 73.1 ms at C3)
-      if (slice < 1) slice = 1 << 20;
-    }
-    const int step = sliced ? slice : kb;
-    for (int k0 = 0; k0 < kb; k0 += step) {
-      const int kk = (kb - k0 < step) ? kb - k0 : step;
-      GemmArgs g{};
-      g.A = at(ar, ac + k0); g.lda = ld;
-      g.B = at(br, bc + k0); g.ldb = ld;
-      g.C = at(cr, cc); g.ldc = ld;
-      g.mt = mt; g.nt = nt; g.K = kk * DB; g.tri = tri ? 1 : 0;
-      g.max_ctas = sliced ? side_ctas : 0;
-      check(launch_gemm<GEMM_SUB, false>(s, g));
-    }
+  void set_peers(GemmArgs& g, long long off) const {
+    g.npeer = peers.n;
+    for (int p = 0; p < peers.n; ++p) g.Cpeer[p] = peers.A[p] + off;
   }
 
-  // X * L[c0:c0+nc, c0:c0+nc]^T = A[r0:r0+nr, c0:c0+nc]   (in place)
+  // C[mt x nt blocks at (cr, cc)] -= A[(ar, ac), K blocks] * B[(br, bc), K blocks]^T   (lower tiles only if tri)
+  void update(cudaStream_t s, bool side_grid, int cr, int cc, int mt, int nt, int ar, int ac, int br, int bc, int kb, bool tri) {
+    if (mt <= 0 || nt <= 0 || kb <= 0) return;
+    GemmArgs g{};
+    g.A = at(ar, ac); g.lda = ld;
+    g.B = at(br, bc); g.ldb = ld;
+    g.C = at(cr, cc); g.ldc = ld;
+    g.mt = mt; g.nt = nt; g.K = kb * DB; g.tri = tri ? 1 : 0;
+    g.max_ctas = side_grid ? side_ctas : 0;
+    check(launch_gemm<GEMM_SUB, false>(s, g));
+  }
+
+  // X * L[c0:c0+nc, c0:c0+nc]^T = A[r0:r0+nr, c0:c0+nc]   (in place; the leaves multiply by the explicit inverses of the diagonal blocks)
   void trsm(int r0, int nr, int c0, int nc) {
     if (nr <= 0 || nc <= 0) return;
-    if (nc > 1 && panel_ready(c0, nc)) {
-      GemmArgs g{};
-      g.A = at(r0, c0); g.lda = ld;
-      g.B = linv_at(c0, c0); g.ldb = PIL;   // N x K: inv(L)[j][k], lower triangular
-      g.C = xbuf; g.ldc = (long long)nr * DB;
-      g.mt = nr; g.nt = nc; g.K = nc * DB; g.strip = 1;
-      check(launch_gemm<GEMM_SET, false>(st, g));
-      check(cudaMemcpy2DAsync(at(r0, c0), (size_t)ld * sizeof(double), xbuf, (size_t)nr * DB * sizeof(double), (size_t)nr * DB * sizeof(double),
-                              (size_t)nc * DB, cudaMemcpyDeviceToDevice, st));
-      return;
-    }
     if (nc == 1) {
       GemmArgs g{};
       g.A = at(r0, c0); g.lda = ld;
       g.B = invD + (long long)c0 * DB * DB; g.ldb = DB;
       g.C = at(r0, c0); g.ldc = ld;
       g.mt = nr; g.nt = 1; g.K = DB;
+      set_peers(g, (long long)r0 * DB + (long long)c0 * DB * ld);
       check(launch_gemm<GEMM_SET, false>(st, g));
       return;
     }
@@ -424,6 +371,38 @@ struct Chol {
     trsm(r0, nr, c0, c1);
     update(st, false, r0, c0 + c1, nr, nc - c1, r0, c0, c0 + c1, c0, c1, false);
     trsm(r0, nr, c0 + c1, nc - c1);
+  }
+
+  // ---- the same two operations on a LIST of block rows (distributed factorization: the rows this device owns below a panel).
+  // rows_dev: device array of nrows ascending block-row indices.
+  // C[rows, ccol0 + j] -= A[rows, kcol0 : kcol0 + kb) * L[ccol0 + j, kcol0 : kcol0 + kb)^T,  j < ncolblk; stair: only j with ccol0 + j <= row
+  void update_rows(cudaStream_t s, const int* rows_dev, int nrows, long long valid_tiles, int ccol0, int ncolblk, int kcol0, int kb, bool stair) {
+    if (nrows <= 0 || ncolblk <= 0 || kb <= 0 || valid_tiles <= 0) return;
+    GemmArgs g{};
+    g.A = A + (long long)kcol0 * DB * ld; g.lda = ld;
+    g.B = at(ccol0, kcol0); g.ldb = ld;
+    g.C = A + (long long)ccol0 * DB * ld; g.ldc = ld;
+    g.mt = nrows; g.nt = ncolblk; g.K = kb * DB;
+    g.rows = rows_dev; g.stair = stair ? 1 : 0; g.colblk0 = ccol0;
+    check(launch_gemm<GEMM_SUB, false>(s, g, valid_tiles));
+  }
+  void trsm_rows(cudaStream_t s, const int* rows_dev, int nrows, int c0, int nc) {
+    if (nrows <= 0 || nc <= 0) return;
+    if (nc == 1) {
+      GemmArgs g{};
+      g.A = A + (long long)c0 * DB * ld; g.lda = ld;
+      g.B = invD + (long long)c0 * DB * DB; g.ldb = DB;
+      g.C = A + (long long)c0 * DB * ld; g.ldc = ld;
+      g.mt = nrows; g.nt = 1; g.K = DB;
+      g.rows = rows_dev;
+      set_peers(g, (long long)c0 * DB * ld);
+      check(launch_gemm<GEMM_SET, false>(s, g));
+      return;
+    }
+    const int c1 = nc / 2;
+    trsm_rows(s, rows_dev, nrows, c0, c1);
+    update_rows(s, rows_dev, nrows, (long long)nrows * (nc - c1), c0 + c1, nc - c1, c0, c1, false);
+    trsm_rows(s, rows_dev, nrows, c0 + c1, nc - c1);
   }
 
   // Cholesky of the n diagonal blocks starting at o.  `pend`: event after which the second half [o + n/2, o + n) of the
@@ -434,11 +413,9 @@ struct Chol {
       auto kfn = potrf_diag_kernel;
       check(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM));
       ProfScope prof_("potrf_diag", st);
-      double* inv2 = linv ? linv_at(o, o) : nullptr;
-      GSP_LAUNCH(kfn, dim3(1), dim3(256), (size_t)DIAG_SMEM, st, A, ld, (long long)o, invD, info, inv2, PIL);
+      GSP_LAUNCH(kfn, dim3(1), dim3(256), (size_t)DIAG_SMEM, st, A, ld, (long long)o, invD, info, peers);
       g_launches++;
       check(cudaGetLastError());
-      if (linv) built[0][o] = 1;
       return;
     }
     const int n1 = n / 2, n2 = n - n1;
@@ -449,7 +426,6 @@ struct Chol {
     if (n2 == 1 || depth >= nside || n < 8) {
       update(st, false, p, p, n2, n2, p, o, p, o, n1, true);
       potrf(p, n2, nullptr, depth + 1);
-      if (n <= PIG) build_panel_inverse(o, n);
       return;
     }
     // look-ahead: the leading half of A22 (what the next level factors first) is updated on the main stream,
@@ -463,62 +439,25 @@ struct Chol {
     update(sd, true, p + m1, p + m1, m2, m2, p + m1, o, p + m1, o, n1, true);
     cudaEvent_t rest_done = record(sd);
     potrf(p, n2, rest_done, depth + 1);
-    if (n <= PIG) build_panel_inverse(o, n);
   }
 };
 
+int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
 }  // namespace
 
-// GSP_CHOL_PANELS=1 turns the panel-inverse solves on.  Measured on the B200 (session 3): C3 factorization 70.0 ms against 64.7 ms for
-// the recursive solves, 32k nodes 387 against 384 ms (an in-place variant, one CTA per 64-row strip walking the column tiles right to
-// left, was worse still: 73.9 ms) - the recursion's many small launches run back to back and spread over more CTAs than one
-// triangular-K GEMM per panel, so the saved launches buy nothing.  Off by default.
-static bool chol_panels_enabled() {
-  static int use_panels = -1;
-  if (use_panels < 0) {
-    const char* env = getenv("GSP_CHOL_PANELS");
-    use_panels = (env && env[0] == '1') ? 1 : 0;
-  }
-  return use_panels != 0;
-}
-
-size_t chol_work_doubles(int nblocks) {
-  if (!chol_panels_enabled()) return 0;
-  const size_t groups = (size_t)(nblocks + Chol::PIG - 1) / Chol::PIG;
-  return groups * (size_t)Chol::PIL * Chol::PIL + (size_t)(Chol::PIG / 2 * DB) * (Chol::PIG / 2 * DB) +
-         (size_t)nblocks * DB * Chol::PIL;
-}
-
-cudaError_t chol_factor(cudaStream_t st, cudaStream_t* side, int nside, double* A, long long ld, int nblocks, double* invD, int* info,
-                        double* work) {
+cudaError_t chol_factor(cudaStream_t st, cudaStream_t* side, int nside, double* A, long long ld, int nblocks, double* invD, int* info) {
   Chol c{st, side, nside, A, ld, invD, info};
   cudaError_t e = cudaMemsetAsync(info, 0, sizeof(int), st);
   if (e != cudaSuccess) return e;
-  if (work && chol_panels_enabled() && nblocks >= 4) {
-    const size_t groups = (size_t)(nblocks + Chol::PIG - 1) / Chol::PIG;
-    c.linv = work;
-    c.tmp = work + groups * (size_t)Chol::PIL * Chol::PIL;
-    c.xbuf = c.tmp + (size_t)(Chol::PIG / 2 * DB) * (Chol::PIG / 2 * DB);
-    c.nb_total = nblocks;
-    for (int k = 0; k < 4; ++k) c.built[k].assign((size_t)(nblocks >> k) + 1, 0);
-    // the level builds and the strip kernels read whole tiles of the (triangular) inverses: everything not written must be zero
-    e = cudaMemsetAsync(work, 0, groups * (size_t)Chol::PIL * Chol::PIL * sizeof(double), st);
-    if (e != cudaSuccess) return e;
-  }
-  static int lookahead = -1;  // GSP_CHOL_LOOKAHEAD=0 disables the side streams (A/B measurements)
-  if (lookahead < 0) {
-    const char* env = getenv("GSP_CHOL_LOOKAHEAD");
-    lookahead = (env && env[0] == '0') ? 0 : 1;
-  }
+  static const int lookahead = env_int("GSP_CHOL_LOOKAHEAD", 1);  // 0 disables the side streams (A/B measurements)
   if (!lookahead) c.nside = 0;
   // GSP_CHOL_RESERVE=r: SMs kept free of look-ahead work.  A one-CTA-per-tile look-ahead GEMM fills every SM for the length of
   // a tile (1.2 ms at K = 8192), and the short kernels of the critical path queue behind it whatever their stream priority.
-  static int reserve = -1;
-  if (reserve < 0) {
-    const char* env = getenv("GSP_CHOL_RESERVE");
-    reserve = env ? atoi(env) : GSP_CHOL_RESERVE_DEFAULT;
-    if (reserve < 0) reserve = 0;
-  }
+  static const int reserve = std::max(0, env_int("GSP_CHOL_RESERVE", GSP_CHOL_RESERVE_DEFAULT));
   if (reserve > 0) {
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
@@ -526,45 +465,61 @@ cudaError_t chol_factor(cudaStream_t st, cudaStream_t* side, int nside, double* 
     c.side_ctas = sms - reserve > 8 ? sms - reserve : 8;
   }
   c.potrf(0, nblocks, nullptr, 0);
-  // every side stream was joined into `st` by the events waited on above, except possibly none: nothing left pending
   for (cudaEvent_t ev : c.events) cudaEventDestroy(ev);
   return c.err;
 }
 
-// ------------------------------------------------------------------ multi-GPU factorization
-// 1-D block-cyclic panels of PB 128-blocks over the G devices of a context, every device holding the full
-// matrix buffer.  Step q: owner(q) = q mod G factors panel q (diagonal potrf + TRSM of the rows below), the
-// panel is pushed device-to-device (cudaMemcpy2DAsync over NVLink peer access) INTO THE SAME POSITION of every
-// other device's matrix, and every device applies it to the panels it owns.  Look-ahead: the owner of
-// panel q+1 updates that panel first on its main stream, factors it and starts the next broadcast while the
-// bulk updates of step q still run on the update streams.  Because panels land in place, every device ends
-// with the complete factor L: the all-gather needed for the realization-sharded sampling is free.
-cudaError_t chol_factor_mg(const std::vector<MgDev>& devs, long long ld, int nblocks, int PB) {
+// ------------------------------------------------------------------ distributed (and single-device panel) factorization
+// Right-looking over column panels of PB 128-blocks with ROW-PANEL ownership: block rows [p PB, (p+1) PB) belong to device
+// owner(p) (boustrophedon over the G devices: 0..G-1, G-1..0, ... - the work of a row grows with its index, the snake keeps every
+// device's share within a panel of the mean).  Every device holds a full-size buffer but assembles and updates ONLY its own rows;
+// finished blocks are written straight into the same position of every other device's buffer from the epilogue of the kernel
+// that produces them (peer-mapped stores over NVLink: potrf_diag_kernel and the TRSM leaf GEMM), so when the last panel is done
+// every device holds the whole factor L - exactly what the realization-sharded sampling needs - without a separate broadcast.
+// Step q (column panel q, owner o = owner(q)):
+//   D(q)  on o:   Cholesky of the PB x PB diagonal square (needs only o's own rows), square + block inverses multicast
+//   T(q)  on all: each device solves ITS rows below the square against it and multicasts them          [main stream]
+//   LA(q) on all: own rows x column panel q+1 updated with panel q (owner(q+1): its diagonal square first, then D(q+1)) [main / aux]
+//   B(q)  on all: own rows x columns of panels >= q+2 (below the diagonal) updated with panel q        [low-priority stream]
+// Nothing on the critical path D -> T -> LA -> D is done by one device for the others except the PB-square itself: the panel
+// solve and the look-ahead update are split G ways by construction, and the wide update B(q) (one launch of short, K = PB*128
+// tiles on a low-priority stream) is pre-empted at tile granularity by the chain kernels of the high-priority streams.
+static int dist_owner(int p, int G) {
+  const int m = p % (2 * G);
+  return m < G ? m : 2 * G - 1 - m;
+}
+
+void chol_dist_owned_rows(int nblocks, int PB, int G, int g, std::vector<int>* rows) {
+  rows->clear();
+  const int Q = (nblocks + PB - 1) / PB;
+  for (int p = 0; p < Q; ++p)
+    if (dist_owner(p, G) == g)
+      for (int b = p * PB; b < std::min(nblocks, (p + 1) * PB); ++b) rows->push_back(b);
+}
+
+cudaError_t chol_factor_dist(const std::vector<DistDev>& devs, long long ld, int nblocks, int PB) {
   const int G = (int)devs.size();
   const int Q = (nblocks + PB - 1) / PB;
   cudaError_t err = cudaSuccess;
   auto check = [&](cudaError_t e) {
     if (err == cudaSuccess && e != cudaSuccess) err = e;
   };
-  // GSP_CHOL_MG_RESERVE=r: the bulk updates on the update streams run as persistent grids that leave r SMs to the main stream, where the
-  // next panel is updated, factored and sent (see chol_factor's GSP_CHOL_RESERVE)
-  static int mg_reserve = -1;
-  if (mg_reserve < 0) {
-    const char* env = getenv("GSP_CHOL_MG_RESERVE");
-    mg_reserve = env ? atoi(env) : GSP_CHOL_MG_RESERVE_DEFAULT;
-    if (mg_reserve < 0) mg_reserve = 0;
-  }
   std::vector<Chol> ch;
   ch.reserve(G);
+  std::vector<std::vector<int>> rows(G);
   for (int g = 0; g < G; ++g) {
     check(cudaSetDevice(devs[g].dev));
     ch.push_back(Chol{devs[g].main, nullptr, 0, devs[g].A, ld, devs[g].invD, devs[g].info});
-    if (mg_reserve > 0) {
-      int sms = 0;
-      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, devs[g].dev);
-      ch.back().side_ctas = sms - mg_reserve > 8 ? sms - mg_reserve : 8;
-    }
+    for (int h = 0; h < G; ++h)
+      if (h != g) {
+        ch[g].peers.A[ch[g].peers.n] = devs[h].A;
+        ch[g].peers.invD[ch[g].peers.n] = devs[h].invD;
+        ch[g].peers.n++;
+      }
     check(cudaMemsetAsync(devs[g].info, 0, sizeof(int), devs[g].main));
+    chol_dist_owned_rows(nblocks, PB, G, g, &rows[g]);
+    if (!rows[g].empty())
+      check(cudaMemcpyAsync(devs[g].rows, rows[g].data(), rows[g].size() * sizeof(int), cudaMemcpyHostToDevice, devs[g].main));
   }
   std::vector<cudaEvent_t> evs;
   auto record = [&](int g, cudaStream_t s) {
@@ -575,76 +530,84 @@ cudaError_t chol_factor_mg(const std::vector<MgDev>& devs, long long ld, int nbl
     evs.push_back(ev);
     return ev;
   };
-  std::vector<cudaEvent_t> upd_done(G, nullptr);   // last event of device g's update stream
-  std::vector<cudaEvent_t> have(G, nullptr);       // panel q is present on device g (factored there or received)
-  const size_t esz = sizeof(double);
+  // index of the first own row >= block b, per device
+  auto first_at = [&](int g, int b) { return (int)(std::lower_bound(rows[g].begin(), rows[g].end(), b) - rows[g].begin()); };
+  // tiles (own row r, column block c) with c0 <= c < c1 and c <= r
+  auto stair_tiles = [&](int g, int i0, int c0, int c1) {
+    long long t = 0;
+    for (size_t i = (size_t)i0; i < rows[g].size(); ++i) t += std::max(0, std::min(c1, rows[g][i] + 1) - c0);
+    return t;
+  };
+  std::vector<cudaEvent_t> evT(G, nullptr), evBulk(G, nullptr), evLA(G, nullptr);
+  cudaEvent_t evD = nullptr;
   for (int q = 0; q < Q && err == cudaSuccess; ++q) {
-    const int o = q % G;
-    const int r0 = q * PB;
-    const int nq = (nblocks - r0 < PB) ? nblocks - r0 : PB;
-    const int below = nblocks - r0 - nq;
-    // ---- factor panel q on its owner.  No extra wait: the panel's last update (by panel q-1) ran on this main stream as
-    // the look-ahead update of step q-1, and that update already waited for the update stream's earlier work on the panel;
-    // the bulk updates of step q-1 touch other panels and keep running underneath.
+    const int o = dist_owner(q, G);
+    const int c0 = q * PB;
+    const int nq = std::min(PB, nblocks - c0);
+    const int cn = c0 + nq;  // first block below / right of the panel
+    // ---- D(q): the diagonal square on its owner.  It is up to date: LA(q-1) updated it on this stream.
     check(cudaSetDevice(devs[o].dev));
-    ch[o].potrf(r0, nq, nullptr, 0);
-    ch[o].trsm(r0 + nq, below, r0, nq);
+    ch[o].potrf(c0, nq, nullptr, 0);
     check(ch[o].err);
-    cudaEvent_t ready = record(o, devs[o].main);
-    // ---- broadcast: rows >= r0*128 of the panel's columns, plus the inverses of its diagonal blocks
+    evD = (G > 1) ? record(o, devs[o].main) : nullptr;
+    if (cn >= nblocks) break;
+    // ---- T(q): every device solves its own rows below the square (and multicasts them)
     for (int g = 0; g < G; ++g) {
-      if (g == o) {
-        have[g] = ready;
-        continue;
-      }
+      const int i0 = first_at(g, cn), m = (int)rows[g].size() - i0;
       check(cudaSetDevice(devs[g].dev));
-      check(cudaStreamWaitEvent(devs[g].copy, ready, 0));
-      const size_t off = (size_t)r0 * DB * (size_t)(ld + 1);
-      check(cudaMemcpy2DAsync(devs[g].A + off, (size_t)ld * esz, devs[o].A + off, (size_t)ld * esz, (size_t)(nblocks - r0) * DB * esz,
-                              (size_t)nq * DB, cudaMemcpyDefault, devs[g].copy));
-      check(cudaMemcpyAsync(devs[g].invD + (size_t)r0 * DB * DB, devs[o].invD + (size_t)r0 * DB * DB, (size_t)nq * DB * DB * esz,
-                            cudaMemcpyDefault, devs[g].copy));
-      have[g] = record(g, devs[g].copy);
+      if (g != o && evD) check(cudaStreamWaitEvent(devs[g].main, evD, 0));
+      if (evLA[g]) check(cudaStreamWaitEvent(devs[g].main, evLA[g], 0));  // the rest of LA(q-1) ran on the aux stream
+      evLA[g] = nullptr;
+      ch[g].trsm_rows(devs[g].main, devs[g].rows + i0, m, c0, nq);
+      check(ch[g].err);
+      evT[g] = record(g, devs[g].main);
     }
-    if (below <= 0) break;
-    // ---- trailing updates with panel q on every device, for the panels it owns
+    // ---- LA(q) and B(q)
+    const int o1 = (q + 1 < Q) ? dist_owner(q + 1, G) : -1;
+    const int n1 = std::min(PB, nblocks - cn);  // width of panel q+1
     for (int g = 0; g < G; ++g) {
       check(cudaSetDevice(devs[g].dev));
-      bool any_upd = false;
-      for (int q2 = q + 1; q2 < Q; ++q2) {
-        if (q2 % G != g) continue;
-        const int c0 = q2 * PB;
-        const int n2 = (nblocks - c0 < PB) ? nblocks - c0 : PB;
-        const bool lookahead = (q2 == q + 1);
-        cudaStream_t s = lookahead ? devs[g].main : devs[g].upd;
-        if (lookahead) {
-          check(cudaStreamWaitEvent(s, have[g], 0));
-          if (upd_done[g]) check(cudaStreamWaitEvent(s, upd_done[g], 0));
-        } else if (!any_upd) {
-          check(cudaStreamWaitEvent(s, have[g], 0));
-          any_upd = true;
-        }
-        ch[g].st = s;  // Chol::update launches on the stream it is given; keep st consistent for error paths
-        ch[g].update(s, !lookahead, c0, c0, nblocks - c0, n2, c0, r0, c0, r0, nq, false);
-        ch[g].st = devs[g].main;
-        check(ch[g].err);
+      const int i0 = first_at(g, cn);
+      const int m = (int)rows[g].size() - i0;
+      if (m <= 0) continue;
+      // LA needs the rows of panel q+1 in panel q (solved by o1) and everything B(q-1) did to column panel q+1
+      cudaStream_t sm = devs[g].main, sa = devs[g].aux;
+      if (g != o1 && G > 1) check(cudaStreamWaitEvent(sm, evT[o1], 0));
+      if (evBulk[g]) check(cudaStreamWaitEvent(sm, evBulk[g], 0));
+      int ia = i0;  // own rows from here on are updated on the aux stream
+      if (g == o1) {
+        // the square of panel q+1 first, on the main stream: D(q+1) follows immediately
+        ia = first_at(g, cn + n1);
+        ch[g].update_rows(sm, devs[g].rows + i0, ia - i0, stair_tiles(g, i0, cn, cn + n1) - stair_tiles(g, ia, cn, cn + n1), cn, n1, c0, nq, true);
       }
-      if (any_upd) upd_done[g] = record(g, devs[g].upd);
+      if ((int)rows[g].size() - ia > 0) {
+        cudaEvent_t e = record(g, sm);
+        check(cudaStreamWaitEvent(sa, e, 0));
+        ch[g].update_rows(sa, devs[g].rows + ia, (int)rows[g].size() - ia, stair_tiles(g, ia, cn, cn + n1), cn, n1, c0, nq, true);
+        evLA[g] = record(g, sa);
+      }
+      // B(q): columns of the panels >= q+2, needs every device's rows of panel q
+      if (cn + n1 < nblocks) {
+        cudaStream_t su = devs[g].upd;
+        for (int h = 0; h < G; ++h) check(cudaStreamWaitEvent(su, evT[h], 0));
+        const int ib = first_at(g, cn + n1);
+        ch[g].update_rows(su, devs[g].rows + ib, (int)rows[g].size() - ib, stair_tiles(g, ib, cn + n1, nblocks), cn + n1, nblocks - cn - n1, c0, nq,
+                          true);
+        evBulk[g] = record(g, su);
+      }
+      check(ch[g].err);
     }
   }
-  // join: every stream of every device has finished before the caller continues on the main streams
-  for (int g = 0; g < G; ++g) {
-    check(cudaSetDevice(devs[g].dev));
-    if (upd_done[g]) check(cudaStreamWaitEvent(devs[g].main, upd_done[g], 0));
-    if (have[g]) check(cudaStreamWaitEvent(devs[g].main, have[g], 0));
-  }
+  // join: every stream of every device has finished (and every peer store has landed) before the caller continues
   for (int g = 0; g < G; ++g) {
     check(cudaSetDevice(devs[g].dev));
     check(cudaStreamSynchronize(devs[g].main));
-    check(cudaStreamSynchronize(devs[g].copy));
+    check(cudaStreamSynchronize(devs[g].aux));
     check(cudaStreamSynchronize(devs[g].upd));
   }
   for (cudaEvent_t ev : evs) cudaEventDestroy(ev);
+  for (auto& c : ch)
+    for (cudaEvent_t ev : c.events) cudaEventDestroy(ev);
   return err;
 }
 

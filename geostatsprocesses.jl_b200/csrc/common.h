@@ -45,6 +45,7 @@ struct ProfScope {
 struct DevCtx {
   int dev = 0;
   cudaStream_t stream = nullptr;   // compute (highest priority: carries the critical path)
+  cudaStream_t aux = nullptr;      // second high-priority stream (look-ahead updates next to the panel chain)
   cudaStream_t h2d = nullptr;      // copy-in
   cudaStream_t d2h = nullptr;      // copy-out
   static constexpr int kSide = 8;
@@ -87,13 +88,17 @@ struct DevBuf {
   void* p = nullptr;
   size_t bytes = 0;
   int dev = 0;
+  cudaStream_t owner = nullptr;  // stream every use of the block is ordered on (or joined into) - see release()
   DevBuf() = default;
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
   ~DevBuf() { release(); }
-  cudaError_t alloc(int device, size_t n) {
+  // `st`: the stream that all work on the block is ordered on; the block is then freed stream-ordered (cudaFreeAsync on st), with
+  // no synchronisation at all.  Without it (nullptr) release() falls back to a device-wide synchronisation before the free.
+  cudaError_t alloc(int device, size_t n, cudaStream_t st = nullptr) {
     release();
     dev = device;
+    owner = st;
     cudaSetDevice(dev);
     cudaError_t e = cudaMallocAsync(&p, n ? n : 16, (cudaStream_t)0);
     if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)0);
@@ -104,8 +109,12 @@ struct DevBuf {
   void release() {
     if (p) {
       cudaSetDevice(dev);
-      cudaDeviceSynchronize();
-      cudaFreeAsync(p, (cudaStream_t)0);
+      if (owner) {
+        cudaFreeAsync(p, owner);
+      } else {
+        cudaDeviceSynchronize();
+        cudaFreeAsync(p, (cudaStream_t)0);
+      }
       p = nullptr;
       bytes = 0;
     }

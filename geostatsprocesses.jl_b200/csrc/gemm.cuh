@@ -18,6 +18,7 @@ constexpr int GT = 128;        // block granularity of all callers (matrices are
 constexpr int GKC = 16;        // K chunk per stage
 constexpr int GSTAGES = 4;
 constexpr int GLDBK = GKC + 4; // smem leading dim of [n][k] operand tiles (20 = 4 mod 16)
+#define GSP_MAX_PEERS 7        // one context drives at most 8 devices
 
 enum GemmMode { GEMM_SET = 0, GEMM_SUB = 1, GEMM_SAMPLE = 2 };
 
@@ -51,10 +52,15 @@ struct GemmArgs {
   const long long* sinds;
   double addmu;
   long long Ns, R;
-  int strip;         // 1: B (N x K) is lower triangular -> k < (tj+1)*TN only; column tiles heaviest first (triangular solve by an
-                     // explicit panel inverse, out of place: C must not alias A)
   long long ntiles;  // filled by launch_gemm_cfg
   int max_ctas;      // > 0: persistent grid of at most this many CTAs walking the tiles (look-ahead streams leave SMs free)
+  // ---- distributed factorization (chol.cu, chol_factor_dist): a device works on the block rows it owns
+  const int* rows;   // device array or nullptr: block row (128-row units) of every group of 128 rows of A and C (tile row ti covers
+                     // rows rows[ti*TM/128]*128 + (ti*TM)%128 ...); nullptr: rows are contiguous from the base pointers
+  int stair;         // 1: skip tiles above the diagonal of the GLOBAL matrix: keep tile (ti, tj) iff colblk0*128 + tj*TN <= first row of ti
+  int colblk0;       // global block column of tile column 0 of C (stair only)
+  int npeer;         // GEMM_SET: the finished tile is ALSO stored at the same offsets of Cpeer[0..npeer) - the matrices of the other
+  double* Cpeer[GSP_MAX_PEERS];  // devices (peer-mapped over NVLink): the panel multicast is fused into the TRSM epilogue
 };
 
 template <int MODE, bool BK, int TM, int TN, int WM, int WN>
@@ -88,9 +94,6 @@ __global__ void __launch_bounds__(GemmCfg<TM, TN, WM, WN>::THREADS, 1) gemm_dmma
       // lower-triangular A: row tile ti costs (ti+1) chunks -> heaviest rows first, columns fastest (LPT order)
       tj = (int)(t % g.nt);
       ti = g.mt - 1 - (int)(t / g.nt);
-    } else if (g.strip) {
-      ti = (int)(t % g.mt);
-      tj = g.nt - 1 - (int)(t / g.mt);
     } else {
       ti = (int)(t % g.mt);
       tj = (int)(t / g.mt);
@@ -100,12 +103,15 @@ __global__ void __launch_bounds__(GemmCfg<TM, TN, WM, WN>::THREADS, 1) gemm_dmma
       long long lim = (long long)(ti + 1) * TM;
       if (lim < kend) kend = (int)lim;
     }
-    if (g.strip) {
-      long long lim = (long long)(tj + 1) * TN;
-      if (lim < kend) kend = (int)lim;
-    }
     nchunks = kend / GKC;
   };
+  // first row of A / C tile row ti (row lists: the block rows a device owns in the distributed factorization)
+  auto rowoff = [&](int ti) -> long long {
+    if (!g.rows) return (long long)ti * TM;
+    constexpr int PER = GT / TM;
+    return (long long)g.rows[ti / PER] * GT + (long long)(ti % PER) * TM;
+  };
+  auto skip = [&](int ti, int tj) -> bool { return g.stair && (long long)g.colblk0 * GT + (long long)tj * TN > rowoff(ti); };
   // The grid is either one CTA per tile or (max_ctas) a persistent one walking the tiles; `cg` numbers the K chunks of all the
   // tiles a CTA processes, so the ring and its mbarrier phases simply keep running across tiles.
 
@@ -115,7 +121,8 @@ __global__ void __launch_bounds__(GemmCfg<TM, TN, WM, WN>::THREADS, 1) gemm_dmma
     for (long long t = blockIdx.x; t < g.ntiles; t += gridDim.x) {
     int ti, tj, nchunks;
     decode(t, ti, tj, nchunks);
-    const double* Abase = g.A + (long long)ti * TM;
+    if (skip(ti, tj)) continue;
+    const double* Abase = g.A + rowoff(ti);
     const double* Bbase = BK ? g.B + (long long)tj * TN * g.ldb : g.B + (long long)tj * TN;
     for (int c = 0; c < nchunks; ++c, ++cg) {
       const int s = (int)(cg % GSTAGES);
@@ -151,6 +158,7 @@ __global__ void __launch_bounds__(GemmCfg<TM, TN, WM, WN>::THREADS, 1) gemm_dmma
   for (long long t = blockIdx.x; t < g.ntiles; t += gridDim.x) {
   int ti, tj, nchunks;
   decode(t, ti, tj, nchunks);
+  if (skip(ti, tj)) continue;
   double acc[FM][FN][2];
 #pragma unroll
   for (int a = 0; a < FM; ++a)
@@ -184,7 +192,7 @@ __global__ void __launch_bounds__(GemmCfg<TM, TN, WM, WN>::THREADS, 1) gemm_dmma
   }
 
   // -------------------------------------------------------------- epilogue
-  const long long row0 = (long long)ti * TM + wm * (TM / WM) + lr;
+  const long long row0 = rowoff(ti) + wm * (TM / WM) + lr;
   const long long col0 = (long long)tj * TN + wn * (TN / WN) + 2 * lk;
 #pragma unroll
   for (int a = 0; a < FM; ++a) {
@@ -195,6 +203,10 @@ __global__ void __launch_bounds__(GemmCfg<TM, TN, WM, WN>::THREADS, 1) gemm_dmma
       if (MODE == GEMM_SET) {
         g.C[i + j * g.ldc] = acc[a][b][0];
         g.C[i + (j + 1) * g.ldc] = acc[a][b][1];
+        for (int p = 0; p < g.npeer; ++p) {  // multicast over NVLink: 8 lanes cover 64 contiguous bytes of a column
+          g.Cpeer[p][i + j * g.ldc] = acc[a][b][0];
+          g.Cpeer[p][i + (j + 1) * g.ldc] = acc[a][b][1];
+        }
       } else if (MODE == GEMM_SUB) {
         double* p0 = g.C + i + j * g.ldc;
         double* p1 = p0 + g.ldc;
@@ -240,9 +252,10 @@ inline cudaError_t launch_gemm_cfg(cudaStream_t st, const GemmArgs& g0) {
 // `g.mt`, `g.nt` are given in 128-blocks.  Problems with too few 128x128 tiles to fill the GPU are
 // retiled to 64-row (in-place TRSM: the C tile must span all 128 columns) or 64x64 tiles: 2-4x more CTAs
 // on the latency-bound small GEMMs of the factorisation's critical path.
+// `work_tiles` (>= 0): number of 128x128 tiles that are actually computed when the stair predicate skips part of the mt x nt grid.
 template <int MODE, bool BK>
-inline cudaError_t launch_gemm(cudaStream_t st, const GemmArgs& g0) {
-  const long long tiles128 = g0.tri ? (long long)g0.mt * (g0.mt + 1) / 2 : (long long)g0.mt * g0.nt;
+inline cudaError_t launch_gemm(cudaStream_t st, const GemmArgs& g0, long long work_tiles = -1) {
+  const long long tiles128 = work_tiles >= 0 ? work_tiles : (g0.tri ? (long long)g0.mt * (g0.mt + 1) / 2 : (long long)g0.mt * g0.nt);
   static long long kSmall = -1;  // GSP_GEMM_SMALL_TILES overrides the retiling threshold (tests force either path)
   if (kSmall < 0) {
     const char* env = getenv("GSP_GEMM_SMALL_TILES");

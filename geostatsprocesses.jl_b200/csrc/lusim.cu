@@ -62,6 +62,7 @@ struct LuDev {
   DevCtx* dc = nullptr;
   DevBuf A;       // Np x Np joint matrix -> L
   DevBuf invD;    // inverses of the diagonal 128-blocks
+  DevBuf rows;    // block rows this device owns (distributed factorization)
   DevBuf d2;      // Ns_pad
   DevBuf sinds;   // Ns (0-based)
   DevBuf dinds;   // Nd (0-based)
@@ -179,6 +180,61 @@ int sample_core(gsp_ctx* ctx, gsp_lu_plan* p, LuDev* d, long long cols, const do
 }  // namespace
 }  // namespace gsp
 
+namespace gsp {
+namespace {
+
+// RAII for the timing events of gsp_lu_plan_create (every return path destroys them)
+struct EventSet {
+  std::vector<cudaEvent_t> ev;
+  ~EventSet() {
+    for (cudaEvent_t e : ev)
+      if (e) cudaEventDestroy(e);
+  }
+  cudaError_t make(int n) {
+    ev.assign((size_t)n, nullptr);
+    for (auto& e : ev) {
+      cudaError_t rc = cudaEventCreate(&e);
+      if (rc != cudaSuccess) return rc;
+    }
+    return cudaSuccess;
+  }
+};
+
+void destroy_plan_events(gsp_lu_plan* p) {
+  for (auto& d : p->dev) {
+    cudaSetDevice(d->dc->dev);
+    cudaStreamSynchronize(d->dc->stream);
+    for (cudaEvent_t* e : {&d->ev0, &d->ev1, &d->ev_in[0], &d->ev_in[1], &d->ev_comp[0], &d->ev_comp[1], &d->ev_out[0], &d->ev_out[1]})
+      if (*e) {
+        cudaEventDestroy(*e);
+        *e = nullptr;
+      }
+  }
+}
+
+// Which factorization runs (GSP_CHOL_ALGO): "panel" = chol_factor_dist (row-panel ownership over the devices of the context, also on
+// one device), "recursive" = chol_factor on device 0 (+ copy of L to the other devices).  Default: panel whenever the matrix has
+// at least GSP_CHOL_DIST_MIN_BLOCKS 128-blocks (below that the panel chain dominates and the recursion on one device is as fast).
+struct CholChoice {
+  bool dist;
+  int PB;
+};
+CholChoice choose_chol(int ndev, int nb) {
+  static const char* algo = getenv("GSP_CHOL_ALGO");
+  static const int min_blocks = getenv("GSP_CHOL_DIST_MIN_BLOCKS") ? atoi(getenv("GSP_CHOL_DIST_MIN_BLOCKS")) : 24;
+  static const int pb_env = getenv("GSP_CHOL_PB") ? atoi(getenv("GSP_CHOL_PB")) : 0;
+  CholChoice c{};
+  if (algo && algo[0] == 'r') c.dist = false;
+  else if (algo && algo[0] == 'p') c.dist = true;
+  else c.dist = nb >= min_blocks && ndev > 1;
+  c.PB = pb_env > 0 ? pb_env : 4;
+  if (c.PB > nb) c.PB = nb;
+  return c;
+}
+
+}  // namespace
+}  // namespace gsp
+
 extern "C" int gsp_lu_plan_create(gsp_ctx* ctx, const gsp_cov_model* cov, const gsp_domain* dom, int64_t nd, const int64_t* dinds,
                                   const double* z1, double mu, gsp_lu_plan** out) {
   if (!ctx) return -1;
@@ -196,7 +252,17 @@ extern "C" int gsp_lu_plan_create(gsp_ctx* ctx, const gsp_cov_model* cov, const 
     if (dinds[j] < 1 || dinds[j] > N) return set_err(ctx, -5, "dinds out of range (1-based)");
     if (j > 0 && dinds[j] <= dinds[j - 1]) return set_err(ctx, -5, "dinds must be strictly ascending (findall(mask))");
   }
-  std::unique_ptr<gsp_lu_plan> p(new gsp_lu_plan);
+  // the plan owns CUDA events: on every error return below they are destroyed with it
+  struct PlanGuard {
+    gsp_lu_plan* p;
+    ~PlanGuard() {
+      if (p) {
+        destroy_plan_events(p);
+        delete p;
+      }
+    }
+  } guard{new gsp_lu_plan};
+  gsp_lu_plan* p = guard.p;
   p->ctx = ctx;
   p->N = N;
   p->Nd = nd;
@@ -223,32 +289,31 @@ extern "C" int gsp_lu_plan_create(gsp_ctx* ctx, const gsp_cov_model* cov, const 
     }
   }
 
-  // ---- which devices build: one (factor there, copy L to the others) or all (multi-GPU block-cyclic factorization)
   const int ndev = (int)ctx->devs.size();
-  static int mg_min_blocks = -1, mg_pb_env = 0, mg_force = 0;
-  if (mg_min_blocks < 0) {
-    const char* e3 = getenv("GSP_CHOL_MG_FORCE");  // use the panel algorithm even on one device (A/B against the recursive one)
-    mg_force = (e3 && e3[0] == '1') ? 1 : 0;
-    const char* e1 = getenv("GSP_CHOL_MG_MIN_BLOCKS");
-    const char* e2 = getenv("GSP_CHOL_MG_PB");
-    mg_min_blocks = e1 ? atoi(e1) : 64;  // below ~8k nodes the panel chain dominates: replicate instead
-    if (e2 && atoi(e2) > 0) mg_pb_env = atoi(e2);
-  }
   const int nb = (int)(p->Np / 128);
-  // panel width in 128-blocks (measured on 2 B200: N = 33k: PB 4 -> 298 ms, PB 8 -> 251 ms; N = 16.5k: 49 ms vs 51 ms)
-  const int mg_pb = mg_pb_env > 0 ? mg_pb_env : (nb >= 192 ? 8 : 4);
-  const bool mg = (ndev > 1 || mg_force) && nb >= mg_min_blocks;
-  const int nbuild = mg ? ndev : 1;
+  const CholChoice cc = choose_chol(ndev, nb);
+  const int nbuild = cc.dist ? ndev : 1;   // devices that take part in the factorization
 
-  auto build_one = [&](LuDev* d, bool with_matrix) -> int {
+  EventSet tev;
+  cudaSetDevice(ctx->devs[0].dev);
+  GSP_CUDA_OK(ctx, tev.make(4));
+  GSP_CUDA_OK(ctx, cudaEventRecord(tev.ev[0], ctx->devs[0].stream));
+
+  // ---- per-device buffers; a1: joint covariance (lusim.jl:88,95,96) - with the distributed factorization every device assembles
+  // only the block rows it owns (lower part), otherwise device 0 assembles the lower tiles of the whole matrix
+  for (int i = 0; i < ndev; ++i) {
+    std::unique_ptr<LuDev> dptr(new LuDev);
+    LuDev* d = dptr.get();
+    d->dc = &ctx->devs[i];
+    p->dev.push_back(std::move(dptr));
     DevCtx& dc = *d->dc;
     cudaSetDevice(dc.dev);
     cudaStream_t st = dc.stream;
-    GSP_CUDA_OK(ctx, d->d2.alloc(dc.dev, (size_t)p->Nsp * sizeof(double)));
-    GSP_CUDA_OK(ctx, d->sinds.alloc(dc.dev, (size_t)p->Ns * sizeof(long long)));
-    GSP_CUDA_OK(ctx, d->dinds.alloc(dc.dev, (size_t)std::max<long long>(nd, 1) * sizeof(long long)));
-    GSP_CUDA_OK(ctx, d->z1.alloc(dc.dev, (size_t)std::max<long long>(nd, 1) * sizeof(double)));
-    GSP_CUDA_OK(ctx, d->info.alloc(dc.dev, sizeof(int)));
+    GSP_CUDA_OK(ctx, d->d2.alloc(dc.dev, (size_t)p->Nsp * sizeof(double), st));
+    GSP_CUDA_OK(ctx, d->sinds.alloc(dc.dev, (size_t)p->Ns * sizeof(long long), st));
+    GSP_CUDA_OK(ctx, d->dinds.alloc(dc.dev, (size_t)std::max<long long>(nd, 1) * sizeof(long long), st));
+    GSP_CUDA_OK(ctx, d->z1.alloc(dc.dev, (size_t)std::max<long long>(nd, 1) * sizeof(double), st));
+    GSP_CUDA_OK(ctx, d->info.alloc(dc.dev, sizeof(int), st));
     GSP_CUDA_OK(ctx, cudaEventCreate(&d->ev0));
     GSP_CUDA_OK(ctx, cudaEventCreate(&d->ev1));
     GSP_CUDA_OK(ctx, cudaMemcpyAsync(d->sinds.p, sinds.data(), sinds.size() * sizeof(long long), cudaMemcpyHostToDevice, st));
@@ -256,67 +321,65 @@ extern "C" int gsp_lu_plan_create(gsp_ctx* ctx, const gsp_cov_model* cov, const 
       GSP_CUDA_OK(ctx, cudaMemcpyAsync(d->dinds.p, dind0.data(), dind0.size() * sizeof(long long), cudaMemcpyHostToDevice, st));
       GSP_CUDA_OK(ctx, cudaMemcpyAsync(d->z1.p, z1, (size_t)nd * sizeof(double), cudaMemcpyHostToDevice, st));
     }
-    GSP_CUDA_OK(ctx, d->A.alloc(dc.dev, (size_t)p->Np * p->Np * sizeof(double)));
-    if (!with_matrix) return GSP_OK;
-    GSP_CUDA_OK(ctx, d->invD.alloc(dc.dev, (size_t)nb * 128 * 128 * sizeof(double)));
+    GSP_CUDA_OK(ctx, d->A.alloc(dc.dev, (size_t)p->Np * p->Np * sizeof(double), st));
+    GSP_CUDA_OK(ctx, d->invD.alloc(dc.dev, (size_t)nb * 128 * 128 * sizeof(double), st));
+    if (i >= nbuild) continue;
+    GSP_CUDA_OK(ctx, d->rows.alloc(dc.dev, (size_t)nb * sizeof(int), st));
     DevBuf dperm, dcoords;
-    GSP_CUDA_OK(ctx, dperm.alloc(dc.dev, (size_t)p->Np * sizeof(long long)));
+    GSP_CUDA_OK(ctx, dperm.alloc(dc.dev, (size_t)p->Np * sizeof(long long), st));
     GSP_CUDA_OK(ctx, cudaMemcpyAsync(dperm.p, perm.data(), perm.size() * sizeof(long long), cudaMemcpyHostToDevice, st));
     DomDev ddl = dd;
     if (dd.kind == 0) {
-      GSP_CUDA_OK(ctx, dcoords.alloc(dc.dev, (size_t)N * dd.dim * sizeof(double)));
+      GSP_CUDA_OK(ctx, dcoords.alloc(dc.dev, (size_t)N * dd.dim * sizeof(double), st));
       GSP_CUDA_OK(ctx, cudaMemcpyAsync(dcoords.p, dom->coords, (size_t)N * dd.dim * sizeof(double), cudaMemcpyHostToDevice, st));
       ddl.coords = dcoords.as<double>();
     }
-    // a1: joint covariance, lower tiles only (lusim.jl:88,95,96)
-    launch_assemble(st, cd, ddl, ddl, dperm.as<long long>(), dperm.as<long long>(), p->Np, p->Np, d->A.as<double>(), p->Np, true);
+    if (!cc.dist) {
+      launch_assemble(st, cd, ddl, ddl, dperm.as<long long>(), dperm.as<long long>(), p->Np, p->Np, d->A.as<double>(), p->Np, true);
+    } else {
+      std::vector<int> own;
+      chol_dist_owned_rows(nb, cc.PB, nbuild, i, &own);
+      for (size_t a = 0; a < own.size();) {  // one launch per run of consecutive own block rows: rows [r0, r1) x columns [0, r1)
+        size_t b = a + 1;
+        while (b < own.size() && own[b] == own[b - 1] + 1) ++b;
+        const long long r0 = (long long)own[a] * 128, r1 = (long long)(own[b - 1] + 1) * 128;
+        launch_assemble(st, cd, ddl, ddl, dperm.as<long long>() + r0, dperm.as<long long>(), r1 - r0, r1, d->A.as<double>() + r0, p->Np, true, r0);
+        a = b;
+      }
+    }
     GSP_CUDA_OK(ctx, cudaGetLastError());
-    GSP_CUDA_OK(ctx, cudaStreamSynchronize(st));  // dperm / dcoords go out of scope
-    return GSP_OK;
-  };
-
-  cudaEvent_t tev[4];
-  {
-    cudaSetDevice(ctx->devs[0].dev);
-    for (auto& e : tev) GSP_CUDA_OK(ctx, cudaEventCreate(&e));
-    GSP_CUDA_OK(ctx, cudaEventRecord(tev[0], ctx->devs[0].stream));
-  }
-  for (int i = 0; i < ndev; ++i) {
-    std::unique_ptr<LuDev> d(new LuDev);
-    d->dc = &ctx->devs[i];
-    GSP_TRY(build_one(d.get(), i < nbuild));
-    p->dev.push_back(std::move(d));
+    // dperm / dcoords are freed stream-ordered on st when they go out of scope; the pageable host sources were consumed by the copies
   }
   LuDev* d0 = p->dev[0].get();
   DevCtx& dc = *d0->dc;
   cudaSetDevice(dc.dev);
   cudaStream_t st = dc.stream;
-  DevBuf work;  // panel inverses of the single-device factorization: only needed while it runs, freed when this function returns
-  if (!mg && chol_work_doubles(nb) > 0) GSP_CUDA_OK(ctx, work.alloc(dc.dev, chol_work_doubles(nb) * sizeof(double)));
-  GSP_CUDA_OK(ctx, cudaEventRecord(tev[1], st));
+  GSP_CUDA_OK(ctx, cudaEventRecord(tev.ev[1], st));
   // a2/a3: one joint Cholesky (lusim.jl:92 or 98-103)
-  if (mg) {
-    std::vector<MgDev> mds;
-    for (auto& d : p->dev)
-      mds.push_back(MgDev{d->dc->dev, d->dc->stream, d->dc->side[0], d->dc->h2d, d->A.as<double>(), d->invD.as<double>(), d->info.as<int>()});
-    GSP_CUDA_OK(ctx, chol_factor_mg(mds, p->Np, nb, mg_pb));
+  if (cc.dist) {
+    std::vector<DistDev> dv;
+    for (int i = 0; i < nbuild; ++i) {
+      LuDev* d = p->dev[i].get();
+      dv.push_back(DistDev{d->dc->dev, d->dc->stream, d->dc->aux, d->dc->side[0], d->A.as<double>(), d->invD.as<double>(), d->info.as<int>(),
+                           d->rows.as<int>()});
+    }
+    GSP_CUDA_OK(ctx, chol_factor_dist(dv, p->Np, nb, cc.PB));
     cudaSetDevice(dc.dev);
   } else {
-    GSP_CUDA_OK(ctx, chol_factor(st, dc.side, DevCtx::kSide, d0->A.as<double>(), p->Np, nb, d0->invD.as<double>(), d0->info.as<int>(),
-                                 work.as<double>()));
+    GSP_CUDA_OK(ctx, chol_factor(st, dc.side, DevCtx::kSide, d0->A.as<double>(), p->Np, nb, d0->invD.as<double>(), d0->info.as<int>()));
   }
-  GSP_CUDA_OK(ctx, cudaEventRecord(tev[2], st));
+  GSP_CUDA_OK(ctx, cudaEventRecord(tev.ev[2], st));
   // d2 = A21 * (L11 \ z1)   (lusim.jl:102); zero when unconditional (lusim.jl:91)
   DevBuf y;
   GSP_CUDA_OK(ctx, cudaMemsetAsync(d0->d2.p, 0, (size_t)p->Nsp * sizeof(double), st));
   if (nd > 0) {
-    GSP_CUDA_OK(ctx, y.alloc(dc.dev, (size_t)p->Ndp * sizeof(double)));
+    GSP_CUDA_OK(ctx, y.alloc(dc.dev, (size_t)p->Ndp * sizeof(double), st));
     GSP_CUDA_OK(ctx, cudaMemsetAsync(y.p, 0, (size_t)p->Ndp * sizeof(double), st));
     GSP_CUDA_OK(ctx, cudaMemcpyAsync(y.p, z1, (size_t)nd * sizeof(double), cudaMemcpyHostToDevice, st));
     GSP_CUDA_OK(ctx, chol_forward_solve(st, d0->A.as<double>(), p->Np, d0->invD.as<double>(), (int)(p->Ndp / 128), y.as<double>()));
     GSP_CUDA_OK(ctx, chol_gemv_rows(st, d0->A.as<double>(), p->Np, p->Ndp, p->Nsp, (int)p->Ndp, y.as<double>(), d0->d2.as<double>()));
   }
-  GSP_CUDA_OK(ctx, cudaEventRecord(tev[3], st));
+  GSP_CUDA_OK(ctx, cudaEventRecord(tev.ev[3], st));
   int info = 0;
   for (int i = 0; i < nbuild; ++i) {  // the first non-positive pivot may have been met on any panel owner
     int inf_i = 0;
@@ -329,10 +392,9 @@ extern "C" int gsp_lu_plan_create(gsp_ctx* ctx, const gsp_cov_model* cov, const 
   GSP_CUDA_OK(ctx, cudaStreamSynchronize(st));
   {
     float ms = 0.f;
-    cudaEventElapsedTime(&ms, tev[0], tev[1]); p->t_assemble_ms = ms;
-    cudaEventElapsedTime(&ms, tev[1], tev[2]); p->t_factor_ms = ms;
-    cudaEventElapsedTime(&ms, tev[2], tev[3]); p->t_solve_ms = ms;
-    for (auto& e : tev) cudaEventDestroy(e);
+    cudaEventElapsedTime(&ms, tev.ev[0], tev.ev[1]); p->t_assemble_ms = ms;
+    cudaEventElapsedTime(&ms, tev.ev[1], tev.ev[2]); p->t_factor_ms = ms;
+    cudaEventElapsedTime(&ms, tev.ev[2], tev.ev[3]); p->t_solve_ms = ms;
   }
   if (info > 0) {
     // map the padded position back to the reference ordering [dinds; sinds] (1-based)
@@ -341,31 +403,22 @@ extern "C" int gsp_lu_plan_create(gsp_ctx* ctx, const gsp_cov_model* cov, const 
     set_err(ctx, (int)ref, "matrix is not positive definite (PosDefException)");
     return (int)ref;
   }
-  // the other devices receive d2 (and L, unless the multi-GPU factorization already left it everywhere)
+  // the other devices receive d2 (and L, unless the distributed factorization already left it everywhere)
   for (int i = 1; i < ndev; ++i) {
     LuDev* e = p->dev[i].get();
     cudaSetDevice(e->dc->dev);
-    if (!mg) GSP_CUDA_OK(ctx, cudaMemcpyPeerAsync(e->A.p, e->dc->dev, d0->A.p, d0->dc->dev, d0->A.bytes, e->dc->stream));
+    if (!cc.dist) GSP_CUDA_OK(ctx, cudaMemcpyPeerAsync(e->A.p, e->dc->dev, d0->A.p, d0->dc->dev, d0->A.bytes, e->dc->stream));
     GSP_CUDA_OK(ctx, cudaMemcpyPeerAsync(e->d2.p, e->dc->dev, d0->d2.p, d0->dc->dev, d0->d2.bytes, e->dc->stream));
     GSP_CUDA_OK(ctx, cudaStreamSynchronize(e->dc->stream));
   }
-  *out = p.release();
+  guard.p = nullptr;
+  *out = p;
   return GSP_OK;
 }
 
 extern "C" int gsp_lu_plan_destroy(gsp_lu_plan* p) {
   if (!p) return GSP_OK;
-  for (auto& d : p->dev) {
-    cudaSetDevice(d->dc->dev);
-    cudaStreamSynchronize(d->dc->stream);
-    if (d->ev0) cudaEventDestroy(d->ev0);
-    if (d->ev1) cudaEventDestroy(d->ev1);
-    for (int k = 0; k < 2; ++k) {
-      if (d->ev_in[k]) cudaEventDestroy(d->ev_in[k]);
-      if (d->ev_comp[k]) cudaEventDestroy(d->ev_comp[k]);
-      if (d->ev_out[k]) cudaEventDestroy(d->ev_out[k]);
-    }
-  }
+  destroy_plan_events(p);
   delete p;
   return GSP_OK;
 }
@@ -417,6 +470,7 @@ extern "C" int gsp_lu_sample_dev(gsp_lu_plan* p, int64_t R, const double* W, int
   const bool mix = !std::isnan(rho);
   if (mix && !(rho >= -1.0 && rho <= 1.0)) return set_err(ctx, -8, "rho must be in [-1, 1] (or NaN for the first variable)");
   if (mix && W && !W1) return set_err(ctx, -9, "W1 is required when W is given and rho is set");
+  if (!W && W1) return set_err(ctx, -9, "W1 without W: both noises are injected or both come from the device RNG");
   LuDev* d = p->dev[0].get();
   cudaSetDevice(d->dc->dev);
   const long long chunk = std::min<long long>(std::max<long long>(R, 1), 1024);
@@ -451,6 +505,7 @@ int lu_sample_impl(gsp_lu_plan* p, int64_t R, const double* W, uint64_t seed, in
   const bool mix = !std::isnan(rho);
   if (mix && !(rho >= -1.0 && rho <= 1.0)) return set_err(ctx, -7, "rho must be in [-1, 1] (or NaN for the first variable)");
   if (mix && W && !W1) return set_err(ctx, -8, "W1 is required when W is given and rho is set");
+  if (!W && W1) return set_err(ctx, -8, "W1 without W: both noises are injected or both come from the device RNG");
   const int ndev = (int)p->dev.size();
   std::vector<long long> r0(ndev + 1, 0);
   for (int i = 0; i < ndev; ++i) r0[i + 1] = r0[i] + (R / ndev) + (i < R % ndev ? 1 : 0);

@@ -294,9 +294,9 @@ def test_cholesky_big_tile_path(emu_lib):
     assert out.returncode == 0 and "OK" in out.stdout, out.stderr[-1500:]
 
 
-def test_cholesky_panel_inverse_solves(emu_lib):
-    """opt-in GSP_CHOL_PANELS=1 (measured slower on the B200, kept for A/B): inverses of aligned 2-block panels built from the diagonal
-    blocks' inverses, triangular solves as one triangular-K tile GEMM + copy.  4 blocks exercise the level-2 build and solve."""
+def test_cholesky_panel_algorithm_single_device(emu_lib):
+    """GSP_CHOL_ALGO=panel: the panel algorithm of the distributed factorization (row lists, stair-shaped updates, look-ahead on the
+    aux / low-priority streams) on ONE device through gsp_potrf; 4 blocks in panels of 2."""
     import os, subprocess, sys, textwrap
     code = textwrap.dedent("""
         import sys, numpy as np, scipy.linalg
@@ -310,13 +310,15 @@ def test_cholesky_panel_inverse_solves(emu_lib):
         assert err < 1e-11, err
         print("OK")
     """) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)), emu_lib.path)
-    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, GSP_CHOL_PANELS="1"), timeout=600)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, GSP_CHOL_ALGO="panel", GSP_CHOL_PB="2"), timeout=600)
     assert out.returncode == 0 and "OK" in out.stdout, out.stderr[-1500:]
 
 
 def test_multi_device_block_cyclic_cholesky(emu_lib):
-    """multi-GPU factorization (chol_factor_mg): panels owned cyclically, pushed in place to every device; exercised with the
-    emulated device listed 3 times (separate buffers per listed device), PB = 1 block, in a subprocess (env is cached)."""
+    """distributed factorization (chol_factor_dist): row panels owned by different devices (boustrophedon), every device assembles
+    and updates only its rows, finished blocks are multicast from the kernels' epilogues into every other device's buffer;
+    exercised with the emulated device listed 3 times (separate buffers per listed device), PB = 1 block, in a subprocess
+    (env is cached).  Real peer memory and cross-device event ordering are covered by tests/test_multi_gpu.py on >= 2 GPUs."""
     import os, subprocess, sys, textwrap
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     code = textwrap.dedent("""
@@ -341,7 +343,7 @@ def test_multi_device_block_cyclic_cholesky(emu_lib):
             plan.close(); lib.close()
         print("OK")
     """) % (root, os.path.join(root, "oracle"), os.path.join(root, "tests"), emu_lib.path)
-    env = dict(os.environ, GSP_CHOL_MG_MIN_BLOCKS="2", GSP_CHOL_MG_PB="1")
+    env = dict(os.environ, GSP_CHOL_DIST_MIN_BLOCKS="2", GSP_CHOL_PB="1")
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=900)
     assert out.returncode == 0 and "OK" in out.stdout, out.stderr[-1500:]
 

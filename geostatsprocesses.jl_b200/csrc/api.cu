@@ -23,21 +23,59 @@ void Prof::add(const std::string& n, double ms) {
   acc.push_back({n, {ms, 1}});
 }
 
-void Prof::flush() {
-  // GSP_PROF_TIMELINE=1 (development): print "name start_ms duration_ms" of every launch, relative to the first pending one
+static bool prof_timeline() {
   static int timeline = -1;
   if (timeline < 0) {
     const char* env = getenv("GSP_PROF_TIMELINE");
     timeline = (env && env[0] == '1') ? 1 : 0;
   }
+  return timeline != 0;
+}
+
+void Prof::mark_reference(const std::vector<int>& devs) {
+  if (!on || !prof_timeline()) return;
+  flush();
+  for (auto& r : ref) cudaEventDestroy(r.second);
+  ref.clear();
+  for (int d : devs) {
+    cudaSetDevice(d);
+    cudaDeviceSynchronize();
+  }
+  for (int d : devs) {
+    cudaSetDevice(d);
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, (cudaStream_t)0);
+    ref.push_back({d, e});
+  }
+  for (int d : devs) {
+    cudaSetDevice(d);
+    cudaDeviceSynchronize();
+  }
+}
+
+void Prof::flush() {
+  // GSP_PROF_TIMELINE=1 (development): print "TL dev stream name start_ms duration_ms" of every launch; start is relative to the
+  // device's origin event (mark_reference) or, without one, to the first pending launch of that device
+  const bool timeline = prof_timeline();
   for (auto& p : pending) {
+    cudaSetDevice(p.dev);
     cudaEventSynchronize(p.e1);
     float ms = 0.f;
     cudaEventElapsedTime(&ms, p.e0, p.e1);
     if (timeline) {
+      cudaEvent_t origin = nullptr;
+      for (auto& r : ref)
+        if (r.first == p.dev) origin = r.second;
+      if (!origin)
+        for (auto& q : pending)
+          if (q.dev == p.dev) {
+            origin = q.e0;
+            break;
+          }
       float t0 = 0.f;
-      cudaEventElapsedTime(&t0, pending.front().e0, p.e0);
-      fprintf(stderr, "TL %s %.4f %.4f\n", p.name.c_str(), t0, ms);
+      cudaEventElapsedTime(&t0, origin, p.e0);
+      fprintf(stderr, "TL %d %p %s %.4f %.4f\n", p.dev, (void*)p.st, p.name.c_str(), t0, ms);
     }
     add(p.name, ms);
   }

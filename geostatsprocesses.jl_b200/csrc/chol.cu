@@ -521,6 +521,11 @@ cudaError_t chol_factor_dist(const std::vector<DistDev>& devs, long long ld, int
     if (!rows[g].empty())
       check(cudaMemcpyAsync(devs[g].rows, rows[g].data(), rows[g].size() * sizeof(int), cudaMemcpyHostToDevice, devs[g].main));
   }
+  if (g_prof.on) {
+    std::vector<int> ids;
+    for (auto& d : devs) ids.push_back(d.dev);
+    g_prof.mark_reference(ids);
+  }
   std::vector<cudaEvent_t> evs;
   auto record = [&](int g, cudaStream_t s) {
     cudaEvent_t ev;

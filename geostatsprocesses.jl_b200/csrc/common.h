@@ -15,9 +15,12 @@ extern long long g_launches;  // kernels launched by this library (gsp_kernel_la
 // Optional per-kernel-class timing with CUDA events on the launching stream (gsp_profile_enable).
 // Off by default: the timed paths carry no events besides the per-call pair.
 struct Prof {
-  struct Pending { std::string name; cudaEvent_t e0, e1; };
+  struct Pending { std::string name; cudaEvent_t e0, e1; int dev; cudaStream_t st; };
   bool on = false;
   std::vector<Pending> pending;
+  std::vector<std::pair<int, cudaEvent_t>> ref;  // timeline origin per device (mark_reference)
+  // GSP_PROF_TIMELINE: idle all `devs`, then record one origin event per device back to back (aligned to ~10 us across devices)
+  void mark_reference(const std::vector<int>& devs);
   std::vector<std::pair<std::string, std::pair<double, long long>>> acc;  // name -> (ms, launches)
   void add(const std::string& n, double ms);
   void flush();
@@ -37,7 +40,9 @@ struct ProfScope {
   ~ProfScope() {
     if (e0) {
       cudaEventRecord(e1, st);
-      g_prof.pending.push_back({name, e0, e1});
+      int dev = 0;
+      cudaGetDevice(&dev);
+      g_prof.pending.push_back({name, e0, e1, dev, st});
     }
   }
 };

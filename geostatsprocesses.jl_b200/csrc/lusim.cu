@@ -222,11 +222,12 @@ struct CholChoice {
 CholChoice choose_chol(int ndev, int nb) {
   static const char* algo = getenv("GSP_CHOL_ALGO");
   static const int min_blocks = getenv("GSP_CHOL_DIST_MIN_BLOCKS") ? atoi(getenv("GSP_CHOL_DIST_MIN_BLOCKS")) : 24;
+  static const int min_blocks_1 = getenv("GSP_CHOL_PANEL_MIN_BLOCKS") ? atoi(getenv("GSP_CHOL_PANEL_MIN_BLOCKS")) : 48;
   static const int pb_env = getenv("GSP_CHOL_PB") ? atoi(getenv("GSP_CHOL_PB")) : 0;
   CholChoice c{};
   if (algo && algo[0] == 'r') c.dist = false;
   else if (algo && algo[0] == 'p') c.dist = true;
-  else c.dist = nb >= min_blocks && ndev > 1;
+  else c.dist = ndev > 1 ? nb >= min_blocks : nb >= min_blocks_1;  // one device: measured C3 51.9 vs 59.4 ms, 32k nodes 359 vs 367 ms
   c.PB = pb_env > 0 ? pb_env : 4;
   if (c.PB > nb) c.PB = nb;
   return c;

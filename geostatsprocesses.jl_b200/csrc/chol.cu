@@ -83,7 +83,7 @@ GSP_DEV double frag_b(const double* S, int k0, int c0, int lane) { return S[(c0 
 // (S) rows below = panel * inv(L16)^T.  The inverse of the whole block is then assembled from the eight 16x16 inverses by
 // X21 = -inv(C) * B * inv(A) over 16 -> 32 -> 64 wide halves, again on DMMA tiles (one 8-row block per warp and level).
 __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(double* __restrict__ A, long long lda, long long blk,
-                                                            double* __restrict__ invD, int* __restrict__ info, const GSP_GRID_CONSTANT DiagPeers peers) {
+                                                            double* __restrict__ invD, int* __restrict__ info) {
   GSP_DYN_SMEM(smem);
   double* S = reinterpret_cast<double*>(smem);   // [DB cols][DLD]
   double* Dv = S + DB * DLD;                     // [8 panels][16 k][DVL]: Dv[p][k * DVL + n] = inv(L16_p)[n][k]
@@ -187,12 +187,10 @@ __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(double* __restrict__
     __syncthreads();
   }
 
-  // write L (upper triangle explicitly zero), also into the other devices' matrices (distributed factorization)
+  // write L (upper triangle explicitly zero)
   for (int idx = tid; idx < DB * DB; idx += 256) {
     const int r = idx & (DB - 1), c = idx >> 7;
-    const double v = (r >= c) ? S[c * DLD + r] : 0.0;
-    Ab[r + (long long)c * lda] = v;
-    for (int p = 0; p < peers.n; ++p) peers.A[p][blk * DB * (lda + 1) + r + (long long)c * lda] = v;
+    Ab[r + (long long)c * lda] = (r >= c) ? S[c * DLD + r] : 0.0;
   }
   __syncthreads();
 
@@ -261,7 +259,23 @@ __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(double* __restrict__
     const int r = idx & (DB - 1), c = idx >> 7;
     const double v = (r >= c) ? S[c * DLD + r] : 0.0;
     Xo[r + c * DB] = v;
-    for (int p = 0; p < peers.n; ++p) peers.invD[p][blk * DB * DB + r + c * DB] = v;
+  }
+}
+
+// Distributed factorization: the nq diagonal blocks of a finished square and their inverses go to the other devices (the
+// off-diagonal blocks of the square are multicast by the TRSM leaves that produce them).  One CTA per 16 columns of a block:
+// a single CTA storing 1.8 MB over NVLink from potrf_diag_kernel itself cost 30 us per block on the critical path.
+__global__ void __launch_bounds__(256) push_diag_kernel(const double* __restrict__ A, long long lda, long long blk0, const double* __restrict__ invD,
+                                                        const GSP_GRID_CONSTANT DiagPeers peers) {
+  const int k = blockIdx.x / 8, part = blockIdx.x % 8;
+  const long long blk = blk0 + k;
+  const int tid = threadIdx.x;
+  // 16 columns x 128 rows of L and of the inverse: 2 x 1024 double2 per CTA
+  for (int idx = tid; idx < 2 * 16 * 64; idx += 256) {
+    const int which = idx >> 10, e = idx & 1023, c = part * 16 + (e >> 6), r2 = (e & 63) * 2;
+    const long long off = which ? blk * DB * DB + r2 + (long long)c * DB : blk * DB * (lda + 1) + r2 + (long long)c * lda;
+    const double2 v = *reinterpret_cast<const double2*>((which ? invD : A) + off);
+    for (int p = 0; p < peers.n; ++p) *reinterpret_cast<double2*>((which ? peers.invD[p] : peers.A[p]) + off) = v;
   }
 }
 
@@ -405,6 +419,14 @@ struct Chol {
     trsm_rows(s, rows_dev, nrows, c0 + c1, nc - c1);
   }
 
+  void push_diag(int o, int n) {
+    if (peers.n <= 0 || n <= 0) return;
+    ProfScope prof_("push_diag", st);
+    GSP_LAUNCH(push_diag_kernel, dim3((unsigned)(8 * n)), dim3(256), 0, st, (const double*)A, ld, (long long)o, (const double*)invD, peers);
+    g_launches++;
+    check(cudaGetLastError());
+  }
+
   // Cholesky of the n diagonal blocks starting at o.  `pend`: event after which the second half [o + n/2, o + n) of the
   // block rows/cols is up to date (nullptr: already valid on the main stream).  The first half is always valid on entry.
   void potrf(int o, int n, cudaEvent_t pend, int depth) {
@@ -413,7 +435,7 @@ struct Chol {
       auto kfn = potrf_diag_kernel;
       check(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM));
       ProfScope prof_("potrf_diag", st);
-      GSP_LAUNCH(kfn, dim3(1), dim3(256), (size_t)DIAG_SMEM, st, A, ld, (long long)o, invD, info, peers);
+      GSP_LAUNCH(kfn, dim3(1), dim3(256), (size_t)DIAG_SMEM, st, A, ld, (long long)o, invD, info);
       g_launches++;
       check(cudaGetLastError());
       return;
@@ -476,14 +498,16 @@ cudaError_t chol_factor(cudaStream_t st, cudaStream_t* side, int nside, double* 
 // finished blocks are written straight into the same position of every other device's buffer from the epilogue of the kernel
 // that produces them (peer-mapped stores over NVLink: potrf_diag_kernel and the TRSM leaf GEMM), so when the last panel is done
 // every device holds the whole factor L - exactly what the realization-sharded sampling needs - without a separate broadcast.
-// Step q (column panel q, owner o = owner(q)):
-//   D(q)  on o:   Cholesky of the PB x PB diagonal square (needs only o's own rows), square + block inverses multicast
-//   T(q)  on all: each device solves ITS rows below the square against it and multicasts them          [main stream]
-//   LA(q) on all: own rows x column panel q+1 updated with panel q (owner(q+1): its diagonal square first, then D(q+1)) [main / aux]
-//   B(q)  on all: own rows x columns of panels >= q+2 (below the diagonal) updated with panel q        [low-priority stream]
-// Nothing on the critical path D -> T -> LA -> D is done by one device for the others except the PB-square itself: the panel
-// solve and the look-ahead update are split G ways by construction, and the wide update B(q) (one launch of short, K = PB*128
-// tiles on a low-priority stream) is pre-empted at tile granularity by the chain kernels of the high-priority streams.
+// Step q (column panel q, owner o = owner(q), next owner o1 = owner(q+1)):
+//   D(q)      on o:   Cholesky of the PB x PB diagonal square (needs only o's own rows); blocks + inverses go to every device [main]
+//   T_first   on o1:  o1 solves its rows of panel q+1 against the square, then LA_sq: the square of panel q+1 updated with
+//                     them, then D(q+1) - this is the whole critical path, and it stays on the main streams of two devices   [main]
+//   T(q)      on all: each device solves ITS other rows below the square and multicasts them from the GEMM epilogue         [aux]
+//   LA(q)     on all: own rows x column panel q+1 updated with panel q                                                        [aux]
+//   near(q), far(q) on all: own rows x columns of panel q+2 / of the panels >= q+3 updated with panel q  [low-priority stream]
+// LA(q+1) waits for near(q) only, which is queued before far(q): a look-ahead of depth two - the critical path never waits for
+// the wide update of the current or the previous step.  The panel solve and the updates are split G ways by construction; the
+// wide updates are launches of short (K = PB*128) tiles that the high-priority kernels pre-empt at tile granularity.
 static int dist_owner(int p, int G) {
   const int m = p % (2 * G);
   return m < G ? m : 2 * G - 1 - m;
@@ -543,62 +567,87 @@ cudaError_t chol_factor_dist(const std::vector<DistDev>& devs, long long ld, int
     for (size_t i = (size_t)i0; i < rows[g].size(); ++i) t += std::max(0, std::min(c1, rows[g][i] + 1) - c0);
     return t;
   };
-  std::vector<cudaEvent_t> evT(G, nullptr), evBulk(G, nullptr), evLA(G, nullptr);
-  cudaEvent_t evD = nullptr;
+  // events of the current step (per device): rows solved (T on the aux stream; the next owner's leading rows on its main stream),
+  // look-ahead update done, near / far parts of the wide update done
+  std::vector<cudaEvent_t> evT(G, nullptr), evLA(G, nullptr), evNear(G, nullptr);
+  cudaEvent_t evTfirst = nullptr, evD = nullptr;
   for (int q = 0; q < Q && err == cudaSuccess; ++q) {
     const int o = dist_owner(q, G);
     const int c0 = q * PB;
     const int nq = std::min(PB, nblocks - c0);
     const int cn = c0 + nq;  // first block below / right of the panel
-    // ---- D(q): the diagonal square on its owner.  It is up to date: LA(q-1) updated it on this stream.
+    // ---- D(q): the diagonal square on its owner (up to date: LA_sq(q-1) ran on this stream), then its diagonal blocks and inverses
+    // go to the other devices
     check(cudaSetDevice(devs[o].dev));
     ch[o].potrf(c0, nq, nullptr, 0);
+    ch[o].push_diag(c0, nq);
     check(ch[o].err);
     evD = (G > 1) ? record(o, devs[o].main) : nullptr;
     if (cn >= nblocks) break;
-    // ---- T(q): every device solves its own rows below the square (and multicasts them)
+    const int o1 = dist_owner(q + 1, G);
+    const int n1 = std::min(PB, nblocks - cn);      // width of panel q+1
+    const int cf = std::min(nblocks, cn + n1 + PB); // first block column of the far update (panel q+3 on)
+    // ---- T(q): every device solves its own rows below the square and multicasts them.  The rows of panel q+1 (on o1) are on the
+    // critical path - T_first, LA_sq, D(q+1) on o1's main stream -, everything else runs on the aux streams.
+    evTfirst = nullptr;
     for (int g = 0; g < G; ++g) {
-      const int i0 = first_at(g, cn), m = (int)rows[g].size() - i0;
+      const int i0 = first_at(g, cn);
+      int ia = i0;
       check(cudaSetDevice(devs[g].dev));
-      if (g != o && evD) check(cudaStreamWaitEvent(devs[g].main, evD, 0));
-      if (evLA[g]) check(cudaStreamWaitEvent(devs[g].main, evLA[g], 0));  // the rest of LA(q-1) ran on the aux stream
-      evLA[g] = nullptr;
-      ch[g].trsm_rows(devs[g].main, devs[g].rows + i0, m, c0, nq);
+      cudaStream_t sm = devs[g].main, sa = devs[g].aux;
+      if (g == o1) {
+        ia = first_at(g, cn + n1);
+        if (g != o && evD) check(cudaStreamWaitEvent(sm, evD, 0));
+        if (evLA[g]) check(cudaStreamWaitEvent(sm, evLA[g], 0));   // LA(q-1) updated these rows in column panel q (aux stream)
+        ch[g].trsm_rows(sm, devs[g].rows + i0, ia - i0, c0, nq);
+        evTfirst = record(g, sm);
+      }
+      const int m = (int)rows[g].size() - ia;
+      if (m > 0) {
+        if (evD) check(cudaStreamWaitEvent(sa, evD, 0));  // (same device: orders the aux stream after D on the main stream)
+        else if (g == o) check(cudaStreamWaitEvent(sa, record(g, sm), 0));
+        ch[g].trsm_rows(sa, devs[g].rows + ia, m, c0, nq);
+      }
+      evT[g] = record(g, sa);
       check(ch[g].err);
-      evT[g] = record(g, devs[g].main);
     }
-    // ---- LA(q) and B(q)
-    const int o1 = (q + 1 < Q) ? dist_owner(q + 1, G) : -1;
-    const int n1 = std::min(PB, nblocks - cn);  // width of panel q+1
+    // ---- LA(q): own rows x column panel q+1 with panel q;  near(q) / far(q): the columns of panel q+2 / of the panels from q+3 on
     for (int g = 0; g < G; ++g) {
       check(cudaSetDevice(devs[g].dev));
       const int i0 = first_at(g, cn);
-      const int m = (int)rows[g].size() - i0;
-      if (m <= 0) continue;
-      // LA needs the rows of panel q+1 in panel q (solved by o1) and everything B(q-1) did to column panel q+1
-      cudaStream_t sm = devs[g].main, sa = devs[g].aux;
-      if (g != o1 && G > 1) check(cudaStreamWaitEvent(sm, evT[o1], 0));
-      if (evBulk[g]) check(cudaStreamWaitEvent(sm, evBulk[g], 0));
-      int ia = i0;  // own rows from here on are updated on the aux stream
+      if ((int)rows[g].size() - i0 <= 0) continue;
+      cudaStream_t sm = devs[g].main, sa = devs[g].aux, su = devs[g].upd;
+      int ia = i0;
       if (g == o1) {
-        // the square of panel q+1 first, on the main stream: D(q+1) follows immediately
+        // the square of panel q+1 first, on the main stream: D(q+1) follows immediately.  Column panel q+1 was last touched by near(q-1).
         ia = first_at(g, cn + n1);
+        if (evNear[g]) check(cudaStreamWaitEvent(sm, evNear[g], 0));
         ch[g].update_rows(sm, devs[g].rows + i0, ia - i0, stair_tiles(g, i0, cn, cn + n1) - stair_tiles(g, ia, cn, cn + n1), cn, n1, c0, nq, true);
       }
       if ((int)rows[g].size() - ia > 0) {
-        cudaEvent_t e = record(g, sm);
-        check(cudaStreamWaitEvent(sa, e, 0));
+        // needs o1's rows of panel q (T_first) besides the own rows (aux stream order)
+        if (evTfirst) check(cudaStreamWaitEvent(sa, evTfirst, 0));
+        if (evNear[g]) check(cudaStreamWaitEvent(sa, evNear[g], 0));
         ch[g].update_rows(sa, devs[g].rows + ia, (int)rows[g].size() - ia, stair_tiles(g, ia, cn, cn + n1), cn, n1, c0, nq, true);
         evLA[g] = record(g, sa);
+      } else {
+        evLA[g] = nullptr;
       }
-      // B(q): columns of the panels >= q+2, needs every device's rows of panel q
       if (cn + n1 < nblocks) {
-        cudaStream_t su = devs[g].upd;
-        for (int h = 0; h < G; ++h) check(cudaStreamWaitEvent(su, evT[h], 0));
+        // near: besides the own rows it needs the rows of panel q+2 in panel q (solved on owner(q+2)'s aux stream)
+        check(cudaStreamWaitEvent(su, evT[g], 0));
+        if (q + 2 < Q) check(cudaStreamWaitEvent(su, evT[dist_owner(q + 2, G)], 0));
         const int ib = first_at(g, cn + n1);
-        ch[g].update_rows(su, devs[g].rows + ib, (int)rows[g].size() - ib, stair_tiles(g, ib, cn + n1, nblocks), cn + n1, nblocks - cn - n1, c0, nq,
-                          true);
-        evBulk[g] = record(g, su);
+        ch[g].update_rows(su, devs[g].rows + ib, (int)rows[g].size() - ib, stair_tiles(g, ib, cn + n1, cf), cn + n1, cf - cn - n1, c0, nq, true);
+        evNear[g] = record(g, su);
+        if (cf < nblocks) {
+          // far: needs every device's rows of panel q
+          for (int h = 0; h < G; ++h) check(cudaStreamWaitEvent(su, evT[h], 0));
+          const int ic = first_at(g, cf);
+          ch[g].update_rows(su, devs[g].rows + ic, (int)rows[g].size() - ic, stair_tiles(g, ic, cf, nblocks), cf, nblocks - cf, c0, nq, true);
+        }
+      } else {
+        evNear[g] = nullptr;
       }
       check(ch[g].err);
     }

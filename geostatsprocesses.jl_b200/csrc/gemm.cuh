@@ -209,6 +209,36 @@ __global__ void __launch_bounds__(GemmCfg<TM, TN, WM, WN>::THREADS, 1) gemm_dmma
   }
 
   // -------------------------------------------------------------- epilogue
+  if (MODE == GEMM_SET && g.npeer > 0) {
+    // Multicast epilogue (distributed factorization: the solved panel rows go into every device's matrix).  The tile is staged in
+    // the operand ring - free now: one tile per CTA (launch_gemm_cfg guarantees it when npeer > 0), every chunk consumed once the
+    // consumer warps meet at the barrier - and leaves as whole columns: 16 bytes per lane, TM*8 contiguous bytes per store
+    // instruction and destination, which is what NVLink wants (the fragment layout would give 64-byte pieces).
+    constexpr int LDS = TM + 4;
+    static_assert(TN * LDS * 8 <= GSTAGES * C_::STAGE_BYTES, "staging tile must fit the operand ring");
+    double* S = reinterpret_cast<double*>(stage_base);
+    named_bar_sync(1, CW * 32);
+    const int r0s = wm * (TM / WM) + lr, c0s = wn * (TN / WN) + 2 * lk;
+#pragma unroll
+    for (int a = 0; a < FM; ++a)
+#pragma unroll
+      for (int b = 0; b < FN; ++b) {
+        S[(c0s + b * 8) * LDS + r0s + a * 8] = acc[a][b][0];
+        S[(c0s + b * 8 + 1) * LDS + r0s + a * 8] = acc[a][b][1];
+      }
+    named_bar_sync(1, CW * 32);
+    const long long rbase = rowoff(ti), cbase = (long long)tj * TN;
+    for (int c = warp; c < TN; c += CW) {
+#pragma unroll
+      for (int h = 0; h < TM / 64; ++h) {
+        const double2 v = *reinterpret_cast<const double2*>(S + c * LDS + h * 64 + 2 * lane);
+        const long long off = rbase + h * 64 + 2 * lane + (cbase + c) * g.ldc;
+        *reinterpret_cast<double2*>(g.C + off) = v;
+        for (int p = 0; p < g.npeer; ++p) *reinterpret_cast<double2*>(g.Cpeer[p] + off) = v;
+      }
+    }
+    continue;
+  }
 #pragma unroll
   for (int a = 0; a < FM; ++a) {
     const long long i = row0 + a * 8;
@@ -218,10 +248,6 @@ __global__ void __launch_bounds__(GemmCfg<TM, TN, WM, WN>::THREADS, 1) gemm_dmma
       if (MODE == GEMM_SET) {
         g.C[i + j * g.ldc] = acc[a][b][0];
         g.C[i + (j + 1) * g.ldc] = acc[a][b][1];
-        for (int p = 0; p < g.npeer; ++p) {  // multicast over NVLink: 8 lanes cover 64 contiguous bytes of a column
-          g.Cpeer[p][i + j * g.ldc] = acc[a][b][0];
-          g.Cpeer[p][i + (j + 1) * g.ldc] = acc[a][b][1];
-        }
       } else if (MODE == GEMM_SUB) {
         g.C[i + j * g.ldc] = acc[a][b][0];
         g.C[i + (j + 1) * g.ldc] = acc[a][b][1];
@@ -255,6 +281,7 @@ inline cudaError_t launch_gemm_cfg(cudaStream_t st, const GemmArgs& g0) {
     force_ctas = env ? atoi(env) : 0;
   }
   if (force_ctas > 0) g.max_ctas = force_ctas;
+  if (g.npeer > 0) g.max_ctas = 0;  // the multicast epilogue stages its tile in the operand ring: one tile per CTA
   const long long grid = (g.max_ctas > 0 && g.max_ctas < tiles) ? g.max_ctas : tiles;
   ProfScope prof_(MODE == GEMM_SAMPLE ? "gemm_dmma_sample" : (MODE == GEMM_SET ? "gemm_dmma_trsm" : "gemm_dmma_update"), st);
   GSP_LAUNCH(kfn, dim3((unsigned)grid), dim3(C_::THREADS), (size_t)C_::SMEM_BYTES, st, g);

@@ -172,6 +172,15 @@ GSP_DEV void tma_load_3d(void* dst, const TensorMap* tm, int c0, int c1, int c2,
 int make_tensor_map_f64(TensorMap* out, const void* base, const unsigned long long dims[3], unsigned long long stride1_bytes,
                         unsigned long long stride2_bytes, const unsigned box[3]);
 
+// named barrier over `count` threads of the CTA (a subset of warps, e.g. the consumer warps of a producer/consumer kernel)
+GSP_DEV void named_bar_sync(int id, int count) {
+#ifdef GSP_EMU
+  emu::named_bar_sync(id, count);
+#else
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+#endif
+}
+
 // inter-CTA flags in global memory (persistent kernels): release after the CTA's stores, acquire before dependent loads
 GSP_DEV void spin_pause() {
 #ifdef GSP_EMU

@@ -387,11 +387,12 @@ extern "C" int gsp_potrf(gsp_ctx* ctx, int64_t n, double* A) {
   GSP_CUDA_OK(ctx, cudaMemcpyAsync(dA.p, pad.data(), pad.size() * sizeof(double), cudaMemcpyHostToDevice, dc.stream));
   const char* algo = getenv("GSP_CHOL_ALGO");
   if (algo && algo[0] == 'p') {  // the panel algorithm of the distributed factorization, on this one device
-    DevBuf rows;
+    DevBuf rows, flags;
     GSP_CUDA_OK(ctx, rows.alloc(dc.dev, (size_t)nb * sizeof(int)));
+    GSP_CUDA_OK(ctx, flags.alloc(dc.dev, (size_t)chol_dist_flag_ints() * sizeof(int)));
     const int pb_env = getenv("GSP_CHOL_PB") ? atoi(getenv("GSP_CHOL_PB")) : 0;
-    std::vector<DistDev> dv{DistDev{dc.dev, dc.stream, dc.aux, dc.side[0], dA.as<double>(), dinv.as<double>(), dinfo.as<int>(), rows.as<int>()}};
-    GSP_CUDA_OK(ctx, chol_factor_dist(dv, np, nb, std::min(nb, pb_env > 0 ? pb_env : 4)));
+    std::vector<DistDev> dv{DistDev{dc.dev, dc.stream, dc.aux, dc.side[0], dA.as<double>(), dinv.as<double>(), dinfo.as<int>(), rows.as<int>(), flags.as<int>()}};
+    GSP_CUDA_OK(ctx, chol_factor_dist(dv, np, nb, std::min(nb, pb_env > 0 ? std::min(pb_env, 8) : 4)));
   } else {
     GSP_CUDA_OK(ctx, chol_factor(dc.stream, dc.side, DevCtx::kSide, dA.as<double>(), np, nb, dinv.as<double>(), dinfo.as<int>()));
   }

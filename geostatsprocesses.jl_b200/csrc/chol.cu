@@ -82,9 +82,7 @@ GSP_DEV double frag_b(const double* S, int k0, int c0, int lane) { return S[(c0 
 // shared memory:  (U) panel -= L[:, :c0] * L[c0:c0+16, :c0]^T   (F) warp 0 factors and inverts the 16x16 block in registers
 // (S) rows below = panel * inv(L16)^T.  The inverse of the whole block is then assembled from the eight 16x16 inverses by
 // X21 = -inv(C) * B * inv(A) over 16 -> 32 -> 64 wide halves, again on DMMA tiles (one 8-row block per warp and level).
-__global__ void __launch_bounds__(256, 1) potrf_diag_kernel(double* __restrict__ A, long long lda, long long blk,
-                                                            double* __restrict__ invD, int* __restrict__ info) {
-  GSP_DYN_SMEM(smem);
+GSP_DEV void potrf_diag_body(double* A, long long lda, long long blk, double* invD, int* info, unsigned char* smem) {
   double* S = reinterpret_cast<double*>(smem);   // [DB cols][DLD]
   double* Dv = S + DB * DLD;                     // [8 panels][16 k][DVL]: Dv[p][k * DVL + n] = inv(L16_p)[n][k]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -262,20 +260,148 @@ __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(double* __restrict__
   }
 }
 
-// Distributed factorization: the nq diagonal blocks of a finished square and their inverses go to the other devices (the
-// off-diagonal blocks of the square are multicast by the TRSM leaves that produce them).  One CTA per 16 columns of a block:
-// a single CTA storing 1.8 MB over NVLink from potrf_diag_kernel itself cost 30 us per block on the critical path.
-__global__ void __launch_bounds__(256) push_diag_kernel(const double* __restrict__ A, long long lda, long long blk0, const double* __restrict__ invD,
-                                                        const GSP_GRID_CONSTANT DiagPeers peers) {
-  const int k = blockIdx.x / 8, part = blockIdx.x % 8;
-  const long long blk = blk0 + k;
-  const int tid = threadIdx.x;
-  // 16 columns x 128 rows of L and of the inverse: 2 x 1024 double2 per CTA
-  for (int idx = tid; idx < 2 * 16 * 64; idx += 256) {
-    const int which = idx >> 10, e = idx & 1023, c = part * 16 + (e >> 6), r2 = (e & 63) * 2;
-    const long long off = which ? blk * DB * DB + r2 + (long long)c * DB : blk * DB * (lda + 1) + r2 + (long long)c * lda;
-    const double2 v = *reinterpret_cast<const double2*>((which ? invD : A) + off);
-    for (int p = 0; p < peers.n; ++p) *reinterpret_cast<double2*>((which ? peers.invD[p] : peers.A[p]) + off) = v;
+__global__ void __launch_bounds__(256, 1) potrf_diag_kernel(double* __restrict__ A, long long lda, long long blk,
+                                                            double* __restrict__ invD, int* __restrict__ info) {
+  GSP_DYN_SMEM(smem);
+  potrf_diag_body(A, lda, blk, invD, info, smem);
+}
+
+// ------------------------------------------------------------------ fused diagonal square (the panel head of chol_factor_dist)
+// Cholesky of the nq x nq-block square at block (blk0, blk0) in ONE launch: 2 CTAs per block row (64-row strips), each walks the
+// columns of its row - S: X_ij = A_ij inv(L_jj)^T, U: A_il -= X_ij X_lj^T for j < l <= i - and the upper CTA of a row then factors
+// and inverts its diagonal block (potrf_diag_body).  CTAs synchronise through release / acquire flags in global memory (the whole
+// square is 2 MB and L2-resident): P[j] = diagonal block j done, S[i][j] = strips of X_ij done, H[i] = lower strip of row i final.
+// 12 dependent launches (4 diagonal blocks, 4 solves, 4 updates at PB = 4, 30-40 us each next to the wide updates) become one
+// kernel whose critical path is the four diagonal blocks plus six 10 us strip products.
+constexpr int SQ_MAXB = 8;                                   // blocks per square side
+constexpr int SQ_LDA = 64 + 4, SQ_LDB = DB + 4;              // strip and operand tiles in shared memory, k-major: T[k * LD + r]
+constexpr int SQ_SMEM = (DB * SQ_LDA + DB * SQ_LDB) * 8;     // 204.8 KB (potrf_diag_body overlays it with its 155 KB)
+constexpr int SQ_FLAGS = SQ_MAXB + SQ_MAXB * SQ_MAXB + SQ_MAXB;
+
+GSP_DEV void sq_wait(const int* f, int v) {
+  if (threadIdx.x == 0)
+    while (ld_acquire_gpu(f) < v) spin_pause();
+  __syncthreads();
+}
+GSP_DEV void sq_signal(int* f) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#ifndef GSP_EMU
+    __threadfence();
+#endif
+    red_release_gpu_add(f, 1);
+  }
+}
+
+// C(64 x 128) = Aop(64 x 128) * B(128 x 128)^T  (SUB: C -= ...), column-major operands in global memory, one CTA of 8 warps;
+// warp w owns rows 8w..8w+7.  C may alias Aop (the strip is staged in shared memory before anything is stored).
+template <bool SUB>
+GSP_DEV void sq_strip_gemm(double* C, long long ldc, const double* Aop, long long lda, const double* B, long long ldb, unsigned char* smem) {
+  double* As = reinterpret_cast<double*>(smem);
+  double* Bs = As + DB * SQ_LDA;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, lr = lane >> 2, lk = lane & 3;
+  __syncthreads();  // the previous task's readers of the tiles are done
+  for (int base = 0; base < 64 * DB; base += 8 * 256) {
+    double v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int idx = base + u * 256 + tid;
+      v[u] = Aop[(idx & 63) + (long long)(idx >> 6) * lda];
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int idx = base + u * 256 + tid;
+      As[(idx >> 6) * SQ_LDA + (idx & 63)] = v[u];
+    }
+  }
+  for (int base = 0; base < DB * DB; base += 16 * 256) {
+    double v[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int idx = base + u * 256 + tid;
+      v[u] = B[(idx & (DB - 1)) + (long long)(idx >> 7) * ldb];
+    }
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int idx = base + u * 256 + tid;
+      Bs[(idx >> 7) * SQ_LDB + (idx & (DB - 1))] = v[u];
+    }
+  }
+  double acc[16][2];
+  double* crow = C + 8 * warp + lr + (long long)(2 * lk) * ldc;
+#pragma unroll
+  for (int nb = 0; nb < 16; ++nb) {
+    acc[nb][0] = SUB ? crow[(long long)(nb * 8) * ldc] : 0.0;
+    acc[nb][1] = SUB ? crow[(long long)(nb * 8 + 1) * ldc] : 0.0;
+  }
+  __syncthreads();
+  for (int k0 = 0; k0 < DB; k0 += 4) {
+    const double av = As[(k0 + lk) * SQ_LDA + 8 * warp + lr];
+    const double a = SUB ? -av : av;
+    const double* bp = Bs + (k0 + lk) * SQ_LDB + lr;
+#pragma unroll
+    for (int nb = 0; nb < 16; ++nb) dmma884(acc[nb][0], acc[nb][1], a, bp[nb * 8]);
+  }
+#pragma unroll
+  for (int nb = 0; nb < 16; ++nb) {
+    crow[(long long)(nb * 8) * ldc] = acc[nb][0];
+    crow[(long long)(nb * 8 + 1) * ldc] = acc[nb][1];
+  }
+}
+
+__global__ void __launch_bounds__(256, 1) potrf_square_kernel(double* A, long long lda, long long blk0, int nq, double* invD, int* info,
+                                                              int* flags) {
+  GSP_DYN_SMEM(smem);
+  const int i = blockIdx.x >> 1, h = blockIdx.x & 1;
+  int* Pf = flags;
+  int* Sf = flags + SQ_MAXB;
+  int* Hf = flags + SQ_MAXB + SQ_MAXB * SQ_MAXB;
+  const long long rbase = (blk0 + i) * DB + 64 * h;
+  for (int j = 0; j < i; ++j) {
+    double* Xij = A + rbase + (blk0 + j) * DB * lda;
+    sq_wait(&Pf[j], 1);
+    sq_strip_gemm<false>(Xij, lda, Xij, lda, invD + (blk0 + j) * DB * DB, DB, smem);
+    sq_signal(&Sf[i * SQ_MAXB + j]);
+    for (int l = j + 1; l <= i; ++l) {
+      sq_wait(&Sf[l * SQ_MAXB + j], 2);
+      sq_strip_gemm<true>(A + rbase + (blk0 + l) * DB * lda, lda, Xij, lda, A + (blk0 + l) * DB + (blk0 + j) * DB * lda, lda, smem);
+    }
+  }
+  if (h == 1) {
+    sq_signal(&Hf[i]);
+    return;
+  }
+  sq_wait(&Hf[i], 1);
+  potrf_diag_body(A, lda, blk0 + i, invD, info, smem);
+  sq_signal(&Pf[i]);
+}
+
+// Distributed factorization: the lower blocks of a finished square and the inverses of its diagonal blocks go to the other devices.
+// One CTA per 16 columns of a block (a single CTA storing 1.8 MB over NVLink from the factorizing kernel itself cost 30 us per
+// diagonal block on the critical path).
+__global__ void __launch_bounds__(256) push_square_kernel(const double* __restrict__ A, long long lda, long long blk0, int nq,
+                                                          const double* __restrict__ invD, const GSP_GRID_CONSTANT DiagPeers peers) {
+  const int item = blockIdx.x / 8, part = blockIdx.x % 8, tid = threadIdx.x;
+  long long off0, ldx;
+  const double* src;
+  bool inv = item < nq;
+  if (inv) {
+    off0 = (blk0 + item) * DB * DB;
+    ldx = DB;
+    src = invD;
+  } else {
+    int t = item - nq, bi = 0;
+    while ((bi + 1) * (bi + 2) / 2 <= t) ++bi;
+    const int bj = t - bi * (bi + 1) / 2;
+    off0 = (blk0 + bi) * DB + (blk0 + bj) * DB * lda;
+    ldx = lda;
+    src = A;
+  }
+  for (int idx = tid; idx < 16 * 64; idx += 256) {
+    const int c = part * 16 + (idx >> 6), r2 = (idx & 63) * 2;
+    const long long off = off0 + r2 + (long long)c * ldx;
+    const double2 v = *reinterpret_cast<const double2*>(src + off);
+    for (int p = 0; p < peers.n; ++p) *reinterpret_cast<double2*>((inv ? peers.invD[p] : peers.A[p]) + off) = v;
   }
 }
 
@@ -419,12 +545,27 @@ struct Chol {
     trsm_rows(s, rows_dev, nrows, c0 + c1, nc - c1);
   }
 
-  void push_diag(int o, int n) {
-    if (peers.n <= 0 || n <= 0) return;
-    ProfScope prof_("push_diag", st);
-    GSP_LAUNCH(push_diag_kernel, dim3((unsigned)(8 * n)), dim3(256), 0, st, (const double*)A, ld, (long long)o, (const double*)invD, peers);
-    g_launches++;
-    check(cudaGetLastError());
+  // the whole diagonal square [o, o + n) in one launch (potrf_square_kernel), then its blocks and inverses to the other devices
+  void square(int o, int n, int* flags) {
+    if (n <= 0) return;
+    if (n == 1) {
+      potrf(o, 1, nullptr, 0);
+    } else {
+      check(cudaMemsetAsync(flags, 0, SQ_FLAGS * sizeof(int), st));
+      auto kfn = potrf_square_kernel;
+      check(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, SQ_SMEM));
+      ProfScope prof_("potrf_square", st);
+      GSP_LAUNCH_COOP(kfn, dim3((unsigned)(2 * n)), dim3(256), (size_t)SQ_SMEM, st, A, ld, (long long)o, n, invD, info, flags);
+      g_launches++;
+      check(cudaGetLastError());
+    }
+    if (peers.n > 0) {
+      ProfScope prof_("push_square", st);
+      GSP_LAUNCH(push_square_kernel, dim3((unsigned)(8 * (n + n * (n + 1) / 2))), dim3(256), 0, st, (const double*)A, ld, (long long)o, n,
+                 (const double*)invD, peers);
+      g_launches++;
+      check(cudaGetLastError());
+    }
   }
 
   // Cholesky of the n diagonal blocks starting at o.  `pend`: event after which the second half [o + n/2, o + n) of the
@@ -508,6 +649,8 @@ cudaError_t chol_factor(cudaStream_t st, cudaStream_t* side, int nside, double* 
 // LA(q+1) waits for near(q) only, which is queued before far(q): a look-ahead of depth two - the critical path never waits for
 // the wide update of the current or the previous step.  The panel solve and the updates are split G ways by construction; the
 // wide updates are launches of short (K = PB*128) tiles that the high-priority kernels pre-empt at tile granularity.
+int chol_dist_flag_ints() { return SQ_FLAGS; }
+
 static int dist_owner(int p, int G) {
   const int m = p % (2 * G);
   return m < G ? m : 2 * G - 1 - m;
@@ -567,6 +710,12 @@ cudaError_t chol_factor_dist(const std::vector<DistDev>& devs, long long ld, int
     for (size_t i = (size_t)i0; i < rows[g].size(); ++i) t += std::max(0, std::min(c1, rows[g][i] + 1) - c0);
     return t;
   };
+  // the callers' earlier work on the main streams (assembly of the own rows) precedes everything on the other two streams
+  for (int g = 0; g < G; ++g) {
+    cudaEvent_t e = record(g, devs[g].main);
+    check(cudaStreamWaitEvent(devs[g].aux, e, 0));
+    check(cudaStreamWaitEvent(devs[g].upd, e, 0));
+  }
   // events of the current step (per device): rows solved (T on the aux stream; the next owner's leading rows on its main stream),
   // look-ahead update done, near / far parts of the wide update done
   std::vector<cudaEvent_t> evT(G, nullptr), evLA(G, nullptr), evNear(G, nullptr);
@@ -579,8 +728,19 @@ cudaError_t chol_factor_dist(const std::vector<DistDev>& devs, long long ld, int
     // ---- D(q): the diagonal square on its owner (up to date: LA_sq(q-1) ran on this stream), then its diagonal blocks and inverses
     // go to the other devices
     check(cudaSetDevice(devs[o].dev));
-    ch[o].potrf(c0, nq, nullptr, 0);
-    ch[o].push_diag(c0, nq);
+    static const int fused = env_int("GSP_CHOL_FUSED_SQUARE", 1);  // 0: the recursion of separate launches (A/B)
+    if (fused && nq <= SQ_MAXB) {
+      ch[o].square(c0, nq, devs[o].flags);
+    } else {
+      ch[o].potrf(c0, nq, nullptr, 0);
+      if (ch[o].peers.n > 0) {
+        ProfScope prof_("push_square", devs[o].main);
+        GSP_LAUNCH(push_square_kernel, dim3((unsigned)(8 * (nq + nq * (nq + 1) / 2))), dim3(256), 0, devs[o].main, (const double*)devs[o].A, ld,
+                   (long long)c0, nq, (const double*)devs[o].invD, ch[o].peers);
+        g_launches++;
+        check(cudaGetLastError());
+      }
+    }
     check(ch[o].err);
     evD = (G > 1) ? record(o, devs[o].main) : nullptr;
     if (cn >= nblocks) break;

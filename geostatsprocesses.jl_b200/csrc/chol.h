@@ -21,7 +21,7 @@ struct DiagPeers {
 };
 // Panel factorization over the G >= 1 devices of a context with row-panel ownership (chol.cu).  Every device holds a full
 // (nblocks*128)^2 buffer `A` in which the block rows it owns (chol_dist_owned_rows) are assembled; on return every device holds the
-// whole factor and all block inverses.  `rows`: device scratch of nblocks ints.  main / aux: high-priority streams, upd: low priority.
+// whole factor and all block inverses.  `rows`: device scratch of nblocks ints, `flags`: chol_dist_flag_ints() ints.  main / aux: high-priority streams, upd: low priority.
 struct DistDev {
   int dev;
   cudaStream_t main, aux, upd;
@@ -29,7 +29,9 @@ struct DistDev {
   double* invD;
   int* info;
   int* rows;
+  int* flags;  // chol_dist_flag_ints() ints: inter-CTA flags of the fused diagonal-square kernel
 };
+int chol_dist_flag_ints();
 void chol_dist_owned_rows(int nblocks, int PB, int G, int g, std::vector<int>* rows);
 cudaError_t chol_factor_dist(const std::vector<DistDev>& devs, long long ld, int nblocks, int PB);
 // z[0 : nblocks*128] <- L^{-1} z  for the leading nblocks diagonal blocks

@@ -63,6 +63,7 @@ struct LuDev {
   DevBuf A;       // Np x Np joint matrix -> L
   DevBuf invD;    // inverses of the diagonal 128-blocks
   DevBuf rows;    // block rows this device owns (distributed factorization)
+  DevBuf flags;   // inter-CTA flags of the fused diagonal-square kernel
   DevBuf d2;      // Ns_pad
   DevBuf sinds;   // Ns (0-based)
   DevBuf dinds;   // Nd (0-based)
@@ -228,7 +229,7 @@ CholChoice choose_chol(int ndev, int nb) {
   if (algo && algo[0] == 'r') c.dist = false;
   else if (algo && algo[0] == 'p') c.dist = true;
   else c.dist = ndev > 1 ? nb >= min_blocks : nb >= min_blocks_1;  // one device: measured C3 51.9 vs 59.4 ms, 32k nodes 359 vs 367 ms
-  c.PB = pb_env > 0 ? pb_env : 4;
+  c.PB = pb_env > 0 ? std::min(pb_env, 8) : 4;
   if (c.PB > nb) c.PB = nb;
   return c;
 }
@@ -326,6 +327,7 @@ extern "C" int gsp_lu_plan_create(gsp_ctx* ctx, const gsp_cov_model* cov, const 
     GSP_CUDA_OK(ctx, d->invD.alloc(dc.dev, (size_t)nb * 128 * 128 * sizeof(double), st));
     if (i >= nbuild) continue;
     GSP_CUDA_OK(ctx, d->rows.alloc(dc.dev, (size_t)nb * sizeof(int), st));
+    GSP_CUDA_OK(ctx, d->flags.alloc(dc.dev, (size_t)chol_dist_flag_ints() * sizeof(int), st));
     DevBuf dperm, dcoords;
     GSP_CUDA_OK(ctx, dperm.alloc(dc.dev, (size_t)p->Np * sizeof(long long), st));
     GSP_CUDA_OK(ctx, cudaMemcpyAsync(dperm.p, perm.data(), perm.size() * sizeof(long long), cudaMemcpyHostToDevice, st));
@@ -362,7 +364,7 @@ extern "C" int gsp_lu_plan_create(gsp_ctx* ctx, const gsp_cov_model* cov, const 
     for (int i = 0; i < nbuild; ++i) {
       LuDev* d = p->dev[i].get();
       dv.push_back(DistDev{d->dc->dev, d->dc->stream, d->dc->aux, d->dc->side[0], d->A.as<double>(), d->invD.as<double>(), d->info.as<int>(),
-                           d->rows.as<int>()});
+                           d->rows.as<int>(), d->flags.as<int>()});
     }
     GSP_CUDA_OK(ctx, chol_factor_dist(dv, p->Np, nb, cc.PB));
     cudaSetDevice(dc.dev);

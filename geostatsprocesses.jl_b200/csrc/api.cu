@@ -258,6 +258,12 @@ extern "C" int gsp_ctx_create(int32_t ndev, const int32_t* devs, gsp_ctx** out) 
         // stream-ordered pool memory is not covered by cudaDeviceEnablePeerAccess: device a may map what b's pool hands out
         cudaMemPool_t pool = nullptr;
         if (cudaDeviceGetDefaultMemPool(&pool, b.dev) == cudaSuccess && pool) {
+          // blocks an earlier context of this process left cached in the pool are released first: granting peer access on a pool
+          // that held ~20 GB of cached blocks was followed by "out of memory" on the next 2 GB request (170 GB free)
+          cudaSetDevice(b.dev);
+          cudaDeviceSynchronize();
+          cudaMemPoolTrimTo(pool, 0);
+          cudaSetDevice(a.dev);
           cudaMemAccessDesc desc{};
           desc.location.type = cudaMemLocationTypeDevice;
           desc.location.id = a.dev;

@@ -71,12 +71,21 @@ struct gsp_ctx {
 namespace gsp {
 
 int set_err(gsp_ctx* ctx, int code, const std::string& msg);
+// " [device d: x of y MiB free]" when the failure is an allocation (which device ran out, and by how much)
+inline std::string mem_note(cudaError_t e) {
+  if (e != cudaErrorMemoryAllocation) return "";
+  int dev = 0;
+  size_t fr = 0, tot = 0;
+  cudaGetLastError();
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaMemGetInfo(&fr, &tot) != cudaSuccess) return "";
+  return " [device " + std::to_string(dev) + ": " + std::to_string(fr >> 20) + " of " + std::to_string(tot >> 20) + " MiB free]";
+}
 
 #define GSP_CUDA_OK(ctx, expr)                                                                          \
   do {                                                                                                  \
     cudaError_t e_ = (expr);                                                                            \
     if (e_ != cudaSuccess)                                                                              \
-      return ::gsp::set_err((ctx), GSP_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));     \
+      return ::gsp::set_err((ctx), GSP_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_) + ::gsp::mem_note(e_)); \
   } while (0)
 
 #define GSP_TRY(expr)            \
@@ -94,6 +103,7 @@ struct DevBuf {
   size_t bytes = 0;
   int dev = 0;
   cudaStream_t owner = nullptr;  // stream every use of the block is ordered on (or joined into) - see release()
+  bool pooled = true;            // false: the block came from cudaMalloc (fallback, see alloc)
   DevBuf() = default;
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
@@ -104,9 +114,32 @@ struct DevBuf {
     release();
     dev = device;
     owner = st;
+    pooled = true;
     cudaSetDevice(dev);
     cudaError_t e = cudaMallocAsync(&p, n ? n : 16, (cudaStream_t)0);
     if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)0);
+#ifndef GSP_EMU
+    if (e == cudaErrorMemoryAllocation) {
+      // Seen on a 2-GPU box with > 170 GB free: the pool refused a 2 GB block right after peer access had been granted on a pool
+      // that held ~20 GB of cached blocks.  Hand the cache back and retry; then fall back to a plain cudaMalloc (peer access to
+      // it comes from cudaDeviceEnablePeerAccess).
+      cudaGetLastError();
+      cudaMemPool_t pool = nullptr;
+      if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess && pool) {
+        cudaDeviceSynchronize();
+        cudaMemPoolTrimTo(pool, 0);
+      }
+      p = nullptr;
+      e = cudaMallocAsync(&p, n ? n : 16, (cudaStream_t)0);
+      if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)0);
+      if (e == cudaErrorMemoryAllocation) {
+        cudaGetLastError();
+        p = nullptr;
+        pooled = false;
+        e = cudaMalloc(&p, n ? n : 16);
+      }
+    }
+#endif
     if (e == cudaSuccess) bytes = n;
     else p = nullptr;
     return e;
@@ -114,7 +147,9 @@ struct DevBuf {
   void release() {
     if (p) {
       cudaSetDevice(dev);
-      if (owner) {
+      if (!pooled) {
+        cudaFree(p);  // synchronises the device
+      } else if (owner) {
         cudaFreeAsync(p, owner);
       } else {
         cudaDeviceSynchronize();

@@ -54,6 +54,7 @@ static inline cudaError_t cudaMalloc(void** p, size_t n) { *p = std::malloc(n ? 
 template <class T> static inline cudaError_t cudaMalloc(T** p, size_t n) { return cudaMalloc((void**)p, n); }
 static inline cudaError_t cudaFree(void* p) { std::free(p); return cudaSuccess; }
 static inline cudaError_t cudaMallocAsync(void** p, size_t n, cudaStream_t) { return cudaMalloc(p, n); }
+static inline cudaError_t cudaMemGetInfo(size_t* fr, size_t* tot) { *fr = *tot = 0; return cudaSuccess; }
 static inline cudaError_t cudaFreeAsync(void* p, cudaStream_t) { return cudaFree(p); }
 static inline cudaError_t cudaMallocHost(void** p, size_t n) { return cudaMalloc(p, n); }
 static inline cudaError_t cudaFreeHost(void* p) { std::free(p); return cudaSuccess; }

@@ -232,7 +232,7 @@ extern "C" int gsp_ctx_create(int32_t ndev, const int32_t* devs, gsp_ctx** out) 
 #endif
     if (e == cudaSuccess) e = cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&dc.stream, cudaStreamNonBlocking, prio_hi);
-    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&dc.aux, cudaStreamNonBlocking, prio_hi);
+    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&dc.aux, cudaStreamNonBlocking, (prio_hi + prio_lo) / 2);  // between the chain and the wide updates
     for (int k = 0; k < DevCtx::kSide && e == cudaSuccess; ++k) e = cudaStreamCreateWithPriority(&dc.side[k], cudaStreamNonBlocking, prio_lo);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&dc.h2d, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&dc.d2h, cudaStreamNonBlocking);

@@ -405,6 +405,19 @@ __global__ void __launch_bounds__(256) push_square_kernel(const double* __restri
   }
 }
 
+// blocks (r0 + i, c0 + j), i < nr, of the matrix -> the same position on the other devices; one CTA per 16 columns of a block
+__global__ void __launch_bounds__(256) push_rect_kernel(const double* __restrict__ A, long long lda, long long r0, int nr, long long c0,
+                                                        const GSP_GRID_CONSTANT DiagPeers peers) {
+  const int item = blockIdx.x / 8, part = blockIdx.x % 8, tid = threadIdx.x;
+  const long long off0 = (r0 + item % nr) * DB + (c0 + item / nr) * DB * lda;
+  for (int idx = tid; idx < 16 * 64; idx += 256) {
+    const int c = part * 16 + (idx >> 6), r2 = (idx & 63) * 2;
+    const long long off = off0 + r2 + (long long)c * lda;
+    const double2 v = *reinterpret_cast<const double2*>(A + off);
+    for (int p = 0; p < peers.n; ++p) *reinterpret_cast<double2*>(peers.A[p] + off) = v;
+  }
+}
+
 // y = L11^{-1} z for the leading nb x nb blocks (forward substitution by 128-blocks using invD):
 // y_b = invD_b * (z_b - sum_{j<b} L[b][j] y_j).  One CTA; z is overwritten by y.
 __global__ void __launch_bounds__(256, 1) trsv_blocks_kernel(const double* __restrict__ L, long long ld,
@@ -526,7 +539,7 @@ struct Chol {
     g.rows = rows_dev; g.stair = stair ? 1 : 0; g.colblk0 = ccol0;
     check(launch_gemm<GEMM_SUB, false>(s, g, valid_tiles));
   }
-  void trsm_rows(cudaStream_t s, const int* rows_dev, int nrows, int c0, int nc) {
+  void trsm_rows(cudaStream_t s, const int* rows_dev, int nrows, int c0, int nc, bool multicast = true) {
     if (nrows <= 0 || nc <= 0) return;
     if (nc == 1) {
       GemmArgs g{};
@@ -535,14 +548,22 @@ struct Chol {
       g.C = A + (long long)c0 * DB * ld; g.ldc = ld;
       g.mt = nrows; g.nt = 1; g.K = DB;
       g.rows = rows_dev;
-      set_peers(g, (long long)c0 * DB * ld);
+      if (multicast) set_peers(g, (long long)c0 * DB * ld);
       check(launch_gemm<GEMM_SET, false>(s, g));
       return;
     }
     const int c1 = nc / 2;
-    trsm_rows(s, rows_dev, nrows, c0, c1);
+    trsm_rows(s, rows_dev, nrows, c0, c1, multicast);
     update_rows(s, rows_dev, nrows, (long long)nrows * (nc - c1), c0 + c1, nc - c1, c0, c1, false);
-    trsm_rows(s, rows_dev, nrows, c0 + c1, nc - c1);
+    trsm_rows(s, rows_dev, nrows, c0 + c1, nc - c1, multicast);
+  }
+  // blocks [r0, r0 + nr) x [c0, c0 + nc) of the matrix to the other devices (many CTAs: one SM's peer stores are slow)
+  void push_rect(cudaStream_t s, int r0, int nr, int c0, int nc) {
+    if (peers.n <= 0 || nr <= 0 || nc <= 0) return;
+    ProfScope prof_("push_rect", s);
+    GSP_LAUNCH(push_rect_kernel, dim3((unsigned)(8 * nr * nc)), dim3(256), 0, s, (const double*)A, ld, (long long)r0, nr, (long long)c0, peers);
+    g_launches++;
+    check(cudaGetLastError());
   }
 
   // the whole diagonal square [o, o + n) in one launch (potrf_square_kernel), then its blocks and inverses to the other devices
@@ -759,8 +780,13 @@ cudaError_t chol_factor_dist(const std::vector<DistDev>& devs, long long ld, int
         ia = first_at(g, cn + n1);
         if (g != o && evD) check(cudaStreamWaitEvent(sm, evD, 0));
         if (evLA[g]) check(cudaStreamWaitEvent(sm, evLA[g], 0));   // LA(q-1) updated these rows in column panel q (aux stream)
-        ch[g].trsm_rows(sm, devs[g].rows + i0, ia - i0, c0, nq);
-        evTfirst = record(g, sm);
+        // solved locally on the main stream (LA_sq and D(q+1) only need them here); the copy for the other devices' look-ahead
+        // updates leaves from the aux stream, off the critical path
+        ch[g].trsm_rows(sm, devs[g].rows + i0, ia - i0, c0, nq, false);
+        cudaEvent_t solved = record(g, sm);
+        check(cudaStreamWaitEvent(sa, solved, 0));
+        ch[g].push_rect(sa, cn, n1, c0, nq);
+        evTfirst = record(g, sa);
       }
       const int m = (int)rows[g].size() - ia;
       if (m > 0) {

@@ -50,7 +50,7 @@ struct ProfScope {
 struct DevCtx {
   int dev = 0;
   cudaStream_t stream = nullptr;   // compute (highest priority: carries the critical path)
-  cudaStream_t aux = nullptr;      // second high-priority stream (look-ahead updates next to the panel chain)
+  cudaStream_t aux = nullptr;      // medium priority: panel solves and look-ahead updates next to the panel chain
   cudaStream_t h2d = nullptr;      // copy-in
   cudaStream_t d2h = nullptr;      // copy-out
   static constexpr int kSide = 8;

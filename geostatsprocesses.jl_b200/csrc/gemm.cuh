@@ -228,14 +228,12 @@ __global__ void __launch_bounds__(GemmCfg<TM, TN, WM, WN>::THREADS, 1) gemm_dmma
       }
     named_bar_sync(1, CW * 32);
     const long long rbase = rowoff(ti), cbase = (long long)tj * TN;
-    for (int c = warp; c < TN; c += CW) {
-#pragma unroll
-      for (int h = 0; h < TM / 64; ++h) {
-        const double2 v = *reinterpret_cast<const double2*>(S + c * LDS + h * 64 + 2 * lane);
-        const long long off = rbase + h * 64 + 2 * lane + (cbase + c) * g.ldc;
-        *reinterpret_cast<double2*>(g.C + off) = v;
-        for (int p = 0; p < g.npeer; ++p) *reinterpret_cast<double2*>(g.Cpeer[p] + off) = v;
-      }
+    for (int idx = warp * 32 + lane; idx < TN * (TM / 2); idx += CW * 32) {  // consecutive lanes: consecutive row pairs of a column
+      const int c = idx / (TM / 2), r2 = 2 * (idx % (TM / 2));
+      const double2 v = *reinterpret_cast<const double2*>(S + c * LDS + r2);
+      const long long off = rbase + r2 + (cbase + c) * g.ldc;
+      *reinterpret_cast<double2*>(g.C + off) = v;
+      for (int p = 0; p < g.npeer; ++p) *reinterpret_cast<double2*>(g.Cpeer[p] + off) = v;
     }
     continue;
   }
@@ -300,6 +298,12 @@ inline cudaError_t launch_gemm(cudaStream_t st, const GemmArgs& g0, long long wo
   if (kSmall < 0) {
     const char* env = getenv("GSP_GEMM_SMALL_TILES");
     kSmall = env ? atoll(env) : 100;
+  }
+  if (MODE == GEMM_SET && !BK && g0.npeer > 0 && tiles128 < 48) {
+    // multicast solves: the peer stores of one SM run at ~10 GB/s over NVLink, so the rows are spread over 4x more CTAs
+    GemmArgs g = g0;
+    g.mt = 4 * g0.mt;
+    return launch_gemm_cfg<MODE, BK, 32, 128, 1, 8>(st, g);
   }
   if (MODE == GEMM_SET && !BK && tiles128 < kSmall) {
     GemmArgs g = g0;

@@ -349,21 +349,14 @@ GSP_DEV void sq_strip_gemm(double* C, long long ldc, const double* Aop, long lon
   }
 }
 
-// Prologue (nk > 0, distributed factorization): the look-ahead update of the square with the previous panel (block columns
-// [cprev, cprev + nk), whose rows of this square were solved by panel_solve_kernel just before) - every strip CTA updates its own
-// part of the lower triangle, no flags needed.
 __global__ void __launch_bounds__(256, 1) potrf_square_kernel(double* A, long long lda, long long blk0, int nq, double* invD, int* info,
-                                                              int* flags, long long cprev, int nk) {
+                                                              int* flags) {
   GSP_DYN_SMEM(smem);
   const int i = blockIdx.x >> 1, h = blockIdx.x & 1;
   int* Pf = flags;
   int* Sf = flags + SQ_MAXB;
   int* Hf = flags + SQ_MAXB + SQ_MAXB * SQ_MAXB;
   const long long rbase = (blk0 + i) * DB + 64 * h;
-  for (int l = 0; l <= i && nk > 0; ++l)
-    for (int jj = 0; jj < nk; ++jj)
-      sq_strip_gemm<true>(A + rbase + (blk0 + l) * DB * lda, lda, A + rbase + (cprev + jj) * DB * lda, lda,
-                          A + (blk0 + l) * DB + (cprev + jj) * DB * lda, lda, smem);
   for (int j = 0; j < i; ++j) {
     double* Xij = A + rbase + (blk0 + j) * DB * lda;
     sq_wait(&Pf[j], 1);
@@ -381,22 +374,6 @@ __global__ void __launch_bounds__(256, 1) potrf_square_kernel(double* A, long lo
   sq_wait(&Hf[i], 1);
   potrf_diag_body(A, lda, blk0 + i, invD, info, smem);
   sq_signal(&Pf[i]);
-}
-
-// The rows of the NEXT panel solved against a finished square in one launch: X L_sq^T = A for the nr block rows from rblk0, block
-// columns [c0, c0 + nk) - per 64-row strip a forward substitution over the nk column blocks (S: multiply by the inverse of the
-// diagonal block, U: eliminate it from the columns to the right).  Strips are independent: no flags.  Replaces 2 nk - 1 dependent
-// launches on the critical path of the distributed factorization.
-__global__ void __launch_bounds__(256, 1) panel_solve_kernel(double* A, long long lda, long long rblk0, long long c0, int nk, const double* invD) {
-  GSP_DYN_SMEM(smem);
-  const int i = blockIdx.x >> 1, h = blockIdx.x & 1;
-  const long long rbase = (rblk0 + i) * DB + 64 * h;
-  for (int jj = 0; jj < nk; ++jj) {
-    double* X = A + rbase + (c0 + jj) * DB * lda;
-    sq_strip_gemm<false>(X, lda, X, lda, invD + (c0 + jj) * DB * DB, DB, smem);
-    for (int l = jj + 1; l < nk; ++l)
-      sq_strip_gemm<true>(A + rbase + (c0 + l) * DB * lda, lda, X, lda, A + (c0 + l) * DB + (c0 + jj) * DB * lda, lda, smem);
-  }
 }
 
 // Distributed factorization: the lower blocks of a finished square and the inverses of its diagonal blocks go to the other devices.
@@ -590,27 +567,16 @@ struct Chol {
   }
 
   // the whole diagonal square [o, o + n) in one launch (potrf_square_kernel), then its blocks and inverses to the other devices
-  void panel_solve(cudaStream_t s, int rblk0, int nr, int c0, int nk) {
-    if (nr <= 0 || nk <= 0) return;
-    auto kfn = panel_solve_kernel;
-    check(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, SQ_SMEM));
-    ProfScope prof_("panel_solve", s);
-    GSP_LAUNCH(kfn, dim3((unsigned)(2 * nr)), dim3(256), (size_t)SQ_SMEM, s, A, ld, (long long)rblk0, (long long)c0, nk, (const double*)invD);
-    g_launches++;
-    check(cudaGetLastError());
-  }
-  static bool square_is_fused(int n) { return n >= 2 && n <= SQ_MAXB; }
-  // `cprev`, `nk`: look-ahead prologue of the fused kernel (see potrf_square_kernel); nk = 0: none
-  void square(int o, int n, int* flags, int cprev = 0, int nk = 0) {
+  void square(int o, int n, int* flags) {
     if (n <= 0) return;
-    if (!square_is_fused(n)) {
-      potrf(o, n, nullptr, 0);
+    if (n == 1) {
+      potrf(o, 1, nullptr, 0);
     } else {
       check(cudaMemsetAsync(flags, 0, SQ_FLAGS * sizeof(int), st));
       auto kfn = potrf_square_kernel;
       check(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, SQ_SMEM));
       ProfScope prof_("potrf_square", st);
-      GSP_LAUNCH_COOP(kfn, dim3((unsigned)(2 * n)), dim3(256), (size_t)SQ_SMEM, st, A, ld, (long long)o, n, invD, info, flags, (long long)cprev, nk);
+      GSP_LAUNCH_COOP(kfn, dim3((unsigned)(2 * n)), dim3(256), (size_t)SQ_SMEM, st, A, ld, (long long)o, n, invD, info, flags);
       g_launches++;
       check(cudaGetLastError());
     }
@@ -775,7 +741,6 @@ cudaError_t chol_factor_dist(const std::vector<DistDev>& devs, long long ld, int
   // look-ahead update done, near / far parts of the wide update done
   std::vector<cudaEvent_t> evT(G, nullptr), evLA(G, nullptr), evNear(G, nullptr);
   cudaEvent_t evTfirst = nullptr, evD = nullptr;
-  int la_c0 = 0, la_nk = 0;  // look-ahead update handed to the next fused square kernel as its prologue
   for (int q = 0; q < Q && err == cudaSuccess; ++q) {
     const int o = dist_owner(q, G);
     const int c0 = q * PB;
@@ -785,10 +750,8 @@ cudaError_t chol_factor_dist(const std::vector<DistDev>& devs, long long ld, int
     // go to the other devices
     check(cudaSetDevice(devs[o].dev));
     static const int fused = env_int("GSP_CHOL_FUSED_SQUARE", 1);  // 0: the recursion of separate launches (A/B)
-    static const int fused_head = env_int("GSP_CHOL_FUSED_HEAD", 1);  // 0: panel-head solve and look-ahead as separate tile GEMMs (A/B)
     if (fused && nq <= SQ_MAXB) {
-      ch[o].square(c0, nq, devs[o].flags, la_c0, la_nk);
-      la_nk = 0;
+      ch[o].square(c0, nq, devs[o].flags);
     } else {
       ch[o].potrf(c0, nq, nullptr, 0);
       if (ch[o].peers.n > 0) {
@@ -819,9 +782,7 @@ cudaError_t chol_factor_dist(const std::vector<DistDev>& devs, long long ld, int
         if (evLA[g]) check(cudaStreamWaitEvent(sm, evLA[g], 0));   // LA(q-1) updated these rows in column panel q (aux stream)
         // solved locally on the main stream (LA_sq and D(q+1) only need them here); the copy for the other devices' look-ahead
         // updates leaves from the aux stream, off the critical path
-        const bool head = fused && fused_head && G > 0 && Chol::square_is_fused(n1) && nq <= SQ_MAXB;
-        if (head) ch[g].panel_solve(sm, cn, n1, c0, nq);
-        else ch[g].trsm_rows(sm, devs[g].rows + i0, ia - i0, c0, nq, false);
+        ch[g].trsm_rows(sm, devs[g].rows + i0, ia - i0, c0, nq, false);
         cudaEvent_t solved = record(g, sm);
         check(cudaStreamWaitEvent(sa, solved, 0));
         ch[g].push_rect(sa, cn, n1, c0, nq);
@@ -847,12 +808,7 @@ cudaError_t chol_factor_dist(const std::vector<DistDev>& devs, long long ld, int
         // the square of panel q+1 first, on the main stream: D(q+1) follows immediately.  Column panel q+1 was last touched by near(q-1).
         ia = first_at(g, cn + n1);
         if (evNear[g]) check(cudaStreamWaitEvent(sm, evNear[g], 0));
-        if (fused && fused_head && Chol::square_is_fused(n1) && nq <= SQ_MAXB) {
-          la_c0 = c0;  // done by the prologue of the fused square kernel of step q+1 (next on this stream)
-          la_nk = nq;
-        } else {
-          ch[g].update_rows(sm, devs[g].rows + i0, ia - i0, stair_tiles(g, i0, cn, cn + n1) - stair_tiles(g, ia, cn, cn + n1), cn, n1, c0, nq, true);
-        }
+        ch[g].update_rows(sm, devs[g].rows + i0, ia - i0, stair_tiles(g, i0, cn, cn + n1) - stair_tiles(g, ia, cn, cn + n1), cn, n1, c0, nq, true);
       }
       if ((int)rows[g].size() - ia > 0) {
         // needs o1's rows of panel q (T_first) besides the own rows (aux stream order)

@@ -63,6 +63,7 @@ SIGNATURES = {
     "gsp_host_free": (C.c_int, [_vp]),
     "gsp_pairwise": (C.c_int, [_vp, C.POINTER(_CovModel), C.c_int32, C.c_int64, _vp, C.c_int64, _vp, _vp]),
     "gsp_potrf": (C.c_int, [_vp, C.c_int64, _vp]),
+    "gsp_nearest_init": (C.c_int, [_vp, C.POINTER(_Domain), C.c_int64, _vp, _vp, _vp, _vp, C.POINTER(C.c_int64)]),
     "gsp_lu_plan_create": (C.c_int, [_vp, C.POINTER(_CovModel), C.POINTER(_Domain), C.c_int64, _vp, _vp, C.c_double, C.POINTER(_vp)]),
     "gsp_lu_plan_destroy": (C.c_int, [_vp]),
     "gsp_lu_plan_sizes": (C.c_int, [_vp, C.POINTER(C.c_int64 * 3)]),
@@ -218,6 +219,20 @@ class Library:
         m, keep = make_cov(structs)
         self.check(self.lib.gsp_pairwise(self.ctx, C.byref(m), dim, n1, _ptr(X1), n2, _ptr(X2c), _ptr(out)))
         return out
+
+    def nearest_init(self, dims, origin, spacing, dcoords: np.ndarray, dvals: np.ndarray):
+        """initialize + NearestInit on a CartesianGrid (nearest.jl:12-34) on the device -> (dinds0 ascending 0-based, z1)."""
+        if len(dvals) == 0:
+            return np.zeros(0, dtype=np.int64), np.zeros(0)
+        X = np.ascontiguousarray(np.asarray(dcoords, dtype=np.float64).reshape(len(dvals), -1))
+        v = np.ascontiguousarray(dvals, dtype=np.float64)
+        dom = make_grid_domain(dims, origin, spacing)
+        dinds = np.empty(max(len(v), 1), dtype=np.int64)
+        z1 = np.empty(max(len(v), 1))
+        cnt = C.c_int64(0)
+        self.check(self.lib.gsp_nearest_init(self.ctx, C.byref(dom), len(v), _ptr(X), _ptr(v), _ptr(dinds), _ptr(z1), C.byref(cnt)))
+        n = int(cnt.value)
+        return dinds[:n] - 1, z1[:n].copy()
 
     def potrf(self, A: np.ndarray) -> np.ndarray:
         L = np.array(A, dtype=np.float64, order="F", copy=True)

@@ -371,6 +371,7 @@ struct gsp_fft_plan {
   bool cond = false;
   double cond_mu = 0.0;
   long long cond_n = 0, cond_nk = 0, cond_ninds = 0;
+  unsigned long long cond_inds_hash = 0;  // FNV-1a of the view's parent indices given to gsp_fft_plan_condition
   int cond_kk = 0;
   std::vector<std::unique_ptr<FftDev>> dev;
   std::mutex mu;
@@ -1157,10 +1158,23 @@ int apply_conditioning(gsp_fft_plan* p, FftDev* d, double* Z, long long nb, doub
   return GSP_OK;
 }
 
-// conditional plans were built for ONE simulation domain (the view) and ONE mean
-int check_cond_args(gsp_fft_plan* p, double mu, long long n_inds) {
+unsigned long long hash_inds(const int64_t* inds, long long n) {
+  unsigned long long h = 1469598103934665603ull;
+  for (long long q = 0; q < n; ++q) {
+    h ^= (unsigned long long)inds[q];
+    h *= 1099511628211ull;
+  }
+  return h;
+}
+
+// conditional plans were built for ONE simulation domain (the view) and ONE mean.  `inds_host`: the caller's index list when it is
+// a host array (the _dev entry point only checks the length): another view of the same length must not silently get the zbar and
+// the weight tables of the domain the plan was conditioned on.
+int check_cond_args(gsp_fft_plan* p, double mu, long long n_inds, const int64_t* inds_host = nullptr) {
   if (!p->cond) return GSP_OK;
   if (n_inds != p->cond_ninds) return set_err(p->ctx, -8, "conditional plan: n_inds / inds differ from those given to gsp_fft_plan_condition");
+  if (inds_host && n_inds > 0 && hash_inds(inds_host, n_inds) != p->cond_inds_hash)
+    return set_err(p->ctx, -9, "conditional plan: inds differ from the view given to gsp_fft_plan_condition");
   if (mu != p->cond_mu) return set_err(p->ctx, -7, "conditional plan: mu differs from the mean given to gsp_fft_plan_condition");
   return GSP_OK;
 }
@@ -1259,7 +1273,7 @@ int fft_sample_impl(gsp_fft_plan* p, int64_t R, const double* w, uint64_t seed, 
   if (!(sill > 0.0)) return set_err(ctx, -6, "sill must be positive");
   if (!out && !ens) return set_err(ctx, -10, "out is NULL");
   if (n_inds > 0 && !inds) return set_err(ctx, -9, "inds is NULL");
-  GSP_TRY(check_cond_args(p, mu, n_inds));
+  GSP_TRY(check_cond_args(p, mu, n_inds, inds));
   if (n_inds > 0)
     for (long long q = 0; q < n_inds; ++q)
       if (inds[q] < 1 || inds[q] > p->N) return set_err(ctx, -9, "inds out of range (1-based parent indices)");
@@ -1516,6 +1530,7 @@ extern "C" int gsp_fft_plan_condition(gsp_fft_plan* p, double mu, int32_t minnei
   p->cond_n = n;
   p->cond_nk = nk;
   p->cond_ninds = n_inds;
+  p->cond_inds_hash = n_inds > 0 ? hash_inds(inds, n_inds) : 0;
   p->cond_kk = (int)kmax_k;
   return GSP_OK;
 }

@@ -65,10 +65,19 @@ class GaussianProcess:
 
 # ------------------------------------------------------------------ initialization
 class NearestInit:
-    """nearest.jl:10-34: each datum goes to the nearest element, later data overwrite, NaN = missing."""
+    """nearest.jl:10-34: each datum goes to the nearest element, later data overwrite, NaN = missing.
+    On a CartesianGrid with a CUDA library at hand the search runs on the device (gsp_nearest_init: grid arithmetic instead of
+    the reference's KD-tree over all centroids); views and point sets are searched on the host like the reference does."""
 
-    def apply(self, real, mask, dom, data: GeoTable):
+    def apply(self, real, mask, dom, data: GeoTable, lib: Optional[_lib.Library] = None):
         dcoords = data.domain.centroids()
+        if lib is not None and isinstance(dom, CartesianGrid) and dcoords.shape[0] > 0:
+            for var in real:
+                vals = np.array([np.nan if (v is None or (isinstance(v, float) and math.isnan(v))) else float(v) for v in data[var]])
+                dinds0, z1 = lib.nearest_init(dom.dims, dom.origin, dom.spacing, dcoords, vals)
+                real[var][dinds0] = z1
+                mask[var][dinds0] = True
+            return
         for i in range(dcoords.shape[0]):
             j = dom.nearest(dcoords[i])
             for var in real:
@@ -87,7 +96,7 @@ class ExplicitInit:
         else:
             self.orig, self.dest = args
 
-    def apply(self, real, mask, dom, data: GeoTable):
+    def apply(self, real, mask, dom, data: GeoTable, lib=None):
         dest = list(self.dest)
         orig = list(range(1, data.domain.nelements() + 1)) if self.orig is None else list(self.orig)
         assert len(orig) == len(dest), "invalid explicit initialization"
@@ -99,14 +108,14 @@ class ExplicitInit:
                     mask[var][j - 1] = True
 
 
-def initialize(process: GaussianProcess, domain, data: Optional[GeoTable], init):
-    """field.jl:43-58 -> (real, mask) dicts keyed by variable name."""
+def initialize(process: GaussianProcess, domain, data: Optional[GeoTable], init, lib: Optional[_lib.Library] = None):
+    """field.jl:43-58 -> (real, mask) dicts keyed by variable name.  `lib`: lets NearestInit search on the device."""
     names = process.defaultschema() if data is None else data.names()
     n = domain.nelements()
     real = {v: np.zeros(n) for v in names}
     mask = {v: np.zeros(n, dtype=bool) for v in names}
     if data is not None:
-        init.apply(real, mask, domain, data)
+        init.apply(real, mask, domain, data, lib)
     return real, mask
 
 
@@ -159,11 +168,11 @@ def preprocess_lusim(process: GaussianProcess, method: LUSIM, init, domain, data
     if not (f.isstationary() and f.issymmetric() and f.isbanded()):
         raise ValueError("LUSIM requires a geostatistical function that is stationary, symmetric and banded. "
                          "Covariances or composite functions of covariances satisfy these properties.")
-    real, mask = initialize(process, domain, data, init)
+    lib = method.library or default_library()
+    real, mask = initialize(process, domain, data, init, lib)
     names = tuple(real.keys())
     assert len(names) == f.nvariables(), "incompatible number of variables for geostatistical function"
     assert len(names) in (1, 2), "LUSIM only supports univariate and bivariate simulation"
-    lib = method.library or default_library()
     dom = _domain_handle(domain)
     plans = []
     for j, var in enumerate(names):
@@ -218,13 +227,13 @@ def preprocess_fftsim(process: GaussianProcess, method: FFTSIM, init, domain, da
     """fftsim.jl:54-107 (unconditional part)."""
     f = process.func
     assert f.isstationary(), "geostatistical function must be stationary"
-    real, mask = initialize(process, domain, data, init)
+    lib = method.library or default_library()
+    real, mask = initialize(process, domain, data, init, lib)
     assert len(real) == 1, "FFTSIM does not support multivariate simulation"
     var = next(iter(real))
     grid = domain.parent()
     if not isinstance(grid, CartesianGrid):
         raise ValueError("FFTSIM requires a (view of a) CartesianGrid")
-    lib = method.library or default_library()
     plan = _lib.FFTPlan(lib, f.flat(), grid.dims, grid.origin, grid.spacing)
     inds1 = domain.parentindices()
     if data is not None:

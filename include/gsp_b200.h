@@ -105,6 +105,16 @@ int gsp_pairwise(gsp_ctx* ctx, const gsp_cov_model* cov, int32_t dim, int64_t n1
  * lower triangle is read; on return the lower triangle holds L and the strict upper triangle is zero. */
 int gsp_potrf(gsp_ctx* ctx, int64_t n, double* A);
 
+/* initialize + NearestInit for ONE variable on a CartesianGrid - src/processes/field.jl:43-58,
+ * src/initialization/nearest.jl:12-34: every datum goes to the element whose centroid is nearest (grid arithmetic on the device
+ * instead of a KD-tree over all nelems centroids), later data overwrite earlier ones, a NaN value (= missing) is skipped.
+ * grid: kind 1.  dcoords: dim x nd column-major data locations, dvals: nd values.
+ * Out (caller-allocated, capacity nd): dinds = findall(mask) - 1-based, ascending - and z1 = the values in that order;
+ * *count = number of distinct data nodes.  These are the (nd, dinds, z1) of gsp_lu_plan_create and the knodes of
+ * gsp_fft_plan_condition.  Views and non-grid domains keep the host-side search of the glue. */
+int gsp_nearest_init(gsp_ctx* ctx, const gsp_domain* grid, int64_t nd, const double* dcoords, const double* dvals, int64_t* dinds,
+                     double* z1, int64_t* count);
+
 /* LUSIM preprocess for ONE variable - the body of the map at src/simulation/field/lusim.jl:66-107:
  * assembles C11/C12/C22 over the centroids (lusim.jl:81-96), factorises (lusim.jl:92 or 98-103) and
  * computes d2 (lusim.jl:102).  `cov` is the marginal covariance of the variable (lusim.jl:85).

@@ -368,3 +368,29 @@ def test_fftsim_batched_realizations(emu_lib):
         b = np.concatenate([plan.sample(3, None, seed=4), plan.sample(R - 3, None, seed=4, first_real=3)])
         assert np.array_equal(a, b)
         plan.close()
+
+
+def test_nearest_init_device(emu_lib):
+    """gsp_nearest_init (nearest.jl:12-34 on a CartesianGrid): nearest centroid by grid arithmetic, later datum wins, NaN skipped,
+    out-of-grid data clamp to the border elements, output = findall(mask) ascending - against the oracle and the reference's own
+    fixture (test/initialization.jl:16-21: data at (25,25), (50,75), (75,50) on a 100x100 grid -> linear indices 2526, 7551, 5076)."""
+    rng = np.random.default_rng(3)
+    for dims, origin, spacing, nd in (((100, 100), (0.0, 0.0), (1.0, 1.0), 3), ((17,), (0.5,), (2.0,), 40), ((9, 7, 5), (-1.0, 0.0, 2.0), (0.5, 1.5, 1.0), 700),
+                                      ((64, 48), (0.0, 0.0), (1.0, 1.0), 1000)):
+        dim = len(dims)
+        lo = np.asarray(origin) - 1.0
+        hi = np.asarray(origin) + np.asarray(dims) * np.asarray(spacing) + 1.0
+        X = rng.uniform(lo, hi, (nd, dim))
+        v = rng.standard_normal(nd)
+        if nd == 3:
+            X = np.array([[25.0, 25.0], [50.0, 75.0], [75.0, 50.0]])
+        else:
+            v[rng.choice(nd, nd // 7, replace=False)] = np.nan     # missing values
+            X[nd // 2:nd // 2 + nd // 5] = X[:nd // 5]             # repeated locations: the later datum wins
+        dinds, z1 = emu_lib.nearest_init(dims, origin, spacing, X, v)
+        do, zo = O.nearest_init(dims, origin, spacing, X, v)
+        assert np.array_equal(dinds, do) and np.array_equal(z1, zo)
+        if nd == 3:
+            assert list(dinds + 1) == [2526, 5076, 7551]
+    d0, z0 = emu_lib.nearest_init((4, 4), (0.0, 0.0), (1.0, 1.0), np.zeros((0, 2)), np.zeros(0))
+    assert len(d0) == 0 and len(z0) == 0

@@ -118,3 +118,24 @@ def test_rand_fftsim_with_data(emu_lib):
     vgrid = grid.view(range(1, 201))
     real = gsp.rand(proc, vgrid, rng=np.random.default_rng(2), data=data, method=gsp.FFTSIM(library=emu_lib))
     assert real.domain == vgrid and real.nrow == 200
+
+
+def test_conditional_plan_rejects_another_view(emu_lib):
+    """a conditional plan carries zbar and weight tables of ONE simulation domain: sampling it with a different view of the same
+    length (or a different mean) is an argument error, not silently wrong fields"""
+    dims = (12, 10)
+    st = iso(O.SPHERICAL, 1.0, 4.0, 2)
+    rng = np.random.default_rng(0)
+    inds0 = np.sort(rng.choice(120, 60, replace=False))
+    other0 = np.sort(rng.choice(120, 60, replace=False))
+    assert not np.array_equal(inds0, other0)
+    cent = O.grid_centroids(dims, [0.0, 0.0], [1.0, 1.0])[inds0]
+    knodes0 = np.sort(rng.choice(60, 8, replace=False))
+    plan = gsp.FFTPlan(emu_lib, st, dims, [0.0, 0.0], [1.0, 1.0])
+    plan.condition(0.3, cent[knodes0], rng.standard_normal(8), knodes0 + 1, inds0 + 1, maxneighbors=4)
+    plan.sample(1, None, seed=1, sill=1.0, mu=0.3, inds1=inds0 + 1)
+    with pytest.raises(ValueError):
+        plan.sample(1, None, seed=1, sill=1.0, mu=0.3, inds1=other0 + 1)
+    with pytest.raises(ValueError):
+        plan.sample(1, None, seed=1, sill=1.0, mu=0.4, inds1=inds0 + 1)
+    plan.close()

@@ -481,6 +481,28 @@ def test_fftsim_variogram_reproduction(gpu_lib):
     plan.close()
 
 
+def test_nearest_init_gpu(gpu_lib):
+    """NearestInit on the device (nearest.jl:12-34) == the oracle, at the conditional-FFTSIM scale too
+    (256^3 grid: the reference would build a KD-tree over 16.7 M centroids for these 5,000 data)"""
+    rng = np.random.default_rng(11)
+    for dims, nd in (((128, 128), 1000), ((256, 256, 256), 5000), ((50,), 300)):
+        dim = len(dims)
+        X = rng.uniform(-2.0, np.asarray(dims) + 2.0, (nd, dim))
+        v = rng.standard_normal(nd)
+        v[rng.choice(nd, nd // 9, replace=False)] = np.nan
+        X[nd // 2:nd // 2 + nd // 4] = X[:nd // 4]
+        dinds, z1 = gpu_lib.nearest_init(dims, [0.0] * dim, [1.0] * dim, X, v)
+        do, zo = O.nearest_init(dims, [0.0] * dim, [1.0] * dim, X, v)
+        assert np.array_equal(dinds, do) and np.array_equal(z1, zo)
+    # through rand(): conditional LUSIM with the data table snapped on the device honours the data exactly
+    proc = gsp.GaussianProcess(gsp.SphericalCovariance(range=10.0))
+    grid = gsp.CartesianGrid(40, 30)
+    pts = [(2.5, 2.5), (10.2, 7.9), (35.5, 12.5), (10.4, 7.6)]   # the last one falls on the node of the second: later wins
+    data = gsp.georef({"Z": [0.3, -1.1, 0.8, 1.9]}, pts)
+    real = gsp.rand(proc, grid, rng=np.random.default_rng(1), method=gsp.LUSIM(library=gpu_lib), data=data)
+    assert real.Z[grid.nearest(np.array([10.4, 7.6]))] == 1.9 and real.Z[grid.nearest(np.array([2.5, 2.5]))] == 0.3
+
+
 # ------------------------------------------------------------------ reference-facing API on the GPU
 def test_rand_api_gpu(gpu_lib):
     rng = np.random.default_rng(123)

@@ -12,7 +12,8 @@ module GeoStatsProcessesB200
 using GeoStatsProcesses
 using GeoStatsProcesses: FieldSimulationMethod, GaussianProcess, Ensemble, NearestInit, initialize
 using GeoStatsFunctions
-using GeoTables: georef
+import GeoTables
+using GeoTables: georef, nrow
 using Meshes
 using LinearAlgebra
 using Random
@@ -120,6 +121,26 @@ function cdomain(dom)
   CDomain(0, size(X, 1), size(X, 2), pointer(X), (1, 1, 1), (0.0, 0.0, 0.0), (1.0, 1.0, 1.0)), X
 end
 
+# data nodes of one variable: `findall(mask[var])` and the values there (lusim.jl:71-75).  NearestInit on a CartesianGrid runs on
+# the device (gsp_nearest_init: grid arithmetic instead of the KD-tree over all centroids that nearest.jl:16 builds); every other
+# combination keeps the reference's `initialize` result.
+function datanodes(domain, data, init, real, mask, var)
+  if !isnothing(data) && init isa GeoStatsProcesses.NearestInit && domain isa CartesianGrid
+    X = reduce(hcat, [collect(Float64.(ustrip.(to(centroid(GeoTables.domain(data), i))))) for i in 1:nrow(data)])   # dim x nd
+    v = [ismissing(x) ? NaN : Float64(ustrip(x)) for x in getproperty(data, var)]
+    nd = length(v)
+    dinds, z₁, cnt = Vector{Int64}(undef, nd), Vector{Float64}(undef, nd), Ref{Int64}(0)
+    cdom, _ = cdomain(domain)
+    ctx = context()
+    check(ctx, ccall((:gsp_nearest_init, LIB), Cint,
+                     (Ptr{Cvoid}, Ptr{CDomain}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}, Ptr{Float64}, Ptr{Int64}),
+                     ctx.ptr, Ref(cdom), nd, X, v, dinds, z₁, cnt))
+    return dinds[1:cnt[]], z₁[1:cnt[]]
+  end
+  dinds = Int64.(findall(mask[var]))                                     # ascending, 1-based (lusim.jl:71)
+  dinds, Float64.(ustrip.(view(real[var], dinds)))
+end
+
 # ---------------------------------------------------------------- LUSIM on the GPU
 """
     LUSIM_B200(; batch=64, seed=nothing)
@@ -164,8 +185,7 @@ function preprocess(::AbstractRNG, process::GaussianProcess, method::LUSIM_B200,
   Ns = 0
   GC.@preserve keep begin
     for (j, var) in enumerate(vars)
-      dinds = Int64.(findall(mask[var]))                                   # ascending, 1-based (lusim.jl:71)
-      z₁ = Float64.(ustrip.(view(real[var], dinds)))
+      dinds, z₁ = datanodes(domain, data, init, real, mask, var)
       structs = flatten(f, j)
       model = Ref(CCovModel(length(structs), 0, pointer(structs)))
       ref = Ref{Ptr{Cvoid}}(C_NULL)

@@ -346,6 +346,11 @@ def test_multi_device_block_cyclic_cholesky(emu_lib):
     env = dict(os.environ, GSP_CHOL_DIST_MIN_BLOCKS="2", GSP_CHOL_PB="1")
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=900)
     assert out.returncode == 0 and "OK" in out.stdout, out.stderr[-1500:]
+    # panels of 2 blocks on 2 devices: the fused diagonal-square kernel (strips + flags), push_square / push_rect, near / far updates
+    env = dict(os.environ, GSP_CHOL_DIST_MIN_BLOCKS="2", GSP_CHOL_PB="2")
+    out = subprocess.run([sys.executable, "-c", code.replace("[0, 0, 0]", "[0, 0]").replace("(20, 18)", "(24, 21)").replace("360", "504")],
+                         capture_output=True, text=True, env=env, timeout=900)
+    assert out.returncode == 0 and "OK" in out.stdout, out.stderr[-1500:]
 
 
 def test_fftsim_batched_realizations(emu_lib):

@@ -229,7 +229,9 @@ CholChoice choose_chol(int ndev, int nb) {
   if (algo && algo[0] == 'r') c.dist = false;
   else if (algo && algo[0] == 'p') c.dist = true;
   else c.dist = ndev > 1 ? nb >= min_blocks : nb >= min_blocks_1;  // one device: measured C3 51.9 vs 59.4 ms, 32k nodes 359 vs 367 ms
-  c.PB = pb_env > 0 ? std::min(pb_env, 8) : 4;
+  // panel width in 128-blocks, measured on B200: 4 everywhere (C3 51.8 vs 52.4 ms on one GPU, C5 63 vs 64 ms and C3 17.5 vs 17.7 ms
+  // on eight) except large matrices on ONE device, where 8 wins (32k nodes: 359 vs 371 ms)
+  c.PB = pb_env > 0 ? std::min(pb_env, 8) : ((ndev == 1 && nb >= 192) ? 8 : 4);
   if (c.PB > nb) c.PB = nb;
   return c;
 }

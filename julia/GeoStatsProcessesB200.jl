@@ -244,6 +244,8 @@ end
 Base.@kwdef struct FFTSIM_B200 <: FieldSimulationMethod
   batch::Int = 16
   seed::Union{Nothing,UInt64} = nothing
+  minneighbors::Int = 1          # conditioning (fftsim.jl:47-52); `neighborhood` / `distance` other than the defaults stay with FFTSIM()
+  maxneighbors::Int = 26
 end
 
 mutable struct FFTPre
@@ -262,7 +264,6 @@ function preprocess(::AbstractRNG, process::GaussianProcess, method::FFTSIM_B200
   @assert isstationary(f) "geostatistical function must be stationary"
   real, mask = initialize(process, domain, data, init)
   @assert length(keys(real)) == 1 "FFTSIM does not support multivariate simulation"
-  isnothing(data) || throw(ArgumentError("FFTSIM_B200: conditional simulation is not offloaded yet, use FFTSIM() or LUSIM_B200()"))
   grid = parent(domain)
   ctx = context()
   cdom, _ = cdomain(grid)
@@ -274,6 +275,20 @@ function preprocess(::AbstractRNG, process::GaussianProcess, method::FFTSIM_B200
                      ctx.ptr, model, Ref(cdom), ref))
   end
   inds = domain === grid ? Int64[] : Int64.(collect(parentindices(domain)))
+  if !isnothing(data)
+    # fftsim.jl:94-104: zbar = simple Kriging of the data where they are (k nearest, Euclidean); dinds = findall(mask[var]).
+    # The weights of the per-realization Kriging (fftsim.jl:140-149) depend on geometry only and are built here, once.
+    var = first(keys(real))
+    knodes, _ = datanodes(domain, data, init, real, mask, var)
+    vals = getproperty(data, var)
+    keep = findall(!ismissing, vals)
+    X = reduce(hcat, [collect(Float64.(ustrip.(to(centroid(GeoTables.domain(data), i))))) for i in keep])   # dim x nd, where the data are
+    v = Float64.(ustrip.(vals[keep]))
+    check(ctx, ccall((:gsp_fft_plan_condition, LIB), Cint,
+                     (Ptr{Cvoid}, Float64, Int32, Int32, Int64, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Int64}, Int64, Ptr{Int64}),
+                     ref[], Float64(ustrip(process.mean)), method.minneighbors, method.maxneighbors, length(v), X, v,
+                     length(knodes), knodes, length(inds), isempty(inds) ? C_NULL : inds))
+  end
   pre = FFTPre(ref[], first(keys(real)), inds, size(grid), Matrix{Float64}(undef, 0, 0), 0, 0, ReentrantLock())
   finalizer(p -> ccall((:gsp_fft_plan_destroy, LIB), Cint, (Ptr{Cvoid},), p.plan), pre)
   pre

@@ -78,6 +78,10 @@ def test_argument_errors_emulated(emu_lib):
         plan.sample(1, np.zeros((1, 64)) + 0.5, sill=-1.0)
     with pytest.raises(ValueError):
         plan.sample(1, np.zeros((1, 64)) + 0.5, inds1=np.array([0, 3]))
+    lp = gsp.LUPlan(emu_lib, st, dom, None, None, 0.0)
+    with pytest.raises(ValueError):  # W1 without W: both noises are injected or both come from the device RNG
+        lp.sample(2, None, rho=0.5, W1=np.zeros((lp.Ns, 2)))
+    lp.close()
     # non-positive-definite matrix -> PosDefException(info) like cholesky (lusim.jl:92)
     A = np.eye(5)
     A[3, 3] = -1.0

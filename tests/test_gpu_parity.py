@@ -152,6 +152,15 @@ def test_lusim_bivariate(gpu_lib):
         p.close()
 
 
+def test_lusim_rejects_w1_without_w(gpu_lib):
+    """both noises are injected or both come from the device RNG (a lone W1 used to be ignored silently)"""
+    plan = gsp.LUPlan(gpu_lib, iso(O.SPHERICAL, 1.0, 5.0, 2), grid_dom((16, 12)), None, None, 0.0)
+    W1 = np.random.default_rng(0).standard_normal((plan.Ns, 3))
+    with pytest.raises(ValueError):
+        plan.sample(3, None, rho=0.5, W1=W1)
+    plan.close()
+
+
 def test_lusim_pointset_3d(gpu_lib):
     rng = np.random.default_rng(8)
     X = rng.uniform(0, 20, (700, 3))
@@ -446,6 +455,22 @@ def test_fftsim_c2_config(gpu_lib):
     assert np.abs((Z ** 2).sum(axis=1) / (N - 1) - 1.0).max() < 1e-12
     for r in (0, 63):
         assert relerr(Z[r], O.fftsim_sample(Fo, w[r], 1.0, 0.0)) < 1e-6  # conditioning-limited, see docstring
+    plan.close()
+
+
+def test_fftsim_c2_size_well_conditioned_parity(gpu_lib):
+    """the C2 grid (1024 x 1024, 64 realizations) with a covariance whose spectrum does NOT underflow (Exponential, range 50): every
+    realization at 1e-9 - an indexing error at this size cannot hide under the 1e-6 that the Gaussian model's conditioning forces above"""
+    dims = (1024, 1024)
+    st = iso(O.EXPONENTIAL, 1.0, 50.0, 2)
+    plan = gsp.FFTPlan(gpu_lib, st, dims, [0.0, 0.0], [1.0, 1.0])
+    Fo = O.fftsim_preprocess(ostructs(st), dims, [0.0, 0.0], [1.0, 1.0])
+    assert relerr(plan.spectrum(), Fo) < 1e-10
+    N = 1 << 20
+    w = np.random.default_rng(22).random((64, N))
+    Z = plan.sample(64, w, sill=1.0, mu=-0.5)
+    for r in range(64):
+        assert relerr(Z[r], O.fftsim_sample(Fo, w[r], 1.0, -0.5)) < TOL, r
     plan.close()
 
 

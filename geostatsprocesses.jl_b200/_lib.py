@@ -65,6 +65,7 @@ SIGNATURES = {
     "gsp_potrf": (C.c_int, [_vp, C.c_int64, _vp]),
     "gsp_nearest_init": (C.c_int, [_vp, C.POINTER(_Domain), C.c_int64, _vp, _vp, _vp, _vp, C.POINTER(C.c_int64)]),
     "gsp_lu_plan_create": (C.c_int, [_vp, C.POINTER(_CovModel), C.POINTER(_Domain), C.c_int64, _vp, _vp, C.c_double, C.POINTER(_vp)]),
+    "gsp_lu_plan_create_like": (C.c_int, [_vp, C.c_int64, _vp, _vp, C.c_double, C.POINTER(_vp)]),
     "gsp_lu_plan_destroy": (C.c_int, [_vp]),
     "gsp_lu_plan_sizes": (C.c_int, [_vp, C.POINTER(C.c_int64 * 3)]),
     "gsp_lu_plan_times": (C.c_int, [_vp, C.POINTER(C.c_double * 3)]),
@@ -242,16 +243,24 @@ class Library:
 
 
 class LUPlan:
-    def __init__(self, lib: Library, structs, domain, dinds1: Optional[np.ndarray], z1: Optional[np.ndarray], mu: float):
+    def __init__(self, lib: Library, structs, domain, dinds1: Optional[np.ndarray], z1: Optional[np.ndarray], mu: float,
+                 like: Optional["LUPlan"] = None):
+        """`like`: a plan with the same marginal covariance and data nodes - its factor is shared (gsp_lu_plan_create_like), only
+        d2 is computed; `structs` / `domain` are then ignored."""
         self.lib = lib
-        m, keep = make_cov(structs)
         dinds1 = np.zeros(0, dtype=np.int64) if dinds1 is None else np.ascontiguousarray(dinds1, dtype=np.int64)
         z1 = np.zeros(0) if z1 is None else np.ascontiguousarray(z1, dtype=np.float64)
-        dom, keep2 = domain
         h = _vp()
-        rc = lib.lib.gsp_lu_plan_create(lib.ctx, C.byref(m), C.byref(dom), len(dinds1), _ptr(dinds1) if len(dinds1) else None,
-                                        _ptr(z1) if len(z1) else None, float(mu), C.byref(h))
-        lib.check(rc, posdef=True)
+        if like is not None:
+            rc = lib.lib.gsp_lu_plan_create_like(like.h, len(dinds1), _ptr(dinds1) if len(dinds1) else None, _ptr(z1) if len(z1) else None,
+                                                 float(mu), C.byref(h))
+            lib.check(rc)
+        else:
+            m, keep = make_cov(structs)
+            dom, keep2 = domain
+            rc = lib.lib.gsp_lu_plan_create(lib.ctx, C.byref(m), C.byref(dom), len(dinds1), _ptr(dinds1) if len(dinds1) else None,
+                                            _ptr(z1) if len(z1) else None, float(mu), C.byref(h))
+            lib.check(rc, posdef=True)
         self.h = h
         sizes = (C.c_int64 * 3)()
         lib.check(lib.lib.gsp_lu_plan_sizes(h, C.byref(sizes)))

@@ -60,8 +60,8 @@ namespace {
 
 struct LuDev {
   DevCtx* dc = nullptr;
-  DevBuf A;       // Np x Np joint matrix -> L
-  DevBuf invD;    // inverses of the diagonal 128-blocks
+  std::shared_ptr<DevBuf> A;     // Np x Np joint matrix -> L   (shared with the plans made by gsp_lu_plan_create_like)
+  std::shared_ptr<DevBuf> invD;  // inverses of the diagonal 128-blocks
   DevBuf rows;    // block rows this device owns (distributed factorization)
   DevBuf flags;   // inter-CTA flags of the fused diagonal-square kernel
   DevBuf d2;      // Ns_pad
@@ -95,6 +95,7 @@ struct gsp_lu_plan {
   double mu = 0.0;
   double t_assemble_ms = 0.0, t_factor_ms = 0.0, t_solve_ms = 0.0;  // device times of the plan stages (CUDA events)
   std::vector<std::unique_ptr<LuDev>> dev;
+  std::vector<long long> h_sinds, h_dind0;  // 0-based simulation / data nodes (kept for gsp_lu_plan_create_like)
   std::mutex mu_lock;
 };
 
@@ -165,7 +166,7 @@ int sample_core(gsp_ctx* ctx, gsp_lu_plan* p, LuDev* d, long long cols, const do
     g_launches++;
     GSP_CUDA_OK(ctx, cudaGetLastError());
   }
-  const double* L22 = d->A.as<double>() + p->Ndp * (p->Np + 1);
+  const double* L22 = d->A->as<double>() + p->Ndp * (p->Np + 1);
   const double addmu = (p->Nd == 0) ? p->mu : 0.0;  // lusim.jl:172
   GSP_CUDA_OK(ctx, sample_gemm(st, L22, p->Np, (int)(p->Nsp / 128), Wp, cpad, (int)(cpad / 128), Z, ldz, d->d2.as<double>(),
                                d->sinds.as<long long>(), addmu, p->Ns, cols));
@@ -216,6 +217,24 @@ void destroy_plan_events(gsp_lu_plan* p) {
 // Which factorization runs (GSP_CHOL_ALGO): "panel" = chol_factor_dist (row-panel ownership over the devices of the context, also on
 // one device), "recursive" = chol_factor on device 0 (+ copy of L to the other devices).  Default: panel whenever the matrix has
 // at least GSP_CHOL_DIST_MIN_BLOCKS 128-blocks (below that the panel chain dominates and the recursion on one device is as fast).
+// d2 = A21 * (L11 \ z1) on device 0 (lusim.jl:102); zero when unconditional (lusim.jl:91).  Enqueued on device 0's stream.
+int compute_d2(gsp_ctx* ctx, gsp_lu_plan* p, const double* z1) {
+  LuDev* d0 = p->dev[0].get();
+  DevCtx& dc = *d0->dc;
+  cudaSetDevice(dc.dev);
+  cudaStream_t st = dc.stream;
+  DevBuf y;
+  GSP_CUDA_OK(ctx, cudaMemsetAsync(d0->d2.p, 0, (size_t)p->Nsp * sizeof(double), st));
+  if (p->Nd > 0) {
+    GSP_CUDA_OK(ctx, y.alloc(dc.dev, (size_t)p->Ndp * sizeof(double), st));
+    GSP_CUDA_OK(ctx, cudaMemsetAsync(y.p, 0, (size_t)p->Ndp * sizeof(double), st));
+    GSP_CUDA_OK(ctx, cudaMemcpyAsync(y.p, z1, (size_t)p->Nd * sizeof(double), cudaMemcpyHostToDevice, st));
+    GSP_CUDA_OK(ctx, chol_forward_solve(st, d0->A->as<double>(), p->Np, d0->invD->as<double>(), (int)(p->Ndp / 128), y.as<double>()));
+    GSP_CUDA_OK(ctx, chol_gemv_rows(st, d0->A->as<double>(), p->Np, p->Ndp, p->Nsp, (int)p->Ndp, y.as<double>(), d0->d2.as<double>()));
+  }
+  return GSP_OK;  // y is freed stream-ordered on st
+}
+
 struct CholChoice {
   bool dist;
   int PB;
@@ -293,6 +312,8 @@ extern "C" int gsp_lu_plan_create(gsp_ctx* ctx, const gsp_cov_model* cov, const 
     }
   }
 
+  p->h_sinds = sinds;
+  p->h_dind0 = dind0;
   const int ndev = (int)ctx->devs.size();
   const int nb = (int)(p->Np / 128);
   const CholChoice cc = choose_chol(ndev, nb);
@@ -325,8 +346,10 @@ extern "C" int gsp_lu_plan_create(gsp_ctx* ctx, const gsp_cov_model* cov, const 
       GSP_CUDA_OK(ctx, cudaMemcpyAsync(d->dinds.p, dind0.data(), dind0.size() * sizeof(long long), cudaMemcpyHostToDevice, st));
       GSP_CUDA_OK(ctx, cudaMemcpyAsync(d->z1.p, z1, (size_t)nd * sizeof(double), cudaMemcpyHostToDevice, st));
     }
-    GSP_CUDA_OK(ctx, d->A.alloc(dc.dev, (size_t)p->Np * p->Np * sizeof(double), st));
-    GSP_CUDA_OK(ctx, d->invD.alloc(dc.dev, (size_t)nb * 128 * 128 * sizeof(double), st));
+    d->A = std::make_shared<DevBuf>();
+    d->invD = std::make_shared<DevBuf>();
+    GSP_CUDA_OK(ctx, d->A->alloc(dc.dev, (size_t)p->Np * p->Np * sizeof(double), st));
+    GSP_CUDA_OK(ctx, d->invD->alloc(dc.dev, (size_t)nb * 128 * 128 * sizeof(double), st));
     if (i >= nbuild) continue;
     GSP_CUDA_OK(ctx, d->rows.alloc(dc.dev, (size_t)nb * sizeof(int), st));
     GSP_CUDA_OK(ctx, d->flags.alloc(dc.dev, (size_t)chol_dist_flag_ints() * sizeof(int), st));
@@ -340,7 +363,7 @@ extern "C" int gsp_lu_plan_create(gsp_ctx* ctx, const gsp_cov_model* cov, const 
       ddl.coords = dcoords.as<double>();
     }
     if (!cc.dist) {
-      launch_assemble(st, cd, ddl, ddl, dperm.as<long long>(), dperm.as<long long>(), p->Np, p->Np, d->A.as<double>(), p->Np, true);
+      launch_assemble(st, cd, ddl, ddl, dperm.as<long long>(), dperm.as<long long>(), p->Np, p->Np, d->A->as<double>(), p->Np, true);
     } else {
       std::vector<int> own;
       chol_dist_owned_rows(nb, cc.PB, nbuild, i, &own);
@@ -348,7 +371,7 @@ extern "C" int gsp_lu_plan_create(gsp_ctx* ctx, const gsp_cov_model* cov, const 
         size_t b = a + 1;
         while (b < own.size() && own[b] == own[b - 1] + 1) ++b;
         const long long r0 = (long long)own[a] * 128, r1 = (long long)(own[b - 1] + 1) * 128;
-        launch_assemble(st, cd, ddl, ddl, dperm.as<long long>() + r0, dperm.as<long long>(), r1 - r0, r1, d->A.as<double>() + r0, p->Np, true, r0);
+        launch_assemble(st, cd, ddl, ddl, dperm.as<long long>() + r0, dperm.as<long long>(), r1 - r0, r1, d->A->as<double>() + r0, p->Np, true, r0);
         a = b;
       }
     }
@@ -365,25 +388,16 @@ extern "C" int gsp_lu_plan_create(gsp_ctx* ctx, const gsp_cov_model* cov, const 
     std::vector<DistDev> dv;
     for (int i = 0; i < nbuild; ++i) {
       LuDev* d = p->dev[i].get();
-      dv.push_back(DistDev{d->dc->dev, d->dc->stream, d->dc->aux, d->dc->side[0], d->A.as<double>(), d->invD.as<double>(), d->info.as<int>(),
+      dv.push_back(DistDev{d->dc->dev, d->dc->stream, d->dc->aux, d->dc->side[0], d->A->as<double>(), d->invD->as<double>(), d->info.as<int>(),
                            d->rows.as<int>(), d->flags.as<int>()});
     }
     GSP_CUDA_OK(ctx, chol_factor_dist(dv, p->Np, nb, cc.PB));
     cudaSetDevice(dc.dev);
   } else {
-    GSP_CUDA_OK(ctx, chol_factor(st, dc.side, DevCtx::kSide, d0->A.as<double>(), p->Np, nb, d0->invD.as<double>(), d0->info.as<int>()));
+    GSP_CUDA_OK(ctx, chol_factor(st, dc.side, DevCtx::kSide, d0->A->as<double>(), p->Np, nb, d0->invD->as<double>(), d0->info.as<int>()));
   }
   GSP_CUDA_OK(ctx, cudaEventRecord(tev.ev[2], st));
-  // d2 = A21 * (L11 \ z1)   (lusim.jl:102); zero when unconditional (lusim.jl:91)
-  DevBuf y;
-  GSP_CUDA_OK(ctx, cudaMemsetAsync(d0->d2.p, 0, (size_t)p->Nsp * sizeof(double), st));
-  if (nd > 0) {
-    GSP_CUDA_OK(ctx, y.alloc(dc.dev, (size_t)p->Ndp * sizeof(double), st));
-    GSP_CUDA_OK(ctx, cudaMemsetAsync(y.p, 0, (size_t)p->Ndp * sizeof(double), st));
-    GSP_CUDA_OK(ctx, cudaMemcpyAsync(y.p, z1, (size_t)nd * sizeof(double), cudaMemcpyHostToDevice, st));
-    GSP_CUDA_OK(ctx, chol_forward_solve(st, d0->A.as<double>(), p->Np, d0->invD.as<double>(), (int)(p->Ndp / 128), y.as<double>()));
-    GSP_CUDA_OK(ctx, chol_gemv_rows(st, d0->A.as<double>(), p->Np, p->Ndp, p->Nsp, (int)p->Ndp, y.as<double>(), d0->d2.as<double>()));
-  }
+  GSP_TRY(compute_d2(ctx, p, z1));
   GSP_CUDA_OK(ctx, cudaEventRecord(tev.ev[3], st));
   int info = 0;
   for (int i = 0; i < nbuild; ++i) {  // the first non-positive pivot may have been met on any panel owner
@@ -412,9 +426,85 @@ extern "C" int gsp_lu_plan_create(gsp_ctx* ctx, const gsp_cov_model* cov, const 
   for (int i = 1; i < ndev; ++i) {
     LuDev* e = p->dev[i].get();
     cudaSetDevice(e->dc->dev);
-    if (!cc.dist) GSP_CUDA_OK(ctx, cudaMemcpyPeerAsync(e->A.p, e->dc->dev, d0->A.p, d0->dc->dev, d0->A.bytes, e->dc->stream));
+    if (!cc.dist) GSP_CUDA_OK(ctx, cudaMemcpyPeerAsync(e->A->p, e->dc->dev, d0->A->p, d0->dc->dev, d0->A->bytes, e->dc->stream));
     GSP_CUDA_OK(ctx, cudaMemcpyPeerAsync(e->d2.p, e->dc->dev, d0->d2.p, d0->dc->dev, d0->d2.bytes, e->dc->stream));
     GSP_CUDA_OK(ctx, cudaStreamSynchronize(e->dc->stream));
+  }
+  guard.p = nullptr;
+  *out = p;
+  return GSP_OK;
+}
+
+extern "C" int gsp_lu_plan_create_like(gsp_lu_plan* base, int64_t nd, const int64_t* dinds, const double* z1, double mu, gsp_lu_plan** out) {
+  if (!base) return -1;
+  gsp_ctx* ctx = base->ctx;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (!out) return set_err(ctx, -6, "out is NULL");
+  *out = nullptr;
+  if (nd != base->Nd) return set_err(ctx, -2, "nd differs from the base plan: the factor cannot be shared");
+  if (nd > 0 && (!dinds || !z1)) return set_err(ctx, !dinds ? -3 : -4, "dinds / z1 is NULL");
+  for (long long j = 0; j < nd; ++j)
+    if (dinds[j] - 1 != base->h_dind0[(size_t)j]) return set_err(ctx, -3, "dinds differ from the base plan: the factor cannot be shared");
+  struct PlanGuard {
+    gsp_lu_plan* p;
+    ~PlanGuard() {
+      if (p) {
+        destroy_plan_events(p);
+        delete p;
+      }
+    }
+  } guard{new gsp_lu_plan};
+  gsp_lu_plan* p = guard.p;
+  p->ctx = ctx;
+  p->N = base->N; p->Nd = base->Nd; p->Ns = base->Ns; p->Ndp = base->Ndp; p->Nsp = base->Nsp; p->Np = base->Np;
+  p->mu = mu;
+  p->h_sinds = base->h_sinds;
+  p->h_dind0 = base->h_dind0;
+  EventSet tev;
+  cudaSetDevice(ctx->devs[0].dev);
+  GSP_CUDA_OK(ctx, tev.make(2));
+  for (size_t i = 0; i < base->dev.size(); ++i) {
+    std::unique_ptr<LuDev> dptr(new LuDev);
+    LuDev* d = dptr.get();
+    const LuDev* b = base->dev[i].get();
+    d->dc = b->dc;
+    p->dev.push_back(std::move(dptr));
+    DevCtx& dc = *d->dc;
+    cudaSetDevice(dc.dev);
+    cudaStream_t st = dc.stream;
+    d->A = b->A;        // the factor and the block inverses are shared (reference counted)
+    d->invD = b->invD;
+    GSP_CUDA_OK(ctx, d->d2.alloc(dc.dev, (size_t)p->Nsp * sizeof(double), st));
+    GSP_CUDA_OK(ctx, d->sinds.alloc(dc.dev, (size_t)p->Ns * sizeof(long long), st));
+    GSP_CUDA_OK(ctx, d->dinds.alloc(dc.dev, (size_t)std::max<long long>(nd, 1) * sizeof(long long), st));
+    GSP_CUDA_OK(ctx, d->z1.alloc(dc.dev, (size_t)std::max<long long>(nd, 1) * sizeof(double), st));
+    GSP_CUDA_OK(ctx, d->info.alloc(dc.dev, sizeof(int), st));
+    GSP_CUDA_OK(ctx, cudaEventCreate(&d->ev0));
+    GSP_CUDA_OK(ctx, cudaEventCreate(&d->ev1));
+    GSP_CUDA_OK(ctx, cudaMemcpyAsync(d->sinds.p, p->h_sinds.data(), p->h_sinds.size() * sizeof(long long), cudaMemcpyHostToDevice, st));
+    if (nd > 0) {
+      GSP_CUDA_OK(ctx, cudaMemcpyAsync(d->dinds.p, p->h_dind0.data(), p->h_dind0.size() * sizeof(long long), cudaMemcpyHostToDevice, st));
+      GSP_CUDA_OK(ctx, cudaMemcpyAsync(d->z1.p, z1, (size_t)nd * sizeof(double), cudaMemcpyHostToDevice, st));
+    }
+  }
+  LuDev* d0 = p->dev[0].get();
+  cudaSetDevice(d0->dc->dev);
+  GSP_CUDA_OK(ctx, cudaEventRecord(tev.ev[0], d0->dc->stream));
+  GSP_TRY(compute_d2(ctx, p, z1));
+  GSP_CUDA_OK(ctx, cudaEventRecord(tev.ev[1], d0->dc->stream));
+  GSP_CUDA_OK(ctx, cudaStreamSynchronize(d0->dc->stream));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, tev.ev[0], tev.ev[1]);
+  p->t_solve_ms = ms;  // assembly and factorization were paid by the base plan: their times stay 0 here
+  for (size_t i = 1; i < p->dev.size(); ++i) {
+    LuDev* e = p->dev[i].get();
+    cudaSetDevice(e->dc->dev);
+    GSP_CUDA_OK(ctx, cudaMemcpyPeerAsync(e->d2.p, e->dc->dev, d0->d2.p, d0->dc->dev, d0->d2.bytes, e->dc->stream));
+    GSP_CUDA_OK(ctx, cudaStreamSynchronize(e->dc->stream));
+  }
+  for (auto& d : p->dev) {  // the host staging of sinds / dinds / z1 must be consumed before the caller's arrays go away
+    cudaSetDevice(d->dc->dev);
+    GSP_CUDA_OK(ctx, cudaStreamSynchronize(d->dc->stream));
   }
   guard.p = nullptr;
   *out = p;
@@ -453,7 +543,7 @@ extern "C" int gsp_lu_plan_get(gsp_lu_plan* p, double* d2, double* L22) {
   cudaStream_t st = d->dc->stream;
   if (d2) GSP_CUDA_OK(ctx, cudaMemcpyAsync(d2, d->d2.p, (size_t)p->Ns * sizeof(double), cudaMemcpyDeviceToHost, st));
   if (L22) {
-    const double* src = d->A.as<double>() + p->Ndp * (p->Np + 1);
+    const double* src = d->A->as<double>() + p->Ndp * (p->Np + 1);
     GSP_CUDA_OK(ctx, cudaMemcpy2DAsync(L22, (size_t)p->Ns * sizeof(double), src, (size_t)p->Np * sizeof(double), (size_t)p->Ns * sizeof(double),
                                        (size_t)p->Ns, cudaMemcpyDeviceToHost, st));
   }

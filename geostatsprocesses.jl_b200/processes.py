@@ -126,8 +126,10 @@ class FieldSimulationMethod:
 
 @dataclass
 class LUSIM(FieldSimulationMethod):
-    """GPU LUSIM (lusim.jl:36).  `library` selects the context (default: device 0)."""
+    """GPU LUSIM (lusim.jl:36).  `library` selects the context (default: device 0).  `share_factor`: variables with the same marginal
+    covariance and data nodes share one Cholesky factor (the results are identical to factoring twice)."""
     library: Optional[_lib.Library] = None
+    share_factor: bool = True
 
 
 @dataclass
@@ -174,12 +176,19 @@ def preprocess_lusim(process: GaussianProcess, method: LUSIM, init, domain, data
     assert len(names) == f.nvariables(), "incompatible number of variables for geostatistical function"
     assert len(names) in (1, 2), "LUSIM only supports univariate and bivariate simulation"
     dom = _domain_handle(domain)
-    plans = []
+    plans, keys = [], []
     for j, var in enumerate(names):
         dinds0 = np.flatnonzero(mask[var])
         z1 = real[var][dinds0]
-        plans.append(_lib.LUPlan(lib, f.marginal(j), dom, dinds0 + 1 if len(dinds0) else None, z1 if len(dinds0) else None,
-                                 process.mean_of(j)))
+        marg = f.marginal(j)
+        # lusim.jl:66-107 assembles and factors once per variable; when the marginal covariance and the data nodes of a variable equal
+        # those of an earlier one (e.g. [1 rho; rho 1] * cov with shared data locations) the factor is shared and only d2 is computed
+        key = ([(int(m[0]), float(m[1]), np.asarray(m[2], dtype=np.float64).tobytes(), float(m[3]) if len(m) > 3 else 0.0) for m in marg],
+               dinds0.tobytes())
+        like = next((plans[i] for i, k in enumerate(keys) if k == key), None) if method.share_factor else None
+        plans.append(_lib.LUPlan(lib, marg, dom, dinds0 + 1 if len(dinds0) else None, z1 if len(dinds0) else None,
+                                 process.mean_of(j), like=like))
+        keys.append(key)
     if len(plans) == 2 and plans[0].Ns != plans[1].Ns:
         raise ValueError("DimensionMismatch: both variables must have the same number of simulation nodes (lusim.jl:164)")
     rho = f.rho() if len(names) == 2 else math.nan

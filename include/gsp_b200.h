@@ -122,6 +122,11 @@ int gsp_nearest_init(gsp_ctx* ctx, const gsp_domain* grid, int64_t nd, const dou
  * nd == 0 => unconditional.  Returns >0 (info) if the matrix is not positive definite. */
 int gsp_lu_plan_create(gsp_ctx* ctx, const gsp_cov_model* cov, const gsp_domain* dom, int64_t nd, const int64_t* dinds,
                        const double* z1, double mu, gsp_lu_plan** out);
+/* Plan of ANOTHER variable whose marginal covariance and data nodes are those of `base` - cosimulation with a proportional model
+ * such as [1 rho; rho 1] * cov, where the `map` at lusim.jl:66-107 assembles and factors the same matrix once per variable: the new
+ * plan SHARES base's factor (reference counted; either plan may be destroyed first) and only computes its own d2 from z1 (lusim.jl:102).
+ * nd / dinds must equal base's.  The caller decides that the marginal covariances are equal (the glue compares the flattened structures). */
+int gsp_lu_plan_create_like(gsp_lu_plan* base, int64_t nd, const int64_t* dinds, const double* z1, double mu, gsp_lu_plan** out);
 int gsp_lu_plan_destroy(gsp_lu_plan* plan);
 /* sizes[0] = N, sizes[1] = Nd, sizes[2] = Ns */
 int gsp_lu_plan_sizes(gsp_lu_plan* plan, int64_t sizes[3]);

@@ -182,6 +182,7 @@ function preprocess(::AbstractRNG, process::GaussianProcess, method::LUSIM_B200,
   ctx = context()
   cdom, keep = cdomain(domain)
   plans = Ptr{Cvoid}[]
+  keys = Tuple{Vector{CStructure},Vector{Int64}}[]
   Ns = 0
   GC.@preserve keep begin
     for (j, var) in enumerate(vars)
@@ -189,13 +190,23 @@ function preprocess(::AbstractRNG, process::GaussianProcess, method::LUSIM_B200,
       structs = flatten(f, j)
       model = Ref(CCovModel(length(structs), 0, pointer(structs)))
       ref = Ref{Ptr{Cvoid}}(C_NULL)
+      # the `map` at lusim.jl:66-107 assembles and factors once per variable; a variable whose marginal covariance and data nodes
+      # equal an earlier one's (e.g. [1 ρ; ρ 1] * cov with shared data locations) shares that factor and only gets its own d₂
+      twin = findfirst(k -> k == (structs, dinds), keys)
       GC.@preserve structs dinds z₁ begin
-        rc = ccall((:gsp_lu_plan_create, LIB), Cint,
-                   (Ptr{Cvoid}, Ptr{CCovModel}, Ptr{CDomain}, Int64, Ptr{Int64}, Ptr{Float64}, Float64, Ptr{Ptr{Cvoid}}),
-                   ctx.ptr, model, Ref(cdom), length(dinds), dinds, z₁, Float64(ustrip(μ[j])), ref)
+        rc = if isnothing(twin)
+          ccall((:gsp_lu_plan_create, LIB), Cint,
+                (Ptr{Cvoid}, Ptr{CCovModel}, Ptr{CDomain}, Int64, Ptr{Int64}, Ptr{Float64}, Float64, Ptr{Ptr{Cvoid}}),
+                ctx.ptr, model, Ref(cdom), length(dinds), dinds, z₁, Float64(ustrip(μ[j])), ref)
+        else
+          ccall((:gsp_lu_plan_create_like, LIB), Cint,
+                (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Float64}, Float64, Ptr{Ptr{Cvoid}}),
+                plans[twin], length(dinds), dinds, z₁, Float64(ustrip(μ[j])), ref)
+        end
       end
       check(ctx, rc)
       push!(plans, ref[])
+      push!(keys, (structs, dinds))
       Ns = nelements(domain) - length(dinds)
     end
   end

@@ -399,3 +399,35 @@ def test_nearest_init_device(emu_lib):
             assert list(dinds + 1) == [2526, 5076, 7551]
     d0, z0 = emu_lib.nearest_init((4, 4), (0.0, 0.0), (1.0, 1.0), np.zeros((0, 2)), np.zeros(0))
     assert len(d0) == 0 and len(z0) == 0
+
+
+def test_lusim_shared_factor_plan(emu_lib):
+    """gsp_lu_plan_create_like: a second variable with the same marginal covariance and data nodes shares the factor and gets its own d2;
+    fields equal those of an independently built plan bit for bit; the base plan may be destroyed first; mismatching nodes are rejected"""
+    rng = np.random.default_rng(12)
+    dims = (14, 11)
+    st = iso(O.SPHERICAL, 1.0, 6.0, 2)
+    dom = (gsp._lib.make_grid_domain(dims, [0, 0], [1, 1]), None)
+    dinds = np.sort(rng.choice(154, 20, replace=False))
+    za, zb = rng.standard_normal(20), rng.standard_normal(20)
+    base = gsp.LUPlan(emu_lib, st, dom, dinds + 1, za, 0.0)
+    shared = gsp.LUPlan(emu_lib, None, None, dinds + 1, zb, 0.0, like=base)
+    own = gsp.LUPlan(emu_lib, st, dom, dinds + 1, zb, 0.0)
+    W, W1 = rng.standard_normal((134, 5)), rng.standard_normal((134, 5))
+    assert np.array_equal(shared.sample(5, W, rho=0.7, W1=W1), own.sample(5, W, rho=0.7, W1=W1))
+    assert np.array_equal(shared.get()[0], own.get()[0])
+    base.close()                                                   # the factor lives on in `shared`
+    Z = shared.sample(5, W)
+    assert np.array_equal(Z, own.sample(5, W)) and np.array_equal(Z[dinds], np.repeat(zb[:, None], 5, 1))
+    other = dinds.copy()
+    other[3] += 1 if other[3] + 1 not in dinds else 2
+    with pytest.raises(ValueError):
+        gsp.LUPlan(emu_lib, None, None, np.sort(other) + 1, zb, 0.0, like=shared)
+    shared.close(), own.close()
+    # through rand(): the cosimulation of test/field.jl:33-38 with and without sharing gives the same fields
+    func = [[1.0, 0.95], [0.95, 1.0]] * gsp.SphericalCovariance(range=10.0)
+    proc = gsp.GaussianProcess(func, [0.0, 0.0])
+    grid = gsp.CartesianGrid(30)
+    a = gsp.rand(proc, grid, 2, rng=np.random.default_rng(5), method=gsp.LUSIM(library=emu_lib))
+    b = gsp.rand(proc, grid, 2, rng=np.random.default_rng(5), method=gsp.LUSIM(library=emu_lib, share_factor=False))
+    assert np.array_equal(a[1].field2, b[1].field2) and np.array_equal(a[0].field1, b[0].field1)

@@ -161,6 +161,33 @@ def test_lusim_rejects_w1_without_w(gpu_lib):
     plan.close()
 
 
+def test_lusim_shared_factor_gpu(gpu_lib):
+    """gsp_lu_plan_create_like on the GPU: the second variable of a cosimulation shares the first one's factor; fields are bit-identical
+    to those of a plan that factored on its own, and equal the oracle (lusim.jl:66-107,164)"""
+    rng = np.random.default_rng(21)
+    dims = (96, 80)                                  # 7,680 nodes: the panel algorithm (60 blocks)
+    N, nd, R = 7680, 200, 16
+    C = np.array([[1.0, 0.7], [0.7, 1.0]])
+    mv = [(O.SPHERICAL, C, np.eye(3) / 15.0)]
+    m0 = O.marginalize(mv, 0)
+    st = [(s_.kind, s_.sill, s_.A) for s_ in m0]
+    coords = O.grid_centroids(dims, [0, 0], [1, 1])
+    dinds = np.sort(rng.choice(N, nd, replace=False))
+    z = [rng.standard_normal(nd) * 0.4, rng.standard_normal(nd) * 0.4]
+    base = gsp.LUPlan(gpu_lib, st, grid_dom(dims), dinds + 1, z[0], 0.0)
+    shared = gsp.LUPlan(gpu_lib, None, None, dinds + 1, z[1], 0.0, like=base)
+    own = gsp.LUPlan(gpu_lib, st, grid_dom(dims), dinds + 1, z[1], 0.0)
+    W1, W2 = rng.standard_normal((base.Ns, R)), rng.standard_normal((base.Ns, R))
+    Z2 = shared.sample(R, W2, rho=0.7, W1=W1)
+    assert np.array_equal(Z2, own.sample(R, W2, rho=0.7, W1=W1))
+    pre = O.lusim_preprocess(m0, coords, dinds, z[1], 0.0)
+    assert relerr(Z2, O.lusim_sample(pre, W2, 0.7, W1)) < TOL
+    base.close()
+    assert np.array_equal(shared.sample(R, W2, rho=0.7, W1=W1), Z2)
+    assert shared.times()[1] == 0.0 and shared.times()[2] > 0.0
+    shared.close(), own.close()
+
+
 def test_lusim_pointset_3d(gpu_lib):
     rng = np.random.default_rng(8)
     X = rng.uniform(0, 20, (700, 3))

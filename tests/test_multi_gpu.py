@@ -104,6 +104,30 @@ def test_fftsim_and_ensemble_over_devices_bit_identical(gpu_lib, G):
     e1.close(), eG.close(), p1.close(), pG.close(), libG.close()
 
 
+@pytest.mark.parametrize("G", GS)
+def test_shared_factor_plan_over_devices(gpu_lib, G):
+    """gsp_lu_plan_create_like on a multi-device context: the second variable shares the distributed factor on every device"""
+    rng = np.random.default_rng(60 + G)
+    dims = (96, 96)
+    N, nd, R = 9216, 150, 4 * G + 1
+    st = iso(O.SPHERICAL, 1.0, 12.0, 2)
+    dinds = np.sort(rng.choice(N, nd, replace=False))
+    za, zb = rng.standard_normal(nd), rng.standard_normal(nd)
+    libG = gsp.Library(devices=list(range(G)))
+    base = gsp.LUPlan(libG, st, grid_dom(dims), dinds + 1, za, 0.0)
+    shared = gsp.LUPlan(libG, None, None, dinds + 1, zb, 0.0, like=base)
+    own = gsp.LUPlan(libG, st, grid_dom(dims), dinds + 1, zb, 0.0)
+    W1, W2 = rng.standard_normal((base.Ns, R)), rng.standard_normal((base.Ns, R))
+    Zs = shared.sample(R, W2, rho=0.7, W1=W1)
+    assert relerr(Zs, own.sample(R, W2, rho=0.7, W1=W1)) < 1e-12   # two factorizations over G devices: not bit-identical to each other
+    assert np.array_equal(Zs[dinds], np.repeat(zb[:, None], R, 1))
+    one = gsp.LUPlan(gpu_lib, st, grid_dom(dims), dinds + 1, zb, 0.0)
+    assert relerr(Zs, one.sample(R, W2, rho=0.7, W1=W1)) < 1e-12
+    base.close()
+    assert np.array_equal(shared.sample(R, W2, rho=0.7, W1=W1), Zs)
+    shared.close(), own.close(), one.close(), libG.close()
+
+
 @need(2)
 def test_c3_over_all_devices(gpu_lib):
     """BASELINE configs[2] (16,384 nodes + 1,000 data) factored over every visible GPU == the single-device plan"""

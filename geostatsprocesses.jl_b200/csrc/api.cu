@@ -250,7 +250,11 @@ extern "C" int gsp_ctx_create(int32_t ndev, const int32_t* devs, gsp_ctx** out) 
     for (auto& b : ctx->devs) {
       if (a.dev == b.dev) continue;
       int can = 0;
-      if (cudaDeviceCanAccessPeer(&can, a.dev, b.dev) == cudaSuccess && can) {
+      const bool asked = cudaDeviceCanAccessPeer(&can, a.dev, b.dev) == cudaSuccess;
+#ifndef GSP_EMU
+      if (!asked || !can) ctx->peer_ok = false;  // no NVLink / PCIe peer path: the factorization then runs on device 0 and L is copied
+#endif
+      if (asked && can) {
         cudaSetDevice(a.dev);
         cudaDeviceEnablePeerAccess(b.dev, 0);
         cudaGetLastError();  // "already enabled" is fine

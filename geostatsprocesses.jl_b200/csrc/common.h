@@ -63,6 +63,7 @@ struct DevCtx {
 
 struct gsp_ctx {
   std::vector<gsp::DevCtx> devs;
+  bool peer_ok = true;  // every device of the context can map every other one's memory (needed by the distributed factorization)
   std::string err;
   std::mutex mu;
   double last_sample_ms = 0.0;

@@ -316,7 +316,8 @@ extern "C" int gsp_lu_plan_create(gsp_ctx* ctx, const gsp_cov_model* cov, const 
   p->h_dind0 = dind0;
   const int ndev = (int)ctx->devs.size();
   const int nb = (int)(p->Np / 128);
-  const CholChoice cc = choose_chol(ndev, nb);
+  CholChoice cc = choose_chol(ndev, nb);
+  if (ndev > 1 && !ctx->peer_ok) cc.dist = false;  // peer stores need peer access; without it: factor on device 0, copy L (cudaMemcpyPeer)
   const int nbuild = cc.dist ? ndev : 1;   // devices that take part in the factorization
 
   EventSet tev;

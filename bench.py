@@ -438,6 +438,16 @@ def run_gpu(args):
         # pass-model bytes: 5 passes, each reads and writes a half spectrum (or the real field), + F in the z pass
         pass_bytes = 8.0 * N * 2 + 16.0 * plan_nh(DIMS) * 8 + 8.0 * plan_nh(DIMS)
         dram = pass_bytes * Rg * args.steps / dev_max / 1e9
+        try:  # the same with the DRAM bytes ncu counted for the five kernels (per-kernel windows: stores still in L2 at a kernel's end are
+            # not counted anywhere, so this is a LOWER bound of the traffic and the pass model an upper one)
+            with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+                tj = json.load(f)
+            ncu_bytes = sum(k["traffic_bytes"] for k in tj["kernels"].values()) if DIMS == (256, 256, 256) else None
+        except Exception:
+            ncu_bytes = None
+        if ncu_bytes:
+            roof.update({"pipeline_ncu_dram_bytes_per_realization": ncu_bytes,
+                         "pipeline_dram_frac_ncu_bytes": ncu_bytes * Rg * args.steps / dev_max / 1e9 / pk["hbm_gbs"]})
         roof.update({"pipeline_alg_bytes_per_realization": alg_bytes, "pipeline_achieved": pipe, "pipeline_frac": pipe / pk["hbm_gbs"],
                      "pipeline_pass_model_bytes_per_realization": pass_bytes, "pipeline_dram_achieved": dram,
                      "pipeline_dram_frac": dram / pk["hbm_gbs"],

@@ -12,7 +12,7 @@ from .functions import (MaternCovariance, MaternVariogram, CircularCovariance, C
                         GaussianCovariance, GaussianVariogram, GeoStatsFunction, NuggetEffect, PentasphericalCovariance,
                         PentasphericalVariogram, SphericalCovariance, SphericalVariogram, metric_matrix)
 from .processes import (FFTSIM, LUSIM, Ensemble, ExplicitInit, FieldSimulationMethod, GaussianProcess, NearestInit,  # noqa: F401
-                        default_library, defaultsimulation, initialize, merge_moments, preprocess_fftsim, preprocess_lusim, rand,
+                        default_library, defaultsimulation, expectedvalue, initialize, mean, merge_moments, preprocess_fftsim, preprocess_lusim, rand,
                         rand_fftsim, rand_lusim, set_devices)
 
 __version__ = "0.1.0"

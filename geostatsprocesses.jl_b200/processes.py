@@ -346,6 +346,50 @@ def merge_moments(parts):
     return cnt, mean, m2 / (cnt - 1)
 
 
+def mean(process: GaussianProcess, domain, *, data: Optional[GeoTable] = None, init=None, minneighbors: int = 1, maxneighbors: int = 10,
+         neighborhood=None, distance=None, library: Optional[_lib.Library] = None) -> GeoTable:
+    """mean(process, domain; data, init, kwargs...) - src/expectation/field.jl:43-44.
+    Without data: priormean (expectation/field/gaussian.jl:5-19), the process mean on every element.  With data: posteriormean
+    (gaussian.jl:21-25) = simple Kriging of the data where they are onto the domain, GeoStatsModels.fitpredict's defaults
+    (k nearest neighbours, maxneighbors = 10, Euclidean) - computed on the device by the Kriging kernel that conditions FFTSIM
+    (gsp_fft_plan_condition -> gsp_fft_plan_condmean).  Grids and views of grids, univariate functions; `init` places nothing here
+    (the Kriging uses the data's own coordinates) and is accepted for signature parity."""
+    f = process.func
+    if data is None:
+        names = process.defaultschema()
+        n = domain.nelements()
+        return georef({v: np.full(n, process.mean_of(j)) for j, v in enumerate(names)}, domain)
+    if neighborhood is not None or distance is not None:
+        raise NotImplementedError("posterior mean on the GPU supports the default search only (k nearest neighbours, Euclidean distance)")
+    assert f.nvariables() == 1, "the posterior mean is offloaded for univariate functions only"
+    grid = domain.parent()
+    if not isinstance(grid, CartesianGrid):
+        raise ValueError("the posterior mean on the GPU requires a (view of a) CartesianGrid")
+    lib = library or default_library()
+    names = data.names()
+    plan = _lib.FFTPlan(lib, f.flat(), grid.dims, grid.origin, grid.spacing)
+    try:
+        out = {}
+        inds1 = domain.parentindices()
+        for var in names:
+            vals = np.asarray(data[var], dtype=np.float64)
+            keep = ~np.isnan(vals)
+            real, mask = initialize(process, domain, GeoTable({var: vals}, data.domain), init or NearestInit(), lib)
+            knodes0 = np.flatnonzero(mask[var])
+            plan.condition(process.mean_of(0), data.domain.centroids()[keep], vals[keep], knodes0 + 1, inds1, minneighbors=minneighbors,
+                           maxneighbors=maxneighbors)
+            out[var] = plan.condmean()
+    finally:
+        plan.close()
+    return georef(out, domain)
+
+
+def expectedvalue(process: GaussianProcess, domain, **kwargs) -> GeoTable:
+    """expectedvalue(process, domain; kwargs...) - src/expectation/field.jl:17-23: Gaussian processes are continuous and analytical,
+    so this is `mean`."""
+    return mean(process, domain, **kwargs)
+
+
 def _fresh_seed() -> int:
     """64 fresh bits per unseeded call (os entropy through numpy's SeedSequence)."""
     return int(np.random.SeedSequence().generate_state(1, dtype=np.uint64)[0])

@@ -568,6 +568,24 @@ def test_rand_api_gpu(gpu_lib):
     assert real.domain == vgrid and real.nrow == 5000
 
 
+def test_expectation_gpu(gpu_lib):
+    """mean(process, domain; data) / expectedvalue (src/expectation/field.jl:17-44, field/gaussian.jl:21-25) - the reference's own
+    "Expectation" test (test/field.jl:156-176) on the device Kriging, plus the oracle's Kriging on every element"""
+    proc = gsp.GaussianProcess(gsp.SphericalVariogram(range=35.0))
+    grid = gsp.CartesianGrid((0.5, 0.5), (100.5, 100.5), dims=(100, 100))
+    assert np.all(gsp.mean(proc, grid).field == 0.0)
+    pts = [(25.0, 25.0), (50.0, 75.0), (75.0, 50.0)]
+    data = gsp.georef({"Z": [1.0, 0.0, 1.0]}, pts)
+    mval = gsp.mean(proc, grid, data=data, library=gpu_lib)
+    Z = mval.Z.reshape(100, 100)
+    assert abs(Z[24, 24] - 1.0) < 1e-12 and abs(Z[74, 49]) < 1e-12 and abs(Z[49, 74] - 1.0) < 1e-12
+    st = ostructs(iso(O.SPHERICAL, 1.0, 35.0, 2))
+    cent = O.grid_centroids((100, 100), [0.5, 0.5], [1.0, 1.0])
+    nbr, lam = O.krige_neighbors_weights(st, cent, np.array(pts), 10)
+    assert np.abs(mval.Z - (lam * np.array([1.0, 0.0, 1.0])[nbr]).sum(axis=1)).max() < 1e-10
+    assert np.array_equal(gsp.expectedvalue(proc, grid, data=data, library=gpu_lib).Z, mval.Z)
+
+
 # ------------------------------------------------------------------ §8f rank 1: device-resident ensembles (src/ensembles.jl:42-52)
 def test_ensemble_reference_pins_gpu(gpu_lib):
     """the reference's value-level ensemble test (test/ensembles.jl:24-59) on the CUDA kernels"""

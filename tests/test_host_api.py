@@ -144,3 +144,31 @@ def test_unseeded_rand_calls_are_independent(emu_lib):
         c = gsp.rand(proc, grid, 2, rng=11, method=method)
         d = gsp.rand(proc, grid, 2, rng=11, method=method)
         assert np.array_equal(c[0].field, d[0].field) and np.array_equal(c[1].field, d[1].field)
+
+
+def test_expectation(emu_lib):  # test/field.jl:156-176 ("Expectation") on a 40 x 40 grid (the emulator is slow); posterior mean = simple Kriging
+    import gsp_oracle as O
+    from helpers import ostructs, iso
+
+    proc = gsp.GaussianProcess(gsp.SphericalVariogram(range=14.0))
+    grid = gsp.CartesianGrid((0.5, 0.5), (40.5, 40.5), dims=(40, 40))
+    mval = gsp.mean(proc, grid)
+    assert np.all(mval.field == 0.0) and mval.nrow == 1600
+    assert np.all(gsp.mean(gsp.GaussianProcess(gsp.SphericalCovariance(range=5.0), 2.5), grid).field == 2.5)
+    pts = [(10.0, 10.0), (20.0, 30.0), (30.0, 20.0)]
+    data = gsp.georef({"Z": [1.0, 0.0, 1.0]}, pts)
+    mval = gsp.mean(proc, grid, data=data, library=emu_lib)
+    Z = mval.Z.reshape(40, 40)                # [y][x]: element (i, j), 1-based, is Z[j-1, i-1]; the data sit on centroids
+    assert abs(Z[9, 9] - 1.0) < 1e-12 and abs(Z[29, 19] - 0.0) < 1e-12 and abs(Z[19, 29] - 1.0) < 1e-12
+    # against the oracle's Kriging (expectation/field/gaussian.jl:21-25; GeoStatsModels.fitpredict defaults: 10 nearest -> all 3 data)
+    st = ostructs(iso(O.SPHERICAL, 1.0, 14.0, 2))
+    cent = O.grid_centroids((40, 40), [0.5, 0.5], [1.0, 1.0])
+    nbr, lam = O.krige_neighbors_weights(st, cent, np.array(pts), 10)
+    zo = (lam * np.array([1.0, 0.0, 1.0])[nbr]).sum(axis=1)
+    assert np.abs(mval.Z - zo).max() < 1e-10
+    ev = gsp.expectedvalue(proc, grid, data=data, library=emu_lib)
+    assert np.array_equal(ev.Z, mval.Z) and np.array_equal(gsp.expectedvalue(proc, grid).field, gsp.mean(proc, grid).field)
+    # a view of the grid: only its elements are predicted
+    vgrid = grid.view(range(1, 801))
+    mv = gsp.mean(proc, vgrid, data=data, library=emu_lib)
+    assert mv.nrow == 800 and np.abs(mv.Z - zo[:800]).max() < 1e-10

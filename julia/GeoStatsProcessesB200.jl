@@ -326,6 +326,18 @@ function randsingle(rng::AbstractRNG, process::GaussianProcess, method::FFTSIM_B
 end
 
 # ------------------------------------------------------------------------------------------------
+# Posterior mean (src/expectation/field/gaussian.jl:21-25: simple Kriging of the data onto the domain, fitpredict's default search:
+# k nearest neighbours, maxneighbors = 10) with the device Kriging that conditions FFTSIM.  `mean(process, domain; data)` has no
+# method argument to dispatch on, so the offload is a separate function.
+function mean_b200(process::GaussianProcess, domain; data, init=NearestInit(), minneighbors=1, maxneighbors=10)
+  pre = preprocess(Random.default_rng(), process, FFTSIM_B200(; minneighbors, maxneighbors), init, domain, data)
+  n = isempty(pre.inds) ? prod(pre.dims) : length(pre.inds)
+  z̄ = Vector{Float64}(undef, n)
+  check(context(), ccall((:gsp_fft_plan_condmean, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), pre.plan, z̄))
+  georef((; pre.var => z̄ .* unit(process.mean)), domain)
+end
+
+# ------------------------------------------------------------------------------------------------
 # Device-resident ensembles: Ensemble(domain, reals; fetch) (src/ensembles.jl:10-16) whose realizations stay in
 # HBM.  `reals` are lightweight handles, `fetch` downloads one realization (ensembles.jl:27-31), and the
 # statistics of ensembles.jl:42-52 are overloaded to run on the device instead of the O(n R) `ereduce` loops.
@@ -403,6 +415,6 @@ end
 quantile(e::Ensemble{<:Any,DeviceReals}, p::Number) = first(quantile(e, [p]))
 release!(e::Ensemble{<:Any,DeviceReals}) = ccall((:gsp_ensemble_destroy, LIB), Cint, (Ptr{Cvoid},), e.reals.ptr)
 
-export LUSIM_B200, FFTSIM_B200, rand_resident, release!
+export LUSIM_B200, FFTSIM_B200, rand_resident, mean_b200, release!
 
 end # module

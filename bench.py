@@ -3,11 +3,19 @@
   python bench.py --gpus N --steps K --warmup W            (N>1: launched by torchrun, one rank per GPU)
   python bench.py --impl reference ...                     (CPU arm: the oracle restatement on the host cores)
 
-Workload (config.workload): FFTSIM on a 3-D CartesianGrid 256^3, anisotropic SphericalCovariance
+Headline workload (config.workload): FFTSIM on a 3-D CartesianGrid 256^3, anisotropic SphericalCovariance
 (ranges 40/20/10, 30 deg z-rotation), 64 realizations per GPU per step (BASELINE.json configs[3]: 512
 realizations over 8 GPUs), injected uniform noise resident in HBM.  A "step" = one pass of the hot
 path over that batch.  Realizations shard over ranks with no data-path collective ("scaling": "weak").
-LUSIM 16k nodes (configs[2]) is measured in the same run and reported under "lusim".
+`e2e`: the same metric through gsp_fft_sample with pinned HOST buffers (H2D + D2H inside the timed region), the measured
+pinned-copy rate of the box beside it, and the resident variant (ensemble stays in HBM, mean + variance maps return).
+
+LUSIM half of the metric (`lusim`, every N): rank 0 opens ONE context over all N GPUs of the job - the library's multi-device model -
+and times configs[2] (C3: 16,384 nodes + 1,000 data, 1,000 realizations) and configs[4] (C5: bivariate, 32,768 nodes, 4,096
+realizations): plan (assembly + distributed Cholesky + d2), resident sampling, end to end with host noise / host fields; `roofline`
+per configuration against the FP64 tensor peak measured IN THIS RUN (cuBLAS Dgemm through torch.matmul), `speedup_vs_n1` against a
+1-device context in the same run, `cpu_baseline` (oracle on the host cores) at N = 1.  `lusim.c1` and `fftsim_c2` are one-line
+results of configs[0] and configs[1].
 """
 import argparse
 import json

@@ -26,6 +26,10 @@ which tests/test_oracle.py re-checks).  The oracle is additionally pinned to
 mathematics by known-answer tests in tests/test_oracle.py (L L' = C, conditional
 mean/covariance identities, FFT-MA invariants).
 
+What WOULD pin it: tests/golden/make_golden.jl runs the real GeoStatsProcesses v0.13.0 (Julia needed, absent here),
+captures the noise it drew and writes reference vectors that tests/test_reference_fixtures.py compares this file
+with at 1e-12 (strict-xfail until the vectors are committed).
+
 All noise is INJECTED (normals for LUSIM, uniforms for FFTSIM) so that the GPU path
 and the oracle consume identical arrays.
 """

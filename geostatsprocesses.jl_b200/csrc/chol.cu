@@ -504,6 +504,9 @@ struct Chol {
     g.C = at(cr, cc); g.ldc = ld;
     g.mt = mt; g.nt = nt; g.K = kb * DB; g.tri = tri ? 1 : 0;
     g.max_ctas = side_grid ? side_ctas : 0;
+    GSP_DEP_ACCESS(A, ar, ar + mt, ac, ac + kb, false);
+    GSP_DEP_ACCESS(A, br, br + nt, bc, bc + kb, false);
+    GSP_DEP_ACCESS(A, cr, cr + mt, cc, cc + nt, true);
     check(launch_gemm<GEMM_SUB, false>(s, g));
   }
 
@@ -517,6 +520,9 @@ struct Chol {
       g.C = at(r0, c0); g.ldc = ld;
       g.mt = nr; g.nt = 1; g.K = DB;
       set_peers(g, (long long)r0 * DB + (long long)c0 * DB * ld);
+      GSP_DEP_ACCESS(invD, c0, c0 + 1, 0, 1, false);
+      GSP_DEP_ACCESS(A, r0, r0 + nr, c0, c0 + 1, true);
+      for (int p = 0; p < peers.n; ++p) GSP_DEP_ACCESS(peers.A[p], r0, r0 + nr, c0, c0 + 1, true);
       check(launch_gemm<GEMM_SET, false>(st, g));
       return;
     }
@@ -537,6 +543,14 @@ struct Chol {
     g.C = A + (long long)ccol0 * DB * ld; g.ldc = ld;
     g.mt = nrows; g.nt = ncolblk; g.K = kb * DB;
     g.rows = rows_dev; g.stair = stair ? 1 : 0; g.colblk0 = ccol0;
+#ifdef GSP_EMU
+    for (int i = 0; i < nrows; ++i) {  // (device memory is host memory in the emulator)
+      const int r = rows_dev[i], c1 = stair ? std::min(ccol0 + ncolblk, r + 1) : ccol0 + ncolblk;
+      GSP_DEP_ACCESS(A, r, r + 1, kcol0, kcol0 + kb, false);
+      GSP_DEP_ACCESS(A, r, r + 1, ccol0, c1, true);
+    }
+    GSP_DEP_ACCESS(A, ccol0, ccol0 + ncolblk, kcol0, kcol0 + kb, false);
+#endif
     check(launch_gemm<GEMM_SUB, false>(s, g, valid_tiles));
   }
   void trsm_rows(cudaStream_t s, const int* rows_dev, int nrows, int c0, int nc, bool multicast = true) {
@@ -549,6 +563,13 @@ struct Chol {
       g.mt = nrows; g.nt = 1; g.K = DB;
       g.rows = rows_dev;
       if (multicast) set_peers(g, (long long)c0 * DB * ld);
+#ifdef GSP_EMU
+      GSP_DEP_ACCESS(invD, c0, c0 + 1, 0, 1, false);
+      for (int i = 0; i < nrows; ++i) {
+        GSP_DEP_ACCESS(A, rows_dev[i], rows_dev[i] + 1, c0, c0 + 1, true);
+        for (int p = 0; p < g.npeer; ++p) GSP_DEP_ACCESS(peers.A[p], rows_dev[i], rows_dev[i] + 1, c0, c0 + 1, true);
+      }
+#endif
       check(launch_gemm<GEMM_SET, false>(s, g));
       return;
     }
@@ -560,6 +581,8 @@ struct Chol {
   // blocks [r0, r0 + nr) x [c0, c0 + nc) of the matrix to the other devices (many CTAs: one SM's peer stores are slow)
   void push_rect(cudaStream_t s, int r0, int nr, int c0, int nc) {
     if (peers.n <= 0 || nr <= 0 || nc <= 0) return;
+    GSP_DEP_ACCESS(A, r0, r0 + nr, c0, c0 + nc, false);
+    for (int p = 0; p < peers.n; ++p) GSP_DEP_ACCESS(peers.A[p], r0, r0 + nr, c0, c0 + nc, true);
     ProfScope prof_("push_rect", s);
     GSP_LAUNCH(push_rect_kernel, dim3((unsigned)(8 * nr * nc)), dim3(256), 0, s, (const double*)A, ld, (long long)r0, nr, (long long)c0, peers);
     g_launches++;
@@ -575,12 +598,20 @@ struct Chol {
       check(cudaMemsetAsync(flags, 0, SQ_FLAGS * sizeof(int), st));
       auto kfn = potrf_square_kernel;
       check(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, SQ_SMEM));
+      GSP_DEP_ACCESS(A, o, o + n, o, o + n, true);
+      GSP_DEP_ACCESS(invD, o, o + n, 0, 1, true);
       ProfScope prof_("potrf_square", st);
       GSP_LAUNCH_COOP(kfn, dim3((unsigned)(2 * n)), dim3(256), (size_t)SQ_SMEM, st, A, ld, (long long)o, n, invD, info, flags);
       g_launches++;
       check(cudaGetLastError());
     }
     if (peers.n > 0) {
+      GSP_DEP_ACCESS(A, o, o + n, o, o + n, false);
+      GSP_DEP_ACCESS(invD, o, o + n, 0, 1, false);
+      for (int p = 0; p < peers.n; ++p) {
+        GSP_DEP_ACCESS(peers.A[p], o, o + n, o, o + n, true);
+        GSP_DEP_ACCESS(peers.invD[p], o, o + n, 0, 1, true);
+      }
       ProfScope prof_("push_square", st);
       GSP_LAUNCH(push_square_kernel, dim3((unsigned)(8 * (n + n * (n + 1) / 2))), dim3(256), 0, st, (const double*)A, ld, (long long)o, n,
                  (const double*)invD, peers);
@@ -596,6 +627,8 @@ struct Chol {
     if (n == 1) {
       auto kfn = potrf_diag_kernel;
       check(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM));
+      GSP_DEP_ACCESS(A, o, o + 1, o, o + 1, true);
+      GSP_DEP_ACCESS(invD, o, o + 1, 0, 1, true);
       ProfScope prof_("potrf_diag", st);
       GSP_LAUNCH(kfn, dim3(1), dim3(256), (size_t)DIAG_SMEM, st, A, ld, (long long)o, invD, info);
       g_launches++;
@@ -734,6 +767,9 @@ cudaError_t chol_factor_dist(const std::vector<DistDev>& devs, long long ld, int
   // the callers' earlier work on the main streams (assembly of the own rows) precedes everything on the other two streams
   for (int g = 0; g < G; ++g) {
     cudaEvent_t e = record(g, devs[g].main);
+#ifdef GSP_EMU
+    if (getenv("GSP_DEPCHECK_SELFTEST")) continue;  // test-only: drop this dependency - the checker must then report the race
+#endif
     check(cudaStreamWaitEvent(devs[g].aux, e, 0));
     check(cudaStreamWaitEvent(devs[g].upd, e, 0));
   }
@@ -755,6 +791,12 @@ cudaError_t chol_factor_dist(const std::vector<DistDev>& devs, long long ld, int
     } else {
       ch[o].potrf(c0, nq, nullptr, 0);
       if (ch[o].peers.n > 0) {
+        GSP_DEP_ACCESS(devs[o].A, c0, c0 + nq, c0, c0 + nq, false);
+        GSP_DEP_ACCESS(devs[o].invD, c0, c0 + nq, 0, 1, false);
+        for (int p = 0; p < ch[o].peers.n; ++p) {
+          GSP_DEP_ACCESS(ch[o].peers.A[p], c0, c0 + nq, c0, c0 + nq, true);
+          GSP_DEP_ACCESS(ch[o].peers.invD[p], c0, c0 + nq, 0, 1, true);
+        }
         ProfScope prof_("push_square", devs[o].main);
         GSP_LAUNCH(push_square_kernel, dim3((unsigned)(8 * (nq + nq * (nq + 1) / 2))), dim3(256), 0, devs[o].main, (const double*)devs[o].A, ld,
                    (long long)c0, nq, (const double*)devs[o].invD, ch[o].peers);
@@ -848,6 +890,10 @@ cudaError_t chol_factor_dist(const std::vector<DistDev>& devs, long long ld, int
   for (cudaEvent_t ev : evs) cudaEventDestroy(ev);
   for (auto& c : ch)
     for (cudaEvent_t ev : c.events) cudaEventDestroy(ev);
+#ifdef GSP_EMU
+  // test-only: every pair of launches touching the same blocks (one of them writing) must be ordered by streams / events
+  if (emu::dep_enabled() && emu::dep_check(1) != 0 && err == cudaSuccess) err = cudaErrorInvalidValue;
+#endif
   return err;
 }
 

@@ -19,6 +19,14 @@
 #define GSP_HD __host__ __device__
 #endif
 
+// Region annotations for the emulator's stream-dependency checker (tests/emu: GSP_DEPCHECK=1); nothing in the product build.
+// Units are the callers' choice per base pointer (the factorization uses 128-block rows / columns of a device's matrix).
+#ifdef GSP_EMU
+#define GSP_DEP_ACCESS(base, r0, r1, c0, c1, w) ::emu::dep_access((const void*)(base), (long long)(r0), (long long)(r1), (long long)(c0), (long long)(c1), (w))
+#else
+#define GSP_DEP_ACCESS(base, r0, r1, c0, c1, w) ((void)0)
+#endif
+
 #define GSP_DEV __device__ __forceinline__
 #define GSP_DEV_NOINLINE static __device__ __noinline__  // big scalar routines (bessel_k): one copy per kernel, not one per call site
 

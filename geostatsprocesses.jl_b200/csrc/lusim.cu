@@ -319,6 +319,12 @@ extern "C" int gsp_lu_plan_create(gsp_ctx* ctx, const gsp_cov_model* cov, const 
   CholChoice cc = choose_chol(ndev, nb);
   if (ndev > 1 && !ctx->peer_ok) cc.dist = false;  // peer stores need peer access; without it: factor on device 0, copy L (cudaMemcpyPeer)
   const int nbuild = cc.dist ? ndev : 1;   // devices that take part in the factorization
+#ifdef GSP_EMU
+  {  // test-only: record the stream / event graph of this plan build and check it (chol_factor_dist)
+    const char* env = getenv("GSP_DEPCHECK");
+    emu::dep_enable(env && env[0] == '1');
+  }
+#endif
 
   EventSet tev;
   cudaSetDevice(ctx->devs[0].dev);
@@ -364,6 +370,7 @@ extern "C" int gsp_lu_plan_create(gsp_ctx* ctx, const gsp_cov_model* cov, const 
       ddl.coords = dcoords.as<double>();
     }
     if (!cc.dist) {
+      GSP_DEP_ACCESS(d->A->as<double>(), 0, nb, 0, nb, true);
       launch_assemble(st, cd, ddl, ddl, dperm.as<long long>(), dperm.as<long long>(), p->Np, p->Np, d->A->as<double>(), p->Np, true);
     } else {
       std::vector<int> own;
@@ -372,6 +379,7 @@ extern "C" int gsp_lu_plan_create(gsp_ctx* ctx, const gsp_cov_model* cov, const 
         size_t b = a + 1;
         while (b < own.size() && own[b] == own[b - 1] + 1) ++b;
         const long long r0 = (long long)own[a] * 128, r1 = (long long)(own[b - 1] + 1) * 128;
+        GSP_DEP_ACCESS(d->A->as<double>(), own[a], own[b - 1] + 1, 0, own[b - 1] + 1, true);
         launch_assemble(st, cd, ddl, ddl, dperm.as<long long>() + r0, dperm.as<long long>(), r1 - r0, r1, d->A->as<double>() + r0, p->Np, true, r0);
         a = b;
       }

@@ -183,3 +183,107 @@ void launch_coop(dim3 grid, dim3 block, size_t smem, const std::function<void()>
 }
 
 }  // namespace emu
+
+
+// ---------------------------------------------------------------- stream-dependency recorder (see gsp_emu.h)
+#include <map>
+#include <string>
+namespace emu {
+namespace {
+struct DepAcc { const void* base; long long r0, r1, c0, c1; bool write; };
+struct DepNode { std::string name; void* stream; std::vector<int> deps; std::vector<DepAcc> acc; };
+struct DepState {
+  bool on = false;
+  std::vector<DepNode> nodes;
+  std::map<void*, int> last;                   // last node of a stream
+  std::map<void*, std::vector<int>> pending;   // nodes the stream waited on since its last node
+  std::map<void*, int> event_node;
+  std::vector<int> host_deps;                  // every later node follows these (host synchronisations)
+  std::vector<DepAcc> staged;
+  uintptr_t next_stream = 16;
+};
+DepState D;
+int dep_node(void* stream, const char* name) {
+  DepNode n;
+  n.name = name;
+  n.stream = stream;
+  auto it = D.last.find(stream);
+  if (it != D.last.end()) n.deps.push_back(it->second);
+  for (int d : D.pending[stream]) n.deps.push_back(d);
+  D.pending[stream].clear();
+  for (int d : D.host_deps) n.deps.push_back(d);
+  D.nodes.push_back(std::move(n));
+  D.last[stream] = (int)D.nodes.size() - 1;
+  return (int)D.nodes.size() - 1;
+}
+}  // namespace
+
+void dep_enable(bool on) {
+  D.on = on;
+  D.nodes.clear(); D.last.clear(); D.pending.clear(); D.event_node.clear(); D.host_deps.clear(); D.staged.clear();
+}
+bool dep_enabled() { return D.on; }
+void* dep_new_stream() { D.next_stream += 16; return (void*)D.next_stream; }
+void dep_access(const void* base, long long r0, long long r1, long long c0, long long c1, bool write) {
+  if (D.on && r1 > r0 && c1 > c0) D.staged.push_back({base, r0, r1, c0, c1, write});
+}
+void dep_launch(void* stream, const char* name) {
+  if (!D.on) return;
+  const int id = dep_node(stream, name);
+  D.nodes[id].acc = std::move(D.staged);
+  D.staged.clear();
+}
+void dep_event_record(void* ev, void* stream) {
+  if (!D.on) return;
+  D.event_node[ev] = dep_node(stream, "(event)");   // a marker node: carries the stream's pending waits too
+}
+void dep_stream_wait(void* stream, void* ev) {
+  if (!D.on) return;
+  auto it = D.event_node.find(ev);
+  if (it != D.event_node.end()) D.pending[stream].push_back(it->second);
+}
+void dep_host_sync(void* stream) {
+  if (!D.on) return;
+  if (stream == nullptr) {
+    for (auto& kv : D.last) D.host_deps.push_back(kv.second);
+  } else {
+    auto it = D.last.find(stream);
+    if (it != D.last.end()) D.host_deps.push_back(it->second);
+  }
+  // keep the list short: a host sync on X supersedes X's earlier entries transitively, but duplicates are harmless
+  if (D.host_deps.size() > 4096) D.host_deps.erase(D.host_deps.begin(), D.host_deps.begin() + 2048);
+}
+long long dep_check(int verbose) {
+  const size_t n = D.nodes.size(), words = (n + 63) / 64;
+  std::vector<std::vector<uint64_t>> anc(n, std::vector<uint64_t>(words, 0));
+  for (size_t j = 0; j < n; ++j)
+    for (int d : D.nodes[j].deps) {
+      if (d < 0 || (size_t)d >= j) continue;
+      anc[j][(size_t)d / 64] |= 1ull << ((size_t)d % 64);
+      for (size_t w = 0; w < words; ++w) anc[j][w] |= anc[(size_t)d][w];
+    }
+  long long bad = 0;
+  for (size_t j = 0; j < n; ++j) {
+    if (D.nodes[j].acc.empty()) continue;
+    for (size_t i = 0; i < j; ++i) {
+      if (D.nodes[i].acc.empty() || (anc[j][i / 64] >> (i % 64) & 1)) continue;
+      bool hit = false;
+      for (const DepAcc& a : D.nodes[i].acc) {
+        for (const DepAcc& b : D.nodes[j].acc)
+          if (a.base == b.base && (a.write || b.write) && a.r0 < b.r1 && b.r0 < a.r1 && a.c0 < b.c1 && b.c0 < a.c1) {
+            hit = true;
+            if (verbose && bad < 20)
+              fprintf(stderr, "DEPCHECK: unordered %s (#%zu, stream %p) %s rows [%lld,%lld) cols [%lld,%lld)  vs  %s (#%zu, stream %p) %s rows [%lld,%lld) cols [%lld,%lld) of %p\n",
+                      D.nodes[i].name.c_str(), i, D.nodes[i].stream, a.write ? "W" : "R", a.r0, a.r1, a.c0, a.c1, D.nodes[j].name.c_str(), j,
+                      D.nodes[j].stream, b.write ? "W" : "R", b.r0, b.r1, b.c0, b.c1, a.base);
+            break;
+          }
+        if (hit) break;
+      }
+      if (hit) ++bad;
+    }
+  }
+  if (verbose) fprintf(stderr, "DEPCHECK: %zu launches, %lld unordered conflicting pairs\n", n, bad);
+  return bad;
+}
+}  // namespace emu

@@ -38,6 +38,21 @@ static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) {
 // ---------------------------------------------------------------- runtime API subset
 typedef int cudaError_t;
 typedef struct emuStream_* cudaStream_t;
+// ---- stream-dependency recorder (GSP_DEPCHECK=1): every launch becomes a node ordered by its stream, by the events its stream
+// waited on and by host synchronisations; launches annotate the matrix regions they read / write; dep_check() reports every pair of
+// launches that touch overlapping regions (at least one writing) WITHOUT a happens-before path - a missing cudaStreamWaitEvent that
+// the sequential emulator would otherwise execute correctly by accident.
+namespace emu {
+void dep_enable(bool on);
+bool dep_enabled();
+void* dep_new_stream();
+void dep_access(const void* base, long long r0, long long r1, long long c0, long long c1, bool write);
+void dep_launch(void* stream, const char* name);
+void dep_event_record(void* ev, void* stream);
+void dep_stream_wait(void* stream, void* ev);
+void dep_host_sync(void* stream);  // nullptr: every stream
+long long dep_check(int verbose);
+}  // namespace emu
 typedef struct emuEvent_ { double t; }* cudaEvent_t;
 enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorInvalidValue = 1 };
 enum cudaMemcpyKind { cudaMemcpyHostToHost, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice, cudaMemcpyDefault };
@@ -49,7 +64,7 @@ static inline cudaError_t cudaPeekAtLastError() { return cudaSuccess; }
 static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 static inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
 static inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
-static inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
+static inline cudaError_t cudaDeviceSynchronize() { ::emu::dep_host_sync(nullptr); return cudaSuccess; }
 static inline cudaError_t cudaMalloc(void** p, size_t n) { *p = std::malloc(n ? n : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
 template <class T> static inline cudaError_t cudaMalloc(T** p, size_t n) { return cudaMalloc((void**)p, n); }
 static inline cudaError_t cudaFree(void* p) { std::free(p); return cudaSuccess; }
@@ -66,17 +81,17 @@ static inline cudaError_t cudaMemcpy2DAsync(void* d, size_t dp, const void* s, s
 }
 static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t = 0) { std::memset(d, v, n); return cudaSuccess; }
 static inline cudaError_t cudaMemset(void* d, int v, size_t n) { std::memset(d, v, n); return cudaSuccess; }
-static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = nullptr; return cudaSuccess; }
-static inline cudaError_t cudaStreamCreate(cudaStream_t* s) { *s = nullptr; return cudaSuccess; }
-static inline cudaError_t cudaStreamCreateWithPriority(cudaStream_t* s, unsigned, int) { *s = nullptr; return cudaSuccess; }
+static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = (cudaStream_t)::emu::dep_new_stream(); return cudaSuccess; }
+static inline cudaError_t cudaStreamCreate(cudaStream_t* s) { *s = (cudaStream_t)::emu::dep_new_stream(); return cudaSuccess; }
+static inline cudaError_t cudaStreamCreateWithPriority(cudaStream_t* s, unsigned, int) { *s = (cudaStream_t)::emu::dep_new_stream(); return cudaSuccess; }
 static inline cudaError_t cudaDeviceGetStreamPriorityRange(int* lo, int* hi) { *lo = 0; *hi = -5; return cudaSuccess; }
 static inline cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
-static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
-static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) { return cudaSuccess; }
+static inline cudaError_t cudaStreamSynchronize(cudaStream_t s) { ::emu::dep_host_sync(s ? (void*)s : (void*)1); return cudaSuccess; }
+static inline cudaError_t cudaStreamWaitEvent(cudaStream_t s, cudaEvent_t e, unsigned = 0) { ::emu::dep_stream_wait((void*)s, (void*)e); return cudaSuccess; }
 static inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = new emuEvent_{0}; return cudaSuccess; }
 static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { return cudaEventCreate(e); }
 static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
-static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t = 0) { return cudaSuccess; }
+static inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t s = 0) { ::emu::dep_event_record((void*)e, (void*)s); return cudaSuccess; }
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return cudaSuccess; }
 template <class F> static inline cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess; }
@@ -234,6 +249,8 @@ template <class K, class... Args>
 inline void emu_launch_coop_k(dim3 grid, dim3 block, size_t smem, K kernel, Args... args) {
   ::emu::launch_coop(grid, block, smem, [=]() { kernel(args...); });
 }
-#define GSP_LAUNCH(kernel, grid, block, smem, stream, ...) ::emu::launch_k((grid), (block), (smem), (kernel), __VA_ARGS__)
+#define GSP_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  (::emu::dep_launch((void*)(stream), #kernel), ::emu::launch_k((grid), (block), (smem), (kernel), __VA_ARGS__))
 // persistent kernels whose CTAs wait on each other: the whole grid must be co-resident
-#define GSP_LAUNCH_COOP(kernel, grid, block, smem, stream, ...) ::emu_launch_coop_k((grid), (block), (smem), (kernel), __VA_ARGS__)
+#define GSP_LAUNCH_COOP(kernel, grid, block, smem, stream, ...) \
+  (::emu::dep_launch((void*)(stream), #kernel), ::emu_launch_coop_k((grid), (block), (smem), (kernel), __VA_ARGS__))

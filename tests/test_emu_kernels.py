@@ -343,11 +343,19 @@ def test_multi_device_block_cyclic_cholesky(emu_lib):
             plan.close(); lib.close()
         print("OK")
     """) % (root, os.path.join(root, "oracle"), os.path.join(root, "tests"), emu_lib.path)
-    env = dict(os.environ, GSP_CHOL_DIST_MIN_BLOCKS="2", GSP_CHOL_PB="1")
+    # GSP_DEPCHECK=1: the emulator records every launch with the blocks it reads / writes and the order its stream, the events it
+    # waited on and host synchronisations give it; a pair of conflicting launches without a happens-before path fails the plan
+    # (the sequential emulator would compute the right numbers even with a missing cudaStreamWaitEvent - the GPU would not)
+    env = dict(os.environ, GSP_CHOL_DIST_MIN_BLOCKS="2", GSP_CHOL_PB="1", GSP_DEPCHECK="1")
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=900)
     assert out.returncode == 0 and "OK" in out.stdout, out.stderr[-1500:]
+    assert "0 unordered conflicting pairs" in out.stderr
+    # ... and the checker does see a race: with the assembly -> aux / update stream dependency dropped (the bug of an early version
+    # of the distributed factorization, found on 2 GPUs) the plan is refused
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(env, GSP_DEPCHECK_SELFTEST="1"), timeout=900)
+    assert out.returncode != 0 and "unordered assemble_kernel" in out.stderr
     # panels of 2 blocks on 2 devices: the fused diagonal-square kernel (strips + flags), push_square / push_rect, near / far updates
-    env = dict(os.environ, GSP_CHOL_DIST_MIN_BLOCKS="2", GSP_CHOL_PB="2")
+    env = dict(os.environ, GSP_CHOL_DIST_MIN_BLOCKS="2", GSP_CHOL_PB="2", GSP_DEPCHECK="1")
     out = subprocess.run([sys.executable, "-c", code.replace("[0, 0, 0]", "[0, 0]").replace("(20, 18)", "(24, 21)").replace("360", "504")],
                          capture_output=True, text=True, env=env, timeout=900)
     assert out.returncode == 0 and "OK" in out.stdout, out.stderr[-1500:]

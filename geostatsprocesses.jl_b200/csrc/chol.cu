@@ -890,10 +890,6 @@ cudaError_t chol_factor_dist(const std::vector<DistDev>& devs, long long ld, int
   for (cudaEvent_t ev : evs) cudaEventDestroy(ev);
   for (auto& c : ch)
     for (cudaEvent_t ev : c.events) cudaEventDestroy(ev);
-#ifdef GSP_EMU
-  // test-only: every pair of launches touching the same blocks (one of them writing) must be ordered by streams / events
-  if (emu::dep_enabled() && emu::dep_check(1) != 0 && err == cudaSuccess) err = cudaErrorInvalidValue;
-#endif
   return err;
 }
 

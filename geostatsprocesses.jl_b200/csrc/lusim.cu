@@ -138,6 +138,8 @@ int stage_noise(gsp_ctx* ctx, gsp_lu_plan* p, LuDev* d, double* Wp, const double
                 unsigned long long seed, unsigned stream, long long real0) {
   cudaStream_t st = d->dc->stream;
   if (src) {
+    GSP_DEP_ACCESS(src, 0, 1, 0, 1, false);
+    GSP_DEP_ACCESS(Wp, 0, 1, 0, 1, true);
     ProfScope prof_("pad_transpose", st);
     GSP_LAUNCH(pad_transpose_kernel, dim3((unsigned)(p->Nsp / 32), (unsigned)(cpad / 32)), dim3(256), 0, st, Wp, cpad, p->Nsp, cpad, src, lds, p->Ns,
                cols);
@@ -162,15 +164,20 @@ int sample_core(gsp_ctx* ctx, gsp_lu_plan* p, LuDev* d, long long cols, const do
     double* W1p = d->W1p.as<double>();
     GSP_TRY(stage_noise(ctx, p, d, W1p, W1, ldw, cols, cpad, seed, 0u, real0));
     const long long n = p->Nsp * cpad;
+    GSP_DEP_ACCESS(W1p, 0, 1, 0, 1, false);
+    GSP_DEP_ACCESS(Wp, 0, 1, 0, 1, true);
     GSP_LAUNCH(premix_kernel, dim3(grid_for(n, d->dc->sms)), dim3(256), 0, st, Wp, (const double*)W1p, n, rho, std::sqrt(1.0 - rho * rho));
     g_launches++;
     GSP_CUDA_OK(ctx, cudaGetLastError());
   }
   const double* L22 = d->A->as<double>() + p->Ndp * (p->Np + 1);
   const double addmu = (p->Nd == 0) ? p->mu : 0.0;  // lusim.jl:172
+  GSP_DEP_ACCESS(Wp, 0, 1, 0, 1, false);
+  GSP_DEP_ACCESS(Z, 0, 1, 0, 1, true);
   GSP_CUDA_OK(ctx, sample_gemm(st, L22, p->Np, (int)(p->Nsp / 128), Wp, cpad, (int)(cpad / 128), Z, ldz, d->d2.as<double>(),
                                d->sinds.as<long long>(), addmu, p->Ns, cols));
   if (p->Nd > 0) {
+    GSP_DEP_ACCESS(Z, 0, 1, 0, 1, true);
     GSP_LAUNCH(scatter_data_kernel, dim3(grid_for(p->Nd * cols, d->dc->sms)), dim3(256), 0, st, Z, ldz, (const long long*)d->dinds.as<long long>(),
                (const double*)d->z1.as<double>(), p->Nd, cols);
     g_launches++;
@@ -406,6 +413,15 @@ extern "C" int gsp_lu_plan_create(gsp_ctx* ctx, const gsp_cov_model* cov, const 
     GSP_CUDA_OK(ctx, chol_factor(st, dc.side, DevCtx::kSide, d0->A->as<double>(), p->Np, nb, d0->invD->as<double>(), d0->info.as<int>()));
   }
   GSP_CUDA_OK(ctx, cudaEventRecord(tev.ev[2], st));
+#ifdef GSP_EMU
+  // test-only (GSP_DEPCHECK=1): every pair of launches of the assembly + factorization that touch the same blocks, one of them writing,
+  // must be ordered by streams / events - for the panel algorithm on G devices and for the recursive one with its look-ahead streams
+  if (emu::dep_enabled()) {
+    const long long bad = emu::dep_check(1);
+    emu::dep_enable(false);
+    if (bad != 0) return set_err(ctx, GSP_E_STATE, "stream-dependency check failed: " + std::to_string(bad) + " unordered conflicting launch pairs");
+  }
+#endif
   GSP_TRY(compute_d2(ctx, p, z1));
   GSP_CUDA_OK(ctx, cudaEventRecord(tev.ev[3], st));
   int info = 0;
@@ -624,6 +640,12 @@ int lu_sample_impl(gsp_lu_plan* p, int64_t R, const double* W, uint64_t seed, in
     pipe_on = (env && env[0] == '0') ? 0 : 1;
   }
   const bool piped = pipe_on && !ens && maxshard > chunk;
+#ifdef GSP_EMU
+  {  // test-only: record the H2D / compute / D2H stream graph of this call and check it at the end
+    const char* env = getenv("GSP_DEPCHECK");
+    emu::dep_enable(env && env[0] == '1');
+  }
+#endif
   for (int i = 0; i < ndev; ++i) {
     cudaSetDevice(p->dev[i]->dc->dev);
     GSP_TRY(ensure_chunk(ctx, p, p->dev[i].get(), chunk, mix, piped));
@@ -659,9 +681,11 @@ int lu_sample_impl(gsp_lu_plan* p, int64_t R, const double* W, uint64_t seed, in
       if (W) {
         // the slot's noise buffer is free once the compute of the chunk that used it two steps ago has run
         if (piped && ci >= 2 && !cuda_ok(cudaStreamWaitEvent(sin, d->ev_comp[slot], 0))) break;
+        GSP_DEP_ACCESS(wraw.p, 0, 1, 0, 1, true);
         if (!cuda_ok(cudaMemcpyAsync(wraw.p, W + ra * p->Ns, (size_t)p->Ns * cols * sizeof(double), cudaMemcpyHostToDevice, sin))) break;
         Wd = wraw.as<double>();
         if (mix) {
+          GSP_DEP_ACCESS(w1raw.p, 0, 1, 0, 1, true);
           if (!cuda_ok(cudaMemcpyAsync(w1raw.p, W1 + ra * p->Ns, (size_t)p->Ns * cols * sizeof(double), cudaMemcpyHostToDevice, sin))) break;
           W1d = w1raw.as<double>();
         }
@@ -686,6 +710,7 @@ int lu_sample_impl(gsp_lu_plan* p, int64_t R, const double* W, uint64_t seed, in
       cudaStream_t sout = piped ? d->dc->d2h : d->dc->stream;
       if (piped && !cuda_ok(cudaStreamWaitEvent(sout, d->ev_comp[slot], 0))) break;
       const double* Zs = slot ? d->Zc2.as<double>() : d->Zc.as<double>();
+      GSP_DEP_ACCESS(Zs, 0, 1, 0, 1, false);
       if (!cuda_ok(cudaMemcpyAsync(Z + ra * p->N, Zs, (size_t)p->N * cols * sizeof(double), cudaMemcpyDeviceToHost, sout))) break;
       if (piped) cuda_ok(cudaEventRecord(d->ev_out[slot], sout));
     }
@@ -716,6 +741,14 @@ int lu_sample_impl(gsp_lu_plan* p, int64_t R, const double* W, uint64_t seed, in
     cudaEventElapsedTime(&ms, p->dev[0]->ev0, p->dev[0]->ev1);
     ctx->last_sample_ms = ms;
   }
+#ifdef GSP_EMU
+  if (emu::dep_enabled()) {
+    const long long bad = emu::dep_check(1);
+    emu::dep_enable(false);
+    if (bad != 0 && rc == GSP_OK)
+      rc = set_err(ctx, GSP_E_STATE, "stream-dependency check failed: " + std::to_string(bad) + " unordered conflicting launch pairs");
+  }
+#endif
   return rc;
 }
 

@@ -74,12 +74,12 @@ static inline cudaError_t cudaFreeAsync(void* p, cudaStream_t) { return cudaFree
 static inline cudaError_t cudaMallocHost(void** p, size_t n) { return cudaMalloc(p, n); }
 static inline cudaError_t cudaFreeHost(void* p) { std::free(p); return cudaSuccess; }
 static inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { std::memmove(d, s, n); return cudaSuccess; }
-static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t = 0) { std::memmove(d, s, n); return cudaSuccess; }
+static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t st = 0) { ::emu::dep_launch((void*)st, "memcpy"); std::memmove(d, s, n); return cudaSuccess; }
 static inline cudaError_t cudaMemcpy2DAsync(void* d, size_t dp, const void* s, size_t sp, size_t w, size_t h, cudaMemcpyKind, cudaStream_t = 0) {
   for (size_t r = 0; r < h; ++r) std::memmove((char*)d + r * dp, (const char*)s + r * sp, w);
   return cudaSuccess;
 }
-static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t = 0) { std::memset(d, v, n); return cudaSuccess; }
+static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t st = 0) { ::emu::dep_launch((void*)st, "memset"); std::memset(d, v, n); return cudaSuccess; }
 static inline cudaError_t cudaMemset(void* d, int v, size_t n) { std::memset(d, v, n); return cudaSuccess; }
 static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = (cudaStream_t)::emu::dep_new_stream(); return cudaSuccess; }
 static inline cudaError_t cudaStreamCreate(cudaStream_t* s) { *s = (cudaStream_t)::emu::dep_new_stream(); return cudaSuccess; }
@@ -105,7 +105,7 @@ enum { cudaDevAttrMultiProcessorCount = 16 };
 static inline cudaError_t cudaDeviceGetAttribute(int* v, int, int) { *v = 4; return cudaSuccess; }
 static inline cudaError_t cudaDeviceCanAccessPeer(int* can, int, int) { *can = 0; return cudaSuccess; }
 static inline cudaError_t cudaDeviceEnablePeerAccess(int, unsigned) { return cudaSuccess; }
-static inline cudaError_t cudaMemcpyPeerAsync(void* d, int, const void* s, int, size_t n, cudaStream_t = 0) { std::memmove(d, s, n); return cudaSuccess; }
+static inline cudaError_t cudaMemcpyPeerAsync(void* d, int, const void* s, int, size_t n, cudaStream_t st = 0) { ::emu::dep_launch((void*)st, "memcpy_peer"); std::memmove(d, s, n); return cudaSuccess; }
 static inline cudaError_t cudaHostRegister(void*, size_t, unsigned) { return cudaSuccess; }
 static inline cudaError_t cudaHostUnregister(void*) { return cudaSuccess; }
 

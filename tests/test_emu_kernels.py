@@ -439,3 +439,33 @@ def test_lusim_shared_factor_plan(emu_lib):
     a = gsp.rand(proc, grid, 2, rng=np.random.default_rng(5), method=gsp.LUSIM(library=emu_lib))
     b = gsp.rand(proc, grid, 2, rng=np.random.default_rng(5), method=gsp.LUSIM(library=emu_lib, share_factor=False))
     assert np.array_equal(a[1].field2, b[1].field2) and np.array_equal(a[0].field1, b[0].field1)
+
+
+def test_lusim_host_pipeline_dependencies(emu_lib):
+    """gsp_lu_sample with several chunks per device: H2D / GEMM / D2H of consecutive chunks overlap on three streams with two buffer
+    slots.  Under GSP_DEPCHECK=1 the emulator checks that every pair of conflicting operations (copy into a noise slot vs the transpose
+    reading it, GEMM writing a field slot vs the copy-out reading it, ...) is ordered by the recorded streams / events - and the fields
+    equal the oracle's, rho-mixing included, on one and on two (aliased) devices."""
+    import os, subprocess, sys, textwrap
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = textwrap.dedent("""
+        import sys, numpy as np
+        sys.path.insert(0, %r); sys.path.insert(0, %r); sys.path.insert(0, %r)
+        import gsp_b200 as gsp, gsp_oracle as O
+        from helpers import iso, ostructs, relerr
+        for devs, R in (([0], 1300), ([0, 0], 2300)):
+            lib = gsp.Library(%r, devices=devs)
+            rng = np.random.default_rng(9)
+            dims = (12, 10); st = iso(O.SPHERICAL, 1.0, 4.0, 2)
+            dinds = np.sort(rng.choice(120, 10, replace=False)); z1 = rng.standard_normal(10)
+            plan = gsp.LUPlan(lib, st, (gsp._lib.make_grid_domain(dims, [0, 0], [1, 1]), None), dinds + 1, z1, 0.0)
+            pre = O.lusim_preprocess(ostructs(st), O.grid_centroids(dims, [0, 0], [1, 1]), dinds, z1, 0.0)
+            W = rng.standard_normal((plan.Ns, R)); W1 = rng.standard_normal((plan.Ns, R))
+            assert relerr(plan.sample(R, W), O.lusim_sample(pre, W)) < 1e-12
+            assert relerr(plan.sample(R, W, rho=0.6, W1=W1), O.lusim_sample(pre, W, 0.6, W1)) < 1e-12
+            plan.close(); lib.close()
+        print("OK")
+    """) % (root, os.path.join(root, "oracle"), os.path.join(root, "tests"), emu_lib.path)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, GSP_DEPCHECK="1"), timeout=900)
+    assert out.returncode == 0 and "OK" in out.stdout, out.stderr[-1500:]
+    assert "DEPCHECK" in out.stderr and "unordered" not in out.stderr.replace("0 unordered conflicting pairs", "")

@@ -445,7 +445,7 @@ def test_lusim_host_pipeline_dependencies(emu_lib):
     """gsp_lu_sample with several chunks per device: H2D / GEMM / D2H of consecutive chunks overlap on three streams with two buffer
     slots.  Under GSP_DEPCHECK=1 the emulator checks that every pair of conflicting operations (copy into a noise slot vs the transpose
     reading it, GEMM writing a field slot vs the copy-out reading it, ...) is ordered by the recorded streams / events - and the fields
-    equal the oracle's, rho-mixing included, on one and on two (aliased) devices."""
+    equal the oracle's, rho-mixing included (3 chunks of <= 512 realizations: both slots are reused)."""
     import os, subprocess, sys, textwrap
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     code = textwrap.dedent("""
@@ -453,7 +453,7 @@ def test_lusim_host_pipeline_dependencies(emu_lib):
         sys.path.insert(0, %r); sys.path.insert(0, %r); sys.path.insert(0, %r)
         import gsp_b200 as gsp, gsp_oracle as O
         from helpers import iso, ostructs, relerr
-        for devs, R in (([0], 1300), ([0, 0], 2300)):
+        for devs, R in (([0], 1030),):
             lib = gsp.Library(%r, devices=devs)
             rng = np.random.default_rng(9)
             dims = (12, 10); st = iso(O.SPHERICAL, 1.0, 4.0, 2)

@@ -1195,7 +1195,12 @@ int sample_on_device(gsp_fft_plan* p, FftDev* d, long long R, const double* w, u
                      DevBuf* scratch_z) {
   gsp_ctx* ctx = p->ctx;
   const double s = fold_scale(p, sill);
-  const long long rb = p->rb;  // realizations per batch (1 for 3-D grids)
+  long long rb = p->rb;  // realizations per batch (1-D / 2-D grids: one launch per pass for the batch; 3-D: concurrent lanes)
+  // 3-D grids writing whole fields from a noise array (or the fused RNG) need no per-batch scratch: ALL R realizations go to the
+  // lanes in one round-robin, each lane streams through its realizations and the lanes join the compute stream once at the end,
+  // instead of a fork / join every `rb` realizations (GSP_FFT_STREAM=0: the batched fork / join, for A/B runs)
+  static const bool stream_all = !(getenv("GSP_FFT_STREAM") && getenv("GSP_FFT_STREAM")[0] == '0');
+  if (stream_all && p->ndim == 3 && n_inds == 0 && (w || (d->ax[0].fast && !d->fused_xy && fused_rng_enabled()))) rb = std::max<long long>(R, 1);
   for (long long r = 0; r < R; r += rb) {
     const long long nb = (R - r < rb) ? R - r : rb;
     const double* wr;
